@@ -1,0 +1,213 @@
+/*
+ * rc_b200.h — C ABI of librc_b200.so: the B200-native radiance-cascade GI path.
+ *
+ * This is the drop-in boundary.  Each entry point names the
+ * reference interface it stands in for (paths relative to the reference
+ * repository jw910731/RadianceCascade).  The reference has NO cascade / ray
+ * march / merge / gather code; the GI stages behind this ABI
+ * implement the builder-owned specification in include/rc_spec.h, while the
+ * scene ingest, camera, material and direct-lighting inputs follow the
+ * reference's source.
+ *
+ * Conventions: plain C, no torch / CUDA types in signatures (the stream is an
+ * opaque void* holding a cudaStream_t, NULL = the context's own stream).
+ * All entry points return rc_status and never abort across the ABI; a
+ * human-readable message for the last failure of a context is available from
+ * rc_last_error().  One context = one GPU = one owning host thread; per frame
+ * the call order is rc_update -> rc_render -> rc_read_target, mirroring
+ * App::handle_redraw (src/window/app.rs:221-267).
+ */
+#ifndef RC_B200_H
+#define RC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_ABI_VERSION 1u
+
+typedef int32_t rc_status;
+enum {
+    RC_OK = 0,
+    RC_ERR_INVALID_ARG = 1,
+    RC_ERR_SCENE_LOAD = 2,   /* ≙ the .unwrap() panic at src/renderer.rs:176 */
+    RC_ERR_CUDA = 3,
+    RC_ERR_NO_DEVICE = 4,    /* no CUDA device: there is NO CPU fallback */
+    RC_ERR_BUFFER_SIZE = 5,
+    RC_ERR_STATE = 6
+};
+
+/* rc_config.flags */
+#define RC_CFG_SEPARATE_MERGE 0x1u /* run march and merge as separate kernels (debug / A-B) instead of the fused path */
+#define RC_CFG_NO_TEXTURES    0x2u /* ignore map_Kd / map_Bump (as if the files were missing, src/primitives.rs:390-404) */
+#define RC_CFG_HALO_EXCHANGE  0x4u /* tile mode: upper-level halo probes are supplied by rc_halo_import instead of recomputed */
+
+/* rc_update flags.  bit0 ≙ AppState::enable_normal_map (src/app.rs:18, src/renderer.rs:620-631) */
+#define RC_UPD_ENABLE_NORMAL_MAP 0x1u
+
+typedef struct rc_ctx rc_ctx;
+
+/* ≙ arguments of DefaultRenderer::new(device, config, queue, state, path)
+ * (src/renderer.rs:168-174): surface size, scene path; plus the cascade
+ * parameters of include/rc_spec.h and the CUDA device ordinal.  Zero means
+ * "default" for every cascade field. */
+typedef struct rc_config {
+    uint32_t struct_size;    /* = sizeof(rc_config) */
+    uint32_t width, height;  /* full frame in pixels (≙ SurfaceConfiguration) */
+    int32_t  device;         /* CUDA ordinal */
+    const char* scene_path;  /* .obj file (≙ `path`, joined onto resource_root when relative) */
+    const char* resource_root; /* ≙ RESOURCE_PATH (src/primitives.rs:12); may be NULL */
+    uint32_t probe_spacing0; /* P0, pixels, default 4 */
+    uint32_t dir_res0;       /* D0, directions per axis at level 0, default 4 */
+    uint32_t num_levels;     /* N, default 6 */
+    float    interval0;      /* L0 world units; <= 0: bbox_diag/256 */
+    float    t_far;          /* end of the top interval; <= 0: 4*bbox_diag */
+    float    normal_offset;  /* probe lift along the geometric normal; <= 0: 1e-3*L0... see rc_spec.h */
+    float    sky[3];         /* radiance of a top-level miss, default 0 */
+    uint32_t flags;          /* RC_CFG_* */
+    /* Screen-space tile rendered by this context (multi-GPU).
+     * tile_w == 0 or tile_h == 0 means the full frame. */
+    uint32_t tile_x0, tile_y0, tile_w, tile_h;
+} rc_config;
+
+/* Same 80-byte layout as UniformCamera (src/camera.rs:9-15): column-major
+ * proj*view matrix, then (eye, 1). */
+typedef struct rc_camera {
+    float view_proj[16];
+    float eye[4];
+} rc_camera;
+
+/* Same 16-byte layout as UniformLight (src/primitives.rs:14-18). */
+typedef struct rc_light {
+    float position[4];
+} rc_light;
+
+typedef enum rc_target {
+    RC_TARGET_IRRADIANCE = 0, /* float16 RGBA  [tile_h][tile_w][4]  linear HDR irradiance E, a = 1 where geometry */
+    RC_TARGET_DIRECT     = 1, /* float16 RGBA  [tile_h][tile_w][4]  fs_main output (linear), a = 1 where geometry */
+    RC_TARGET_DEPTH      = 2, /* float32       [tile_h][tile_w]     primary-ray distance, < 0 where no geometry */
+    RC_TARGET_NORMAL     = 3, /* uint32        [tile_h][tile_w]     shading normal, 2 x snorm16 equal-area octahedral */
+    RC_TARGET_ALBEDO     = 4, /* float16 RGBA  [tile_h][tile_w][4]  linear albedo (`color` of fs_main) */
+    RC_TARGET_PRIM       = 5, /* uint32        [tile_h][tile_w]     global triangle id, 0xffffffff where no geometry */
+    RC_TARGET_COMPOSITE  = 6, /* uint8 BGRA    [tile_h][tile_w][4]  sRGB-encoded albedo*E/pi + direct (Bgra8UnormSrgb, src/window/app.rs:59-75) */
+    RC_TARGET_DIRECT_SRGB8 = 7, /* uint8 BGRA  [tile_h][tile_w][4]  what the reference presents: sRGB_encode(fs_main) */
+    RC_TARGET_CASCADE0   = 16 /* + level i: float16 RGBA, merged cascade level i, layout in rc_spec.h */
+} rc_target;
+
+/* Integer layout of one cascade level, as used by the kernels (must be
+ * bit-exact with the oracle's tables). */
+typedef struct rc_level_info {
+    uint32_t spacing;      /* P_i */
+    uint32_t dir_res;      /* D_i */
+    uint32_t grid_w, grid_h;     /* probes of the full frame at this level */
+    int32_t  px0, py0;     /* first probe column / row held by this context */
+    uint32_t sub_w, sub_h; /* probes held by this context (== grid for a full frame) */
+    uint64_t texel_offset; /* first texel of the level in the cascade buffer */
+    uint64_t texel_count;  /* sub_w*sub_h*dir_res^2 */
+    float    t_begin, t_end;
+} rc_level_info;
+
+typedef struct rc_scene_info {
+    uint32_t num_models, num_vertices, num_triangles, num_materials, num_textures;
+    uint32_t bvh_nodes, light_from_obj; /* light_from_obj ≙ AppState::given_light_position */
+    float    bbox_min[3], bbox_max[3];
+    float    obj_light[3];
+} rc_scene_info;
+
+/* Stage indices for rc_stage_times. */
+enum { RC_STAGE_GBUFFER = 0, RC_STAGE_PROBES = 1, RC_STAGE_MARCH = 2, RC_STAGE_MERGE = 3,
+       RC_STAGE_GATHER = 4, RC_STAGE_FRAME = 5, RC_STAGE_COUNT = 6 };
+
+/* ≙ DefaultRenderer::new (src/renderer.rs:168-555): loads the scene
+ * (ObjScene::load, src/primitives.rs:122-175), builds vertex streams, materials,
+ * textures, the BVH, and sizes every device buffer.  Fails with
+ * RC_ERR_NO_DEVICE when no CUDA device is present. */
+rc_status rc_create(const rc_config* cfg, rc_ctx** out);
+
+/* ≙ the per-frame host->device writes: queue.write_buffer(camera_buffer,
+ * UniformCamera) and queue.write_buffer(light_buffer, UniformLight)
+ * (src/window/app.rs:112-130) followed by RenderStage::update
+ * (src/renderer.rs:620-631).  The reference supports one light; n_lights > 1
+ * sums the diffuse and specular terms over lights. */
+rc_status rc_update(rc_ctx* ctx, const rc_camera* cam, const rc_light* lights,
+                    uint32_t n_lights, uint32_t flags);
+
+/* ≙ RenderStage::resize (src/renderer.rs:615-618) + Projection::resize. */
+rc_status rc_resize(rc_ctx* ctx, uint32_t width, uint32_t height);
+
+/* ≙ RenderStage::render (src/renderer.rs:559-613): enqueues the frame on
+ * `stream` (a cudaStream_t, NULL = context stream); does not synchronise and
+ * does not allocate.  Stages: G-buffer, probe placement, per-level march
+ * (+merge), gather. */
+rc_status rc_render(rc_ctx* ctx, void* stream);
+
+/* Waits for the last rc_render and copies a target into host memory
+ * (≙ reading back the colour attachment the caller owns). */
+rc_status rc_read_target(rc_ctx* ctx, rc_target which, void* host_dst, size_t bytes);
+/* Size in bytes rc_read_target needs for `which`. */
+rc_status rc_target_bytes(rc_ctx* ctx, rc_target which, size_t* bytes);
+
+/* CUDA-event time of each stage of the last rendered frame, in ms. */
+rc_status rc_stage_times(rc_ctx* ctx, float* ms, uint32_t n);
+/* Number of kernels rc_render launches per frame. */
+rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
+
+rc_status rc_get_levels(rc_ctx* ctx, rc_level_info* out, uint32_t max_levels, uint32_t* num_levels);
+rc_status rc_get_scene_info(rc_ctx* ctx, rc_scene_info* out);
+/* Direction table of a level: float[dir_res*dir_res][3], row-major (dy, dx). */
+rc_status rc_get_directions(rc_ctx* ctx, uint32_t level, float* out, size_t bytes);
+
+/* ≙ the 17-float interleaved vertex buffer (src/renderer.rs:371-410) and the
+ * winding-reversed index buffer (src/primitives.rs:369-376) of model `m`.
+ * Pass NULL buffers to query counts. */
+rc_status rc_get_model_stream(rc_ctx* ctx, uint32_t model, float* vertices, size_t vbytes,
+                              uint32_t* indices, size_t ibytes,
+                              uint32_t* num_vertices, uint32_t* num_indices);
+/* ≙ UniformMaterial (64 bytes, src/primitives.rs:37-73) followed by enable_bit
+ * (u32) and emission Ke (3 floats, GI only): 20 x 4 bytes. */
+rc_status rc_get_model_material(rc_ctx* ctx, uint32_t model, void* out80, size_t bytes);
+
+/* Debug / parity entry: closest-hit query of arbitrary rays against the
+ * context's BVH.  rays: float[n][8] = origin xyz, tmin, dir xyz, tmax.
+ * hits: float[n][4] = t (<0 miss), u, v, prim id as float bits. */
+rc_status rc_trace_rays(rc_ctx* ctx, const float* rays, uint32_t n, float* hits);
+/* Debug / parity entry: fs_main (src/shader.wgsl:76-100) evaluated on the GPU at
+ * hit points.  in: float[n][8] = prim id bits, u, v, pad, view-origin xyz, pad. out: float[n][4]. */
+rc_status rc_shade_points(rc_ctx* ctx, const float* in, uint32_t n, float* out);
+
+/* Multi-GPU halo exchange (RC_CFG_HALO_EXCHANGE): device pointer + geometry of the
+ * merged level so a peer (NCCL send/recv or P2P) can fill the halo ring. */
+rc_status rc_cascade_device_ptr(rc_ctx* ctx, uint32_t level, void** dev_ptr, size_t* bytes);
+rc_status rc_irradiance_device_ptr(rc_ctx* ctx, void** dev_ptr, size_t* bytes);
+/* Split rc_render for halo exchange: levels are processed top-down; after
+ * rc_render_level(i) the caller exchanges level i's border ring, then calls
+ * rc_render_level(i-1); rc_render_begin does G-buffer + probes, rc_render_end the gather. */
+rc_status rc_render_begin(rc_ctx* ctx, void* stream);
+rc_status rc_render_level(rc_ctx* ctx, uint32_t level, void* stream);
+rc_status rc_render_end(rc_ctx* ctx, void* stream);
+
+rc_status rc_synchronize(rc_ctx* ctx);
+void rc_destroy(rc_ctx* ctx);
+const char* rc_last_error(const rc_ctx* ctx); /* ctx may be NULL: last rc_create failure */
+uint32_t rc_abi_version(void);
+
+/* Host-side façade keeping the reference's camera math callable from C
+ * (glam conventions). */
+/* ≙ Camera::calc_matrix (src/camera.rs:43-52). out16 column-major. */
+void rc_camera_view_matrix(const float position[3], float yaw, float pitch, float out16[16]);
+/* ≙ Projection::calc_matrix (src/camera.rs:77-79); fovy in radians. */
+void rc_projection_matrix(float fovy, float aspect, float znear, float zfar, float out16[16]);
+/* ≙ UniformCamera::from_camera_project (src/camera.rs:17-22). */
+void rc_uniform_camera(const float position[3], float yaw, float pitch,
+                       float fovy, float aspect, float znear, float zfar, rc_camera* out);
+/* look-at helper for synthetic orbit paths: same look_to_rh arithmetic with dir = normalize(target - position). */
+void rc_uniform_camera_look_at(const float position[3], const float target[3],
+                               float fovy, float aspect, float znear, float zfar, rc_camera* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RC_B200_H */
