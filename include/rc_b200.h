@@ -157,6 +157,10 @@ rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
 
 rc_status rc_get_levels(rc_ctx* ctx, rc_level_info* out, uint32_t max_levels, uint32_t* num_levels);
 rc_status rc_get_scene_info(rc_ctx* ctx, rc_scene_info* out);
+/* The tile this context renders: x0, y0, w, h in full-frame pixels. */
+rc_status rc_get_tile(rc_ctx* ctx, uint32_t xywh[4]);
+/* The cascade intervals actually in use: L0, t_far, probe normal offset. */
+rc_status rc_get_intervals(rc_ctx* ctx, float out3[3]);
 /* Direction table of a level: float[dir_res*dir_res][3], row-major (dy, dx). */
 rc_status rc_get_directions(rc_ctx* ctx, uint32_t level, float* out, size_t bytes);
 
@@ -188,6 +192,22 @@ rc_status rc_irradiance_device_ptr(rc_ctx* ctx, void** dev_ptr, size_t* bytes);
 rc_status rc_render_begin(rc_ctx* ctx, void* stream);
 rc_status rc_render_level(rc_ctx* ctx, uint32_t level, void* stream);
 rc_status rc_render_end(rc_ctx* ctx, void* stream);
+
+/* Device-free scene ingest: the CPU part of ObjScene::load (src/primitives.rs:122-175)
+ * and of DefaultRenderer::new's mesh preparation (src/renderer.rs:370-497) — tobj-style
+ * loading, winding reversal, TBN, 17-float vertex stream, UniformMaterial, enable_bit,
+ * texture decode.  Needs no GPU; rc_create runs exactly this and then uploads. */
+typedef struct rc_scene rc_scene;
+rc_status rc_scene_load(const char* obj_path, uint32_t flags /* RC_CFG_NO_TEXTURES */, rc_scene** out);
+void rc_scene_free(rc_scene* scene);
+rc_status rc_scene_get_info(const rc_scene* scene, rc_scene_info* out); /* bvh_nodes = 0: no BVH is built here */
+rc_status rc_scene_model_stream(rc_scene* scene, uint32_t model, float* vertices, size_t vbytes,
+                                uint32_t* indices, size_t ibytes, uint32_t* num_vertices, uint32_t* num_indices);
+rc_status rc_scene_model_material(const rc_scene* scene, uint32_t model, void* out80, size_t bytes);
+rc_status rc_scene_model_name(const rc_scene* scene, uint32_t model, char* out, size_t bytes);
+/* which: 0 colour map (map_Kd), 1 normal map (map_Bump); width = height = 0 when the model has none */
+rc_status rc_scene_model_texture(const rc_scene* scene, uint32_t model, uint32_t which, uint8_t* rgba, size_t bytes,
+                                 uint32_t* width, uint32_t* height);
 
 rc_status rc_synchronize(rc_ctx* ctx);
 void rc_destroy(rc_ctx* ctx);

@@ -62,6 +62,8 @@
  *   s = o - v0; u = dot(s,p)*inv; reject unless 0 <= u <= 1
  *   q = cross(s,e1); v = dot(dir,q)*inv; reject unless v >= 0 and u+v <= 1
  *   t = dot(e2,q)*inv; accept iff tmin <= t < tmax
+ *   a triangle is skipped entirely when any two of its three vertex positions are
+ *   bitwise-equal floats (the zero-area triangles tobj makes from `l` / `p` elements)
  *   closest hit = minimum (t, global triangle id) lexicographically — independent
  *   of any acceleration structure.  Global triangle id = triangles of model 0,
  *   then model 1, ... in index-buffer order.

@@ -60,6 +60,7 @@ typedef struct {
     const uint32_t* tex_wh;   /* [n_tex][2] */
     /* derived */
     v3 *v0, *e1, *e2;
+    uint8_t* skip;            /* S5: two bitwise-equal vertex positions */
     /* bvh */
     int n_nodes;
     struct onode* nodes;
@@ -135,6 +136,7 @@ rco_scene* rco_scene_create(int n_verts, const float* verts, int n_tris, const u
     s->e2 = (v3*)malloc(sizeof(v3) * (size_t)n_tris);
     g_cent = (float*)malloc(sizeof(float) * 3 * (size_t)n_tris);
     s->order = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_tris);
+    s->skip = (uint8_t*)calloc((size_t)n_tris + 1, 1);
     s->bbmin = V(FLT_MAX, FLT_MAX, FLT_MAX); s->bbmax = V(-FLT_MAX, -FLT_MAX, -FLT_MAX);
     for (int i = 0; i < n_verts; i++) {
         const float* p = verts + 17 * (size_t)i;
@@ -148,6 +150,7 @@ rco_scene* rco_scene_create(int n_verts, const float* verts, int n_tris, const u
         s->v0[t] = V(a[0], a[1], a[2]);
         s->e1[t] = V(b[0] - a[0], b[1] - a[1], b[2] - a[2]);   /* S5: e1 = v1 - v0 */
         s->e2[t] = V(c[0] - a[0], c[1] - a[1], c[2] - a[2]);
+        s->skip[t] = (memcmp(a, b, 12) == 0) || (memcmp(a, c, 12) == 0) || (memcmp(b, c, 12) == 0);
         v3 lo, hi; tri_bounds(s, (uint32_t)t, &lo, &hi);
         g_cent[3 * t + 0] = 0.5f * (lo.x + hi.x); g_cent[3 * t + 1] = 0.5f * (lo.y + hi.y); g_cent[3 * t + 2] = 0.5f * (lo.z + hi.z);
         s->order[t] = (uint32_t)t;
@@ -168,13 +171,14 @@ rco_scene* rco_scene_create(int n_verts, const float* verts, int n_tris, const u
 void rco_scene_destroy(rco_scene* s)
 {
     if (!s) return;
-    free(s->v0); free(s->e1); free(s->e2); free(s->nodes); free(s->order); free(s);
+    free(s->v0); free(s->e1); free(s->e2); free(s->skip); free(s->nodes); free(s->order); free(s);
 }
 
 /* S5: two-sided Moller-Trumbore with the specified operation order. */
 static inline int ray_tri(const rco_scene* s, uint32_t t, v3 o, v3 d, float tmin, float tmax,
                           float* tt, float* uu, float* vv)
 {
+    if (s->skip[t]) return 0;
     v3 e1 = s->e1[t], e2 = s->e2[t];
     v3 p = vcross(d, e2);
     float det = vdot(e1, p);

@@ -1,0 +1,371 @@
+// kernels.cu — hand-written CUDA kernels of the radiance-cascade GI path for sm_100a.
+//
+//   k_gbuffer   primary visibility + fs_main per pixel            (rc_spec.h S4, src/shader.wgsl:76-100)
+//   k_probes    probe placement per cascade level                 (S6)
+//   k_link      per-probe upper-probe slots and bilateral weights (S1, S8)
+//   k_march     per-level interval ray march, optionally fused with the merge from level i+1 (S7, S8)
+//   k_merge     stand-alone merge (A/B against the fused path)    (S8)
+//   k_gather    final irradiance gather                           (S9)
+//
+// Data layout (all in HBM, sized at rc_create): cascade levels are probe-major
+// RGBA16F texels (8 B) so that one warp marches 32 directions of ONE probe
+// (shared origin -> coherent BVH traversal) and stores 256 contiguous bytes;
+// the merge reads, per lower texel, 4 upper probes x 2 rows x 16 B (two adjacent
+// child directions per 128-bit load).  None of these stages is a dense
+// contraction, so tensor cores / TMEM are not used; the BVH + triangles (< 4 MB)
+// live in L2 (126 MB) and are read through the read-only path.
+#include "kernels.cuh"
+
+namespace rc {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ uint2 ldg_u2(const uint2* p) { return __ldg(p); }
+__device__ __forceinline__ uint4 ldg_u4(const uint4* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------ G-buffer
+__global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out)
+{
+    // 2-D tiles of 32x8 pixels keep a warp's primary rays in one screen row segment
+    const int tx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ty = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (tx >= tile.w || ty >= tile.h) return;
+    const size_t o = (size_t)ty * tile.w + tx;
+    const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
+    const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
+    if (h.prim == 0xffffffffu) {
+        out.depth[o] = -1.0f; out.prim[o] = 0xffffffffu; out.normal[o] = 0u;
+        out.albedo[o] = make_uint2(0u, 0u); out.direct[o] = make_uint2(0u, 0u);
+        return;
+    }
+    const float3 P = vfma(h.t, d, cam.eye);
+    const Shade sh = shade_hit(s, L, h.prim, h.u, h.v, P, vneg(d));
+    out.depth[o] = h.t;
+    out.prim[o] = h.prim;
+    out.normal[o] = oct_encode(sh.n);
+    out.albedo[o] = pack_half4(clamp_rad(sh.albedo.x), clamp_rad(sh.albedo.y), clamp_rad(sh.albedo.z), 1.0f);
+    out.direct[o] = pack_half4(clamp_rad(sh.direct.x), clamp_rad(sh.direct.y), clamp_rad(sh.direct.z), 1.0f);
+}
+
+// ------------------------------------------------------------------ probes (S6)
+__global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel lv, float offset,
+                                                   float4* __restrict__ origin, float4* __restrict__ normal)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= lv.sw * lv.sh) return;
+    const int px = lv.px0 + i % lv.sw, py = lv.py0 + i / lv.sw;
+    const int ax = min(px * lv.P + lv.P / 2, cam.W - 1), ay = min(py * lv.P + lv.P / 2, cam.H - 1);
+    const float3 d = primary_dir(cam, ax, ay);
+    const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
+    if (h.prim == 0xffffffffu) {
+        origin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        normal[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float3 hp = vfma(h.t, d, cam.eye);
+    const float3 e1 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim)), e2 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim + 1));
+    float3 ng = vnormalize(vcross(e1, e2));
+    if (vdot(ng, d) > 0.0f) ng = vneg(ng);
+    const float3 og = vfma(offset, ng, hp);
+    origin[i] = make_float4(og.x, og.y, og.z, 1.0f);
+    normal[i] = make_float4(ng.x, ng.y, ng.z, 0.0f);
+}
+
+// ------------------------------------------------------------------ link (S1 + S8 weights)
+__global__ void __launch_bounds__(kBlock) k_link(DLevel lo, DLevel up, const float4* __restrict__ lo_origin,
+                                                 const float4* __restrict__ lo_normal, const float4* __restrict__ up_origin,
+                                                 uint4* __restrict__ link_idx, float4* __restrict__ link_w)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= lo.sw * lo.sh) return;
+    const int px = lo.px0 + i % lo.sw, py = lo.py0 + i / lo.sw;
+    int x0, x1, y0, y1;
+    float wx0, wx1, wy0, wy1;
+    upper_pair(px, up.gw, x0, x1, wx0, wx1);
+    upper_pair(py, up.gh, y0, y1, wy0, wy1);
+    const uint32_t k0 = (uint32_t)((y0 - up.py0) * up.sw + (x0 - up.px0));
+    const uint32_t k1 = (uint32_t)((y0 - up.py0) * up.sw + (x1 - up.px0));
+    const uint32_t k2 = (uint32_t)((y1 - up.py0) * up.sw + (x0 - up.px0));
+    const uint32_t k3 = (uint32_t)((y1 - up.py0) * up.sw + (x1 - up.px0));
+    const float4 og = lo_origin[i];
+    float4 w = make_float4(-1.f, 0.f, 0.f, 0.f);
+    if (og.w != 0.0f) {
+        const float3 op = xyz(og), np = xyz(lo_normal[i]);
+        const float w0 = (wx0 * wy0) * plane_weight(np, op, __ldg(up_origin + k0));
+        const float w1 = (wx1 * wy0) * plane_weight(np, op, __ldg(up_origin + k1));
+        const float w2 = (wx0 * wy1) * plane_weight(np, op, __ldg(up_origin + k2));
+        const float w3 = (wx1 * wy1) * plane_weight(np, op, __ldg(up_origin + k3));
+        const float S = ((w0 + w1) + w2) + w3;
+        if (S > 0.0f) w = make_float4(w0 / S, w1 / S, w2 / S, w3 / S);
+    }
+    link_idx[i] = make_uint4(k0, k1, k2, k3);
+    link_w[i] = w;
+}
+
+// far-field radiance of lower texel (dx, dy) from the merged upper level (S8)
+__device__ __forceinline__ float4 far_field(const uint2* __restrict__ up_texels, int UD, uint4 li, float4 lw, int dx, int dy)
+{
+    if (lw.x < 0.0f) return make_float4(0.f, 0.f, 0.f, 1.f);
+    float4 far = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t idx[4] = {li.x, li.y, li.z, li.w};
+    const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
+    const size_t UDD = (size_t)UD * UD;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint2* base = up_texels + idx[k] * UDD + (size_t)(2 * dy) * UD + 2 * dx;
+        const uint4 r0 = ldg_u4(reinterpret_cast<const uint4*>(base));        // children (2dx,2dy), (2dx+1,2dy)
+        const uint4 r1 = ldg_u4(reinterpret_cast<const uint4*>(base + UD));   // children (2dx,2dy+1), (2dx+1,2dy+1)
+        const float4 c0 = unpack_half4(make_uint2(r0.x, r0.y)), c1 = unpack_half4(make_uint2(r0.z, r0.w));
+        const float4 c2 = unpack_half4(make_uint2(r1.x, r1.y)), c3 = unpack_half4(make_uint2(r1.z, r1.w));
+        far.x = fmaf(wk[k], 0.25f * (((c0.x + c1.x) + c2.x) + c3.x), far.x);
+        far.y = fmaf(wk[k], 0.25f * (((c0.y + c1.y) + c2.y) + c3.y), far.y);
+        far.z = fmaf(wk[k], 0.25f * (((c0.z + c1.z) + c2.z) + c3.z), far.z);
+        far.w = fmaf(wk[k], 0.25f * (((c0.w + c1.w) + c2.w) + c3.w), far.w);
+    }
+    return far;
+}
+
+// ------------------------------------------------------------------ march (+ fused merge)
+// One thread per texel in storage order: a warp = 32 consecutive directions of one probe
+// (level 0 with D0 = 4: two probes), so origins are shared and stores are one 256-byte segment.
+template <bool FUSED>
+__global__ void __launch_bounds__(kBlock) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky,
+                                                  const float4* __restrict__ origin, const float* __restrict__ dirs,
+                                                  uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
+{
+    const size_t DD = (size_t)lv.D * lv.D;
+    const size_t n = (size_t)lv.sw * lv.sh * DD;
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t probe = (uint32_t)(i / DD), d = (uint32_t)(i - (size_t)probe * DD);
+    const float4 og = __ldg(origin + probe);
+    if (og.w == 0.0f) { texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f); return; }   // invalid probe (S7)
+    const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+    const float3 o = xyz(og);
+    const Hit h = trace(s, o, w, lv.t0, lv.t1);
+    float4 c;
+    if (h.prim != 0xffffffffu) {
+        const float3 P = vfma(h.t, w, o);
+        const Shade sh = shade_hit(s, L, h.prim, h.u, h.v, P, vneg(w));
+        c = make_float4(sh.rad.x, sh.rad.y, sh.rad.z, 0.0f);
+    } else if (top) {
+        c = make_float4(sky.x, sky.y, sky.z, 1.0f);
+    } else {
+        c = make_float4(0.f, 0.f, 0.f, 1.0f);
+    }
+    if (FUSED && !top) {
+        // S8 applied to the float16-rounded raw texel (the same value the unfused path reads back)
+        const float4 raw = unpack_half4(pack_half4(c.x, c.y, c.z, c.w));
+        if (raw.w != 0.0f) {
+            const int dx = (int)(d % (uint32_t)lv.D), dy = (int)(d / (uint32_t)lv.D);
+            const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy);
+            c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
+            c.x = fminf(c.x, 65504.0f); c.y = fminf(c.y, 65504.0f); c.z = fminf(c.z, 65504.0f);
+        } else {
+            c = raw;   // a = 0: fma(0, far, raw) = raw exactly, the far field cannot contribute
+        }
+    }
+    texels[i] = pack_half4(c.x, c.y, c.z, c.w);
+}
+
+// ------------------------------------------------------------------ stand-alone merge (in place)
+__global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, const float4* __restrict__ origin,
+                                                  uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
+{
+    const size_t DD = (size_t)lv.D * lv.D;
+    const size_t n = (size_t)lv.sw * lv.sh * DD;
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t probe = (uint32_t)(i / DD), d = (uint32_t)(i - (size_t)probe * DD);
+    if (__ldg(origin + probe).w == 0.0f) return;
+    const float4 raw = unpack_half4(texels[i]);
+    const int dx = (int)(d % (uint32_t)lv.D), dy = (int)(d / (uint32_t)lv.D);
+    const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy);
+    float4 c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
+    texels[i] = pack_half4(fminf(c.x, 65504.0f), fminf(c.y, 65504.0f), fminf(c.z, 65504.0f), c.w);
+}
+
+// ------------------------------------------------------------------ gather (S9)
+__device__ __forceinline__ void gather_axis(int coord, int P, int gmax, int& i0, int& i1, float& w0, float& w1)
+{
+    const int s = coord - P / 2;
+    const int base = (s >= 0) ? s / P : -((-s + P - 1) / P);
+    const float f = (float)(s - base * P) / (float)P;
+    i0 = min(max(base, 0), gmax - 1);
+    i1 = min(max(base + 1, 0), gmax - 1);
+    w0 = 1.0f - f; w1 = f;
+}
+
+__global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileRect tile, const float4* __restrict__ origin0,
+                                                   const uint2* __restrict__ texels0, const float* __restrict__ dirs0,
+                                                   const float* __restrict__ depth, const uint32_t* __restrict__ normal,
+                                                   uint2* __restrict__ out)
+{
+    extern __shared__ float s_dirs[];   // D0*D0*3 floats
+    const int DD = l0.D * l0.D;
+    for (int k = threadIdx.x; k < 3 * DD; k += kBlock) s_dirs[k] = dirs0[k];
+    __syncthreads();
+    const int tx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ty = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (tx >= tile.w || ty >= tile.h) return;
+    const size_t o = (size_t)ty * tile.w + tx;
+    const float dep = depth[o];
+    if (dep < 0.0f) { out[o] = make_uint2(0u, 0u); return; }
+    const int x = tile.x0 + tx, y = tile.y0 + ty;
+    const float3 d = primary_dir(cam, x, y);
+    const float3 hp = vfma(dep, d, cam.eye);
+    const float3 n = oct_decode(normal[o]);
+    int x0, x1, y0, y1;
+    float wx0, wx1, wy0, wy1;
+    gather_axis(x, l0.P, l0.gw, x0, x1, wx0, wx1);
+    gather_axis(y, l0.P, l0.gh, y0, y1, wy0, wy1);
+    const uint32_t pk[4] = {(uint32_t)((y0 - l0.py0) * l0.sw + (x0 - l0.px0)), (uint32_t)((y0 - l0.py0) * l0.sw + (x1 - l0.px0)),
+                            (uint32_t)((y1 - l0.py0) * l0.sw + (x0 - l0.px0)), (uint32_t)((y1 - l0.py0) * l0.sw + (x1 - l0.px0))};
+    float w[4];
+    w[0] = (wx0 * wy0) * plane_weight(n, hp, __ldg(origin0 + pk[0]));
+    w[1] = (wx1 * wy0) * plane_weight(n, hp, __ldg(origin0 + pk[1]));
+    w[2] = (wx0 * wy1) * plane_weight(n, hp, __ldg(origin0 + pk[2]));
+    w[3] = (wx1 * wy1) * plane_weight(n, hp, __ldg(origin0 + pk[3]));
+    const float S = ((w[0] + w[1]) + w[2]) + w[3];
+    float3 E = f3(0.f, 0.f, 0.f);
+    if (S > 0.0f) {
+        const float dw = 4.0f * RC_PI_F / (float)DD;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float wk = w[k] / S;
+            float3 acc = f3(0.f, 0.f, 0.f);
+            const uint4* cb = reinterpret_cast<const uint4*>(texels0 + (size_t)pk[k] * DD);
+            for (int di = 0; di < DD; di += 2) {
+                const uint4 r = ldg_u4(cb + (di >> 1));
+                const float4 a = unpack_half4(make_uint2(r.x, r.y)), b = unpack_half4(make_uint2(r.z, r.w));
+                const float ca = fmaxf(vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])), 0.0f);
+                acc = f3(fmaf(ca, a.x, acc.x), fmaf(ca, a.y, acc.y), fmaf(ca, a.z, acc.z));
+                const float cbv = fmaxf(vdot(n, f3(s_dirs[3 * di + 3], s_dirs[3 * di + 4], s_dirs[3 * di + 5])), 0.0f);
+                acc = f3(fmaf(cbv, b.x, acc.x), fmaf(cbv, b.y, acc.y), fmaf(cbv, b.z, acc.z));
+            }
+            const float wd = wk * dw;
+            E = f3(fmaf(wd, acc.x, E.x), fmaf(wd, acc.y, E.y), fmaf(wd, acc.z, E.z));
+        }
+    }
+    out[o] = pack_half4(fminf(E.x, 65504.0f), fminf(E.y, 65504.0f), fminf(E.z, 65504.0f), 1.0f);
+}
+
+// ------------------------------------------------------------------ display composite (outside the hot path)
+__device__ __forceinline__ unsigned char srgb8(float x)
+{
+    x = fminf(fmaxf(x, 0.0f), 1.0f);
+    const float e = x <= 0.0031308f ? x * 12.92f : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f;
+    return (unsigned char)__float2int_rd(e * 255.0f + 0.5f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_composite(int n, const uint2* __restrict__ irr, const uint2* __restrict__ albedo,
+                                                      const uint2* __restrict__ direct, uchar4* __restrict__ composite,
+                                                      uchar4* __restrict__ direct_srgb)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const float4 e = unpack_half4(irr[i]), a = unpack_half4(albedo[i]), d = unpack_half4(direct[i]);
+    const float ip = 1.0f / RC_PI_F;
+    // Bgra8UnormSrgb (src/window/app.rs:59-75); clear colour (0,0,0,1) where no geometry (src/renderer.rs:573-578)
+    const float r = fmaf(a.x * ip, e.x, d.x), g = fmaf(a.y * ip, e.y, d.y), b = fmaf(a.z * ip, e.z, d.z);
+    composite[i] = make_uchar4(srgb8(b), srgb8(g), srgb8(r), 255);
+    direct_srgb[i] = make_uchar4(srgb8(d.z), srgb8(d.y), srgb8(d.x), 255);
+}
+
+// ------------------------------------------------------------------ debug / parity entry points
+__global__ void __launch_bounds__(kBlock) k_trace_rays(DScene s, const float* __restrict__ rays, uint32_t n, float* __restrict__ hits)
+{
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const float* r = rays + 8 * (size_t)i;
+    const Hit h = trace(s, f3(r[0], r[1], r[2]), f3(r[4], r[5], r[6]), r[3], r[7]);
+    float* o = hits + 4 * (size_t)i;
+    o[0] = h.t; o[1] = h.u; o[2] = h.v; o[3] = __uint_as_float(h.prim);
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade_points(DScene s, DLights L, const float* __restrict__ in, uint32_t n, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const float* r = in + 8 * (size_t)i;
+    const uint32_t prim = __float_as_uint(r[0]);
+    const float u = r[1], v = r[2];
+    const float3 eye = f3(r[4], r[5], r[6]);
+    const float* a = s.verts + 17 * (size_t)s.tris[3 * (size_t)prim];
+    const float* b = s.verts + 17 * (size_t)s.tris[3 * (size_t)prim + 1];
+    const float* c = s.verts + 17 * (size_t)s.tris[3 * (size_t)prim + 2];
+    const float3 P = f3(lerp3(a[0], b[0], c[0], u, v), lerp3(a[1], b[1], c[1], u, v), lerp3(a[2], b[2], c[2], u, v));
+    const Shade sh = shade_hit(s, L, prim, u, v, P, vnormalize(vsub(eye, P)));
+    out[4 * (size_t)i] = sh.rad.x; out[4 * (size_t)i + 1] = sh.rad.y; out[4 * (size_t)i + 2] = sh.rad.z; out[4 * (size_t)i + 3] = 0.f;
+}
+
+inline unsigned blocks_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, cudaStream_t st)
+{
+    dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
+    k_gbuffer<<<grid, kBlock, 0, st>>>(s, cam, L, tile, out);
+}
+
+void launch_probes(const DScene& s, const DCamera& cam, const DLevel& lv, float offset, float4* origin, float4* normal, cudaStream_t st)
+{
+    k_probes<<<blocks_for((size_t)lv.sw * lv.sh), kBlock, 0, st>>>(s, cam, lv, offset, origin, normal);
+}
+
+void launch_link(const DLevel& lo, const DLevel& up, const float4* lo_origin, const float4* lo_normal,
+                 const float4* up_origin, uint4* link_idx, float4* link_w, cudaStream_t st)
+{
+    k_link<<<blocks_for((size_t)lo.sw * lo.sh), kBlock, 0, st>>>(lo, up, lo_origin, lo_normal, up_origin, link_idx, link_w);
+}
+
+void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
+                  const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
+                  const uint4* link_idx, const float4* link_w, bool fused, cudaStream_t st)
+{
+    const size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
+    const int UD = up ? up->D : 0;
+    if (fused && !top)
+        k_march<true><<<blocks_for(n), kBlock, 0, st>>>(s, L, lv, UD, 0, sky, origin, dirs, texels, up_texels, link_idx, link_w);
+    else
+        k_march<false><<<blocks_for(n), kBlock, 0, st>>>(s, L, lv, UD, top ? 1 : 0, sky, origin, dirs, texels, up_texels, link_idx, link_w);
+}
+
+void launch_merge(const DLevel& lv, const DLevel& up, const float4* origin, uint2* texels, const uint2* up_texels,
+                  const uint4* link_idx, const float4* link_w, cudaStream_t st)
+{
+    const size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
+    k_merge<<<blocks_for(n), kBlock, 0, st>>>(lv, up.D, origin, texels, up_texels, link_idx, link_w);
+}
+
+void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
+                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, cudaStream_t st)
+{
+    dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
+    const size_t smem = (size_t)l0.D * l0.D * 3 * sizeof(float);
+    k_gather<<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out);
+}
+
+void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
+                      uchar4* composite, uchar4* direct_srgb, cudaStream_t st)
+{
+    const int n = tile.w * tile.h;
+    k_composite<<<blocks_for((size_t)n), kBlock, 0, st>>>(n, irradiance, albedo, direct, composite, direct_srgb);
+}
+
+void launch_trace_rays(const DScene& s, const float* rays, uint32_t n, float* hits, cudaStream_t st)
+{
+    k_trace_rays<<<blocks_for(n), kBlock, 0, st>>>(s, rays, n, hits);
+}
+
+void launch_shade_points(const DScene& s, const DLights& L, const float* in, uint32_t n, float* out, cudaStream_t st)
+{
+    k_shade_points<<<blocks_for(n), kBlock, 0, st>>>(s, L, in, n, out);
+}
+
+}  // namespace rc

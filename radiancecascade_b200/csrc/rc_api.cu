@@ -1,0 +1,852 @@
+// rc_api.cu — the C ABI of include/rc_b200.h: context, device memory, frame scheduling.
+// Mirrors DefaultRenderer::new / RenderStage::{update, resize, render}
+// (src/renderer.rs:168-632) as a headless CUDA path.  There is no CPU fallback:
+// without a CUDA device rc_create fails with RC_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rc_b200.h"
+#include "bvh.h"
+#include "kernels.cuh"
+#include "scene.h"
+
+using namespace rc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostModel {
+    std::vector<float> stream;      // 17 floats / vertex
+    std::vector<uint32_t> indices;  // reversed winding
+    float material80[20];           // UniformMaterial + enable_bit + Ke
+    int tex_c = -1, tex_n = -1;     // texture slots or -1
+    std::string name;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (!count) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v)
+    {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+// Host-side scene: everything ObjScene::load + DefaultRenderer::new prepare on the CPU
+// (src/primitives.rs:122-175, src/renderer.rs:370-497), flattened for upload.  Device-free.
+struct rc_scene {
+    std::string error;
+    std::vector<HostModel> models;
+    rc_scene_info info{};
+    std::vector<float> verts;                 // [NV][17]
+    std::vector<uint32_t> tris, tri_model;    // global ids
+    std::vector<DMaterial> mats;
+    std::vector<DTexture> tex;
+    std::vector<uint8_t> tex_data;
+    std::vector<float> v0, e1, e2;            // S5 set-up
+    std::vector<uint8_t> skip;
+    float diag = 0.f;
+};
+
+struct rc_ctx {
+    rc_config cfg{};
+    std::string scene_path, error;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    rc_scene host;                            // kept for the parity getters
+
+    // scene (device)
+    DevBuf<float4> d_nodes, d_tri_geom, d_tri_eg;
+    DevBuf<uint32_t> d_tris, d_tri_model;
+    DevBuf<float> d_verts, d_srgb;
+    DevBuf<DMaterial> d_mats;
+    DevBuf<DTexture> d_tex;
+    DevBuf<uint8_t> d_tex_data;
+    DScene scene{};
+
+    // frame state
+    uint32_t W = 0, H = 0;
+    TileRect tile{};
+    uint32_t N = 0;
+    float L0 = 0, t_far = 0, offset = 0;
+    std::vector<DLevel> levels;
+    std::vector<rc_level_info> level_info;
+    std::vector<size_t> dir_offset;      // floats before level i in d_dirs
+    std::vector<std::vector<float>> dirs_host;
+    DevBuf<uint2> d_cascade;             // all levels, RGBA16F texels
+    DevBuf<float4> d_origin, d_normal;   // all probes
+    DevBuf<uint4> d_link_idx;
+    DevBuf<float4> d_link_w;
+    DevBuf<float> d_dirs;
+    DevBuf<float> d_depth;
+    DevBuf<uint32_t> d_prim, d_nrm;
+    DevBuf<uint2> d_albedo, d_direct, d_irr;
+    DevBuf<uchar4> d_composite, d_direct_srgb;
+    DevBuf<float> d_dbg_in, d_dbg_out;
+
+    DCamera cam{};
+    DLights lights{};
+    bool have_camera = false;
+    bool composite_valid = false;
+
+    cudaEvent_t ev[16]{};
+    bool ev_recorded = false;
+    uint32_t launches = 0;
+    cudaStream_t last_stream = nullptr;
+
+    bool fail(rc_status, const std::string& m) { error = m; return false; }
+};
+
+namespace {
+
+#define CU_OK(ctx, call)                                                                  \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            (ctx)->error = std::string(#call) + ": " + cudaGetErrorString(e__);           \
+            return RC_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+// rc_spec.h S3: equal-area octahedral directions, double -> float
+void make_directions(int D, std::vector<float>& out)
+{
+    const double PI = 3.14159265358979323846;
+    out.resize((size_t)D * D * 3);
+    for (int dy = 0; dy < D; dy++)
+        for (int dx = 0; dx < D; dx++) {
+            double u = (2.0 * dx + 1.0) / D - 1.0, v = (2.0 * dy + 1.0) / D - 1.0;
+            double d = 1.0 - (std::fabs(u) + std::fabs(v)), r = 1.0 - std::fabs(d);
+            double phi = (r == 0.0) ? 0.0 : (PI / 4.0) * ((std::fabs(v) - std::fabs(u)) / r + 1.0);
+            double f = r * std::sqrt(2.0 - r * r);
+            float* o = &out[3 * ((size_t)dy * D + dx)];
+            o[0] = (float)std::copysign(f * std::cos(phi), u);
+            o[1] = (float)std::copysign(f * std::sin(phi), v);
+            o[2] = (float)std::copysign(1.0 - r * r, d);
+        }
+}
+
+bool invert4(const double m[16], double inv[16])   // column-major Gauss-Jordan with partial pivoting
+{
+    double a[4][8];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) { a[r][c] = m[c * 4 + r]; a[r][c + 4] = (r == c) ? 1.0 : 0.0; }
+    for (int c = 0; c < 4; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 4; r++) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+        if (a[piv][c] == 0.0) return false;
+        if (piv != c) for (int k = 0; k < 8; k++) std::swap(a[c][k], a[piv][k]);
+        double d = a[c][c];
+        for (int k = 0; k < 8; k++) a[c][k] /= d;
+        for (int r = 0; r < 4; r++)
+            if (r != c) { double f = a[r][c]; for (int k = 0; k < 8; k++) a[r][k] -= f * a[c][k]; }
+    }
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) inv[c * 4 + r] = a[r][c + 4];
+    return true;
+}
+
+// rc_spec.h S4
+bool primary_basis(const rc_camera& c, DCamera& out)
+{
+    double m[16], inv[16];
+    for (int i = 0; i < 16; i++) m[i] = c.view_proj[i];
+    if (!invert4(m, inv)) return false;
+    const double e[3] = {c.eye[0], c.eye[1], c.eye[2]};
+    double A[4], B[4], C[4];
+    for (int r = 0; r < 4; r++) { A[r] = inv[r]; B[r] = inv[4 + r]; C[r] = inv[8 + r] + inv[12 + r]; }
+    double dx[3], dy[3], dc[3];
+    for (int k = 0; k < 3; k++) { dx[k] = A[k] - e[k] * A[3]; dy[k] = B[k] - e[k] * B[3]; dc[k] = C[k] - e[k] * C[3]; }
+    const double sc = (C[3] < 0 ? -1.0 : 1.0) / std::sqrt(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]);
+    out.eye = make_float3(c.eye[0], c.eye[1], c.eye[2]);
+    out.dx = make_float3((float)(dx[0] * sc), (float)(dx[1] * sc), (float)(dx[2] * sc));
+    out.dy = make_float3((float)(dy[0] * sc), (float)(dy[1] * sc), (float)(dy[2] * sc));
+    out.dc = make_float3((float)(dc[0] * sc), (float)(dc[1] * sc), (float)(dc[2] * sc));
+    return true;
+}
+
+inline int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Probe sub-grid every level must hold so the tile can be gathered and merged (S1 footprints).
+void level_rects(uint32_t W, uint32_t H, uint32_t P0, uint32_t N, TileRect t, std::vector<DLevel>& lv)
+{
+    int xlo = 0, xhi = 0, ylo = 0, yhi = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        DLevel& L = lv[i];
+        L.P = (int)(P0 << i);
+        L.gw = (int)((W + L.P - 1) / L.P);
+        L.gh = (int)((H + L.P - 1) / L.P);
+        if (i == 0) {
+            xlo = clampi(floor_div(t.x0 - (int)P0 / 2, (int)P0), 0, L.gw - 1);
+            xhi = clampi(floor_div(t.x0 + t.w - 1 - (int)P0 / 2, (int)P0) + 1, 0, L.gw - 1);
+            ylo = clampi(floor_div(t.y0 - (int)P0 / 2, (int)P0), 0, L.gh - 1);
+            yhi = clampi(floor_div(t.y0 + t.h - 1 - (int)P0 / 2, (int)P0) + 1, 0, L.gh - 1);
+        } else {
+            auto lo_of = [](int q) { return (q % 2 == 0) ? q / 2 - 1 : (q - 1) / 2; };
+            xlo = clampi(lo_of(xlo), 0, L.gw - 1);
+            xhi = clampi(lo_of(xhi) + 1, 0, L.gw - 1);
+            ylo = clampi(lo_of(ylo), 0, L.gh - 1);
+            yhi = clampi(lo_of(yhi) + 1, 0, L.gh - 1);
+        }
+        L.px0 = xlo; L.py0 = ylo; L.sw = xhi - xlo + 1; L.sh = yhi - ylo + 1;
+    }
+}
+
+rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
+{
+    c->W = W; c->H = H;
+    const rc_config& cfg = c->cfg;
+    TileRect t{0, 0, (int)W, (int)H};
+    if (cfg.tile_w && cfg.tile_h) {
+        if (cfg.tile_x0 + cfg.tile_w > W || cfg.tile_y0 + cfg.tile_h > H) { c->error = "tile outside the frame"; return RC_ERR_INVALID_ARG; }
+        t = TileRect{(int)cfg.tile_x0, (int)cfg.tile_y0, (int)cfg.tile_w, (int)cfg.tile_h};
+    }
+    c->tile = t;
+    const uint32_t P0 = cfg.probe_spacing0 ? cfg.probe_spacing0 : RC_DEFAULT_P0;
+    const uint32_t D0 = cfg.dir_res0 ? cfg.dir_res0 : RC_DEFAULT_D0;
+    const uint32_t N = cfg.num_levels ? cfg.num_levels : RC_DEFAULT_LEVELS;
+    if (N > RC_MAX_LEVELS || D0 < 2 || (D0 & 1) || P0 < 1 || (D0 << (N - 1)) > 4096) {
+        c->error = "unsupported cascade parameters (need even D0 >= 2, N <= 10, D_top <= 4096)";
+        return RC_ERR_INVALID_ARG;
+    }
+    c->N = N;
+    c->levels.assign(N, DLevel{});
+    level_rects(W, H, P0, N, t, c->levels);
+    c->level_info.assign(N, rc_level_info{});
+    c->dir_offset.assign(N, 0);
+    c->dirs_host.assign(N, {});
+    size_t texels = 0, probes = 0, dirf = 0;
+    std::vector<float> all_dirs;
+    for (uint32_t i = 0; i < N; i++) {
+        DLevel& L = c->levels[i];
+        L.D = (int)(D0 << i);
+        const double a = (std::pow(4.0, (double)i) - 1.0) / 3.0, b = (std::pow(4.0, (double)i + 1.0) - 1.0) / 3.0;
+        L.t0 = (float)((double)c->L0 * a);                               // S2
+        L.t1 = (i == N - 1) ? c->t_far : (float)((double)c->L0 * b);
+        L.texel_offset = texels;
+        L.probe_offset = (unsigned)probes;
+        const size_t np = (size_t)L.sw * L.sh;
+        texels += np * L.D * L.D;
+        probes += np;
+        make_directions(L.D, c->dirs_host[i]);
+        c->dir_offset[i] = dirf;
+        dirf += c->dirs_host[i].size();
+        all_dirs.insert(all_dirs.end(), c->dirs_host[i].begin(), c->dirs_host[i].end());
+        rc_level_info& I = c->level_info[i];
+        I.spacing = L.P; I.dir_res = L.D; I.grid_w = L.gw; I.grid_h = L.gh;
+        I.px0 = L.px0; I.py0 = L.py0; I.sub_w = L.sw; I.sub_h = L.sh;
+        I.texel_offset = L.texel_offset; I.texel_count = np * L.D * L.D;
+        I.t_begin = L.t0; I.t_end = L.t1;
+    }
+    const size_t npx = (size_t)t.w * t.h;
+    CU_OK(c, c->d_cascade.alloc(texels));
+    CU_OK(c, c->d_origin.alloc(probes));
+    CU_OK(c, c->d_normal.alloc(probes));
+    CU_OK(c, c->d_link_idx.alloc(probes));
+    CU_OK(c, c->d_link_w.alloc(probes));
+    CU_OK(c, c->d_dirs.upload(all_dirs));
+    CU_OK(c, c->d_depth.alloc(npx));
+    CU_OK(c, c->d_prim.alloc(npx));
+    CU_OK(c, c->d_nrm.alloc(npx));
+    CU_OK(c, c->d_albedo.alloc(npx));
+    CU_OK(c, c->d_direct.alloc(npx));
+    CU_OK(c, c->d_irr.alloc(npx));
+    CU_OK(c, c->d_composite.alloc(npx));
+    CU_OK(c, c->d_direct_srgb.alloc(npx));
+    c->cam.W = (int)W; c->cam.H = (int)H;
+    c->ev_recorded = false;
+    return RC_OK;
+}
+
+rc_status load_host_scene(const std::string& scene_path, uint32_t flags, rc_scene* c)
+{
+    std::vector<ObjScene> scenes;
+    std::optional<Vec3> light;
+    LoadError err;
+    // light predicate of the reference: |mt| mt.name == "Light" (src/renderer.rs:176)
+    if (!ObjScene::load(scene_path, [](const TobjMaterial& m) { return m.name == "Light"; }, scenes, light, err)) {
+        c->error = "scene load failed: " + err.message;
+        return RC_ERR_SCENE_LOAD;
+    }
+    if (scenes.empty()) { c->error = "scene has no models (src/renderer.rs:325-329 panics here)"; return RC_ERR_SCENE_LOAD; }
+    const bool use_tex = !(flags & RC_CFG_NO_TEXTURES);
+
+    std::vector<float>& verts = c->verts;
+    std::vector<uint32_t>&tris = c->tris, &tri_model = c->tri_model;
+    std::vector<DMaterial>& mats = c->mats;
+    std::vector<DTexture>& tex = c->tex;
+    std::vector<uint8_t>& tex_data = c->tex_data;
+    uint32_t voff = 0;
+    float bmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (size_t m = 0; m < scenes.size(); m++) {
+        const ObjScene& sc = scenes[m];
+        HostModel hm;
+        hm.name = sc.name();
+        hm.stream = sc.vertex_stream();
+        hm.indices = sc.indices();
+        std::optional<Material> mat = sc.material(use_tex);
+        UniformMaterial um = to_uniform(mat);
+        DMaterial dm;
+        memset(&dm, 0, sizeof(dm));
+        memcpy(dm.ka, um.ambient, 16); memcpy(dm.kd, um.diffuse, 16); memcpy(dm.ks, um.specular, 16);
+        dm.ns = um.shininess;
+        dm.tex_c = dm.tex_n = -1;
+        if (mat) {
+            auto add_tex = [&](const std::shared_ptr<Image>& img) -> int {
+                if (!img) return -1;
+                DTexture t;
+                while (tex_data.size() % 16) tex_data.push_back(0);
+                t.offset = tex_data.size(); t.w = img->width; t.h = img->height;
+                tex_data.insert(tex_data.end(), img->rgba.begin(), img->rgba.end());
+                tex.push_back(t);
+                return (int)tex.size() - 1;
+            };
+            dm.tex_c = add_tex(mat->color_texture);
+            dm.tex_n = add_tex(mat->normal_texture);
+            dm.ke[0] = mat->emission.x; dm.ke[1] = mat->emission.y; dm.ke[2] = mat->emission.z;
+        }
+        dm.ebit = (uint32_t)(dm.tex_c >= 0) | ((uint32_t)(dm.tex_n >= 0) << 1);   // src/renderer.rs:422-423
+        mats.push_back(dm);
+        memcpy(hm.material80, &um, 64);
+        memcpy(&hm.material80[16], &dm.ebit, 4);
+        hm.material80[17] = dm.ke[0]; hm.material80[18] = dm.ke[1]; hm.material80[19] = dm.ke[2];
+        hm.tex_c = dm.tex_c; hm.tex_n = dm.tex_n;
+        const uint32_t nv = (uint32_t)(hm.stream.size() / 17);
+        for (uint32_t i = 0; i < nv; i++)
+            for (int k = 0; k < 3; k++) {
+                bmin[k] = std::fmin(bmin[k], hm.stream[17 * (size_t)i + k]);
+                bmax[k] = std::fmax(bmax[k], hm.stream[17 * (size_t)i + k]);
+            }
+        verts.insert(verts.end(), hm.stream.begin(), hm.stream.end());
+        for (size_t t = 0; t + 2 < hm.indices.size(); t += 3) {
+            tris.push_back(hm.indices[t] + voff); tris.push_back(hm.indices[t + 1] + voff); tris.push_back(hm.indices[t + 2] + voff);
+            tri_model.push_back((uint32_t)m);
+        }
+        voff += nv;
+        c->models.push_back(std::move(hm));
+    }
+    const uint32_t nt = (uint32_t)tri_model.size();
+
+    // S5 triangle set-up: v0, e1 = v1 - v0, e2 = v2 - v0; skip zero-area line/point triangles
+    c->v0.resize(3 * (size_t)nt); c->e1.resize(3 * (size_t)nt); c->e2.resize(3 * (size_t)nt);
+    c->skip.assign(nt, 0);
+    for (uint32_t t = 0; t < nt; t++) {
+        const float* a = &verts[17 * (size_t)tris[3 * (size_t)t]];
+        const float* b = &verts[17 * (size_t)tris[3 * (size_t)t + 1]];
+        const float* cc = &verts[17 * (size_t)tris[3 * (size_t)t + 2]];
+        for (int k = 0; k < 3; k++) { c->v0[3 * (size_t)t + k] = a[k]; c->e1[3 * (size_t)t + k] = b[k] - a[k]; c->e2[3 * (size_t)t + k] = cc[k] - a[k]; }
+        c->skip[t] = !memcmp(a, b, 12) || !memcmp(a, cc, 12) || !memcmp(b, cc, 12);
+    }
+    const float dx = bmax[0] - bmin[0], dy = bmax[1] - bmin[1], dz = bmax[2] - bmin[2];
+    c->diag = std::sqrt((dx * dx + dy * dy) + dz * dz);
+
+    rc_scene_info& I = c->info;
+    I.num_models = (uint32_t)c->models.size(); I.num_vertices = voff; I.num_triangles = nt;
+    I.num_materials = (uint32_t)mats.size();
+    I.num_textures = (uint32_t)tex.size();
+    I.light_from_obj = light ? 1u : 0u;
+    for (int k = 0; k < 3; k++) { I.bbox_min[k] = bmin[k]; I.bbox_max[k] = bmax[k]; }
+    if (light) { I.obj_light[0] = light->x; I.obj_light[1] = light->y; I.obj_light[2] = light->z; }
+    return RC_OK;
+}
+
+rc_status load_scene(rc_ctx* c)
+{
+    rc_status hs = load_host_scene(c->scene_path, c->cfg.flags, &c->host);
+    if (hs != RC_OK) { c->error = c->host.error; return hs; }
+    rc_scene& h = c->host;
+    const uint32_t nt = h.info.num_triangles;
+    const float diag = h.diag;
+    Bvh bvh;
+    build_bvh(h.v0.data(), h.e1.data(), h.e2.data(), h.skip.data(), nt, 1e-4f * diag, bvh);
+    if (bvh.max_depth > 44) { c->error = "BVH deeper than the traversal stack"; return RC_ERR_SCENE_LOAD; }
+    h.info.bvh_nodes = (uint32_t)bvh.nodes.size();
+
+    std::vector<float4> nodes(bvh.nodes.size() * 4), geom(bvh.leaf_tris.size() * 3), eg((size_t)nt * 2);
+    memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(BvhNode));
+    const std::vector<float>&v0 = h.v0, &e1 = h.e1, &e2 = h.e2;
+    for (size_t i = 0; i < bvh.leaf_tris.size(); i++) {
+        const uint32_t t = bvh.leaf_tris[i];
+        float idf;
+        memcpy(&idf, &t, 4);
+        geom[3 * i] = make_float4(v0[3 * (size_t)t], v0[3 * (size_t)t + 1], v0[3 * (size_t)t + 2], idf);
+        geom[3 * i + 1] = make_float4(e1[3 * (size_t)t], e1[3 * (size_t)t + 1], e1[3 * (size_t)t + 2], 0.f);
+        geom[3 * i + 2] = make_float4(e2[3 * (size_t)t], e2[3 * (size_t)t + 1], e2[3 * (size_t)t + 2], 0.f);
+    }
+    for (uint32_t t = 0; t < nt; t++) {
+        eg[2 * (size_t)t] = make_float4(e1[3 * (size_t)t], e1[3 * (size_t)t + 1], e1[3 * (size_t)t + 2], 0.f);
+        eg[2 * (size_t)t + 1] = make_float4(e2[3 * (size_t)t], e2[3 * (size_t)t + 1], e2[3 * (size_t)t + 2], 0.f);
+    }
+    std::vector<float> srgb(256);
+    for (int i = 0; i < 256; i++) {   // S7: decode table in double
+        const double x = i / 255.0;
+        srgb[i] = (float)(x <= 0.04045 ? x / 12.92 : std::pow((x + 0.055) / 1.055, 2.4));
+    }
+    std::vector<DTexture> tex = h.tex;
+    std::vector<uint8_t> tex_data = h.tex_data;
+    if (tex.empty()) tex.push_back(DTexture{0, 1, 1});
+    if (tex_data.empty()) tex_data.assign(16, 0);
+    if (geom.empty()) geom.assign(3, make_float4(0.f, 0.f, 0.f, 0.f));
+
+    CU_OK(c, c->d_nodes.upload(nodes));
+    CU_OK(c, c->d_tri_geom.upload(geom));
+    CU_OK(c, c->d_tri_eg.upload(eg));
+    CU_OK(c, c->d_tris.upload(h.tris));
+    CU_OK(c, c->d_tri_model.upload(h.tri_model));
+    CU_OK(c, c->d_verts.upload(h.verts));
+    CU_OK(c, c->d_mats.upload(h.mats));
+    CU_OK(c, c->d_tex.upload(tex));
+    CU_OK(c, c->d_tex_data.upload(tex_data));
+    CU_OK(c, c->d_srgb.upload(srgb));
+    c->scene = DScene{c->d_nodes.p, c->d_tri_geom.p, c->d_tri_eg.p, c->d_tris.p, c->d_tri_model.p, c->d_verts.p,
+                      c->d_mats.p, c->d_tex.p, c->d_tex_data.p, c->d_srgb.p};
+
+    // S2 / S6 defaults
+    c->L0 = c->cfg.interval0 > 0.f ? c->cfg.interval0 : diag / RC_INTERVAL0_DIVISOR;
+    c->t_far = c->cfg.t_far > 0.f ? c->cfg.t_far : RC_TFAR_FACTOR * diag;
+    c->offset = c->cfg.normal_offset > 0.f ? c->cfg.normal_offset : c->L0 / RC_OFFSET_DIVISOR;
+    return RC_OK;
+}
+
+rc_status scene_model_stream(const rc_scene& s, std::string& error, uint32_t model, float* vertices, size_t vbytes,
+                             uint32_t* indices, size_t ibytes, uint32_t* num_vertices, uint32_t* num_indices)
+{
+    if (model >= s.models.size()) return RC_ERR_INVALID_ARG;
+    const HostModel& m = s.models[model];
+    if (num_vertices) *num_vertices = (uint32_t)(m.stream.size() / 17);
+    if (num_indices) *num_indices = (uint32_t)m.indices.size();
+    if (vertices) {
+        if (vbytes < m.stream.size() * 4) { error = "vertex buffer too small"; return RC_ERR_BUFFER_SIZE; }
+        memcpy(vertices, m.stream.data(), m.stream.size() * 4);
+    }
+    if (indices) {
+        if (ibytes < m.indices.size() * 4) { error = "index buffer too small"; return RC_ERR_BUFFER_SIZE; }
+        memcpy(indices, m.indices.data(), m.indices.size() * 4);
+    }
+    return RC_OK;
+}
+
+void destroy_ctx(rc_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    c->d_nodes.release(); c->d_tri_geom.release(); c->d_tri_eg.release(); c->d_tris.release(); c->d_tri_model.release();
+    c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
+    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release();
+    c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
+    c->d_direct.release(); c->d_irr.release(); c->d_composite.release(); c->d_direct_srgb.release();
+    c->d_dbg_in.release(); c->d_dbg_out.release();
+    delete c;
+}
+
+enum { EV_START = 0, EV_GBUF, EV_PROBES, EV_LEVELS, EV_GATHER, EV_MARCH0 /* .. + 2*level */ };
+
+}  // namespace
+
+extern "C" {
+
+uint32_t rc_abi_version(void) { return RC_ABI_VERSION; }
+
+const char* rc_last_error(const rc_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+rc_status rc_create(const rc_config* cfg, rc_ctx** out)
+{
+    if (!out) return RC_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!cfg || cfg->struct_size != sizeof(rc_config) || !cfg->scene_path || !cfg->width || !cfg->height) {
+        g_create_error = "rc_create: bad config (struct_size / scene_path / size)";
+        return RC_ERR_INVALID_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        g_create_error = "rc_create: no usable CUDA device (this library has no CPU fallback)";
+        return RC_ERR_NO_DEVICE;
+    }
+    rc_ctx* c = new rc_ctx();
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    std::string path = cfg->scene_path;
+    if (!path.empty() && path[0] != '/' && cfg->resource_root && cfg->resource_root[0])
+        path = std::string(cfg->resource_root) + "/" + path;   // RESOURCE_PATH.join(obj_path), src/primitives.rs:106
+    c->scene_path = path;
+    c->cfg.scene_path = nullptr; c->cfg.resource_root = nullptr;
+    rc_status st = RC_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) st = RC_ERR_CUDA;
+    if (st == RC_OK && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) st = RC_ERR_CUDA;
+    if (st == RC_OK) for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
+    if (st != RC_OK) c->error = "CUDA context / stream creation failed";
+    if (st == RC_OK) st = load_scene(c);
+    if (st == RC_OK) st = setup_frame(c, cfg->width, cfg->height);
+    if (st != RC_OK) { g_create_error = c->error; destroy_ctx(c); return st; }
+    c->lights.n = 1;    // AppState::light_position default [0,0,0] (src/app.rs)
+    c->lights.flags = RC_UPD_ENABLE_NORMAL_MAP;
+    *out = c;
+    return RC_OK;
+}
+
+void rc_destroy(rc_ctx* ctx) { destroy_ctx(ctx); }
+
+rc_status rc_update(rc_ctx* c, const rc_camera* cam, const rc_light* lights, uint32_t n_lights, uint32_t flags)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    if (!cam || (n_lights && !lights) || n_lights > RC_MAX_LIGHTS) { c->error = "rc_update: bad arguments"; return RC_ERR_INVALID_ARG; }
+    if (!primary_basis(*cam, c->cam)) { c->error = "rc_update: singular view_proj matrix"; return RC_ERR_INVALID_ARG; }
+    c->cam.W = (int)c->W; c->cam.H = (int)c->H;
+    c->lights.n = (int)n_lights;
+    for (uint32_t i = 0; i < n_lights; i++) memcpy(c->lights.pos[i], lights[i].position, 16);
+    c->lights.flags = flags;
+    c->have_camera = true;
+    return RC_OK;
+}
+
+rc_status rc_resize(rc_ctx* c, uint32_t width, uint32_t height)
+{
+    if (!c || !width || !height) return RC_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->cfg.width = width; c->cfg.height = height;
+    c->cfg.tile_w = c->cfg.tile_h = 0;   // a resize resets the tile to the full frame
+    c->have_camera = false;              // aspect changed: the caller must rc_update (Projection::resize)
+    return setup_frame(c, width, height);
+}
+
+rc_status rc_render_begin(rc_ctx* c, void* stream)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    if (!c->have_camera) { c->error = "rc_render before rc_update"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    c->last_stream = st;
+    c->launches = 0;
+    c->composite_valid = false;
+    CU_OK(c, cudaEventRecord(c->ev[EV_START], st));
+    GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_albedo.p, c->d_direct.p};
+    launch_gbuffer(c->scene, c->cam, c->lights, c->tile, gb, st);
+    c->launches++;
+    CU_OK(c, cudaEventRecord(c->ev[EV_GBUF], st));
+    for (uint32_t i = 0; i < c->N; i++) {
+        const DLevel& L = c->levels[i];
+        launch_probes(c->scene, c->cam, L, c->offset, c->d_origin.p + L.probe_offset, c->d_normal.p + L.probe_offset, st);
+        c->launches++;
+    }
+    for (uint32_t i = 0; i + 1 < c->N; i++) {
+        const DLevel &L = c->levels[i], &U = c->levels[i + 1];
+        launch_link(L, U, c->d_origin.p + L.probe_offset, c->d_normal.p + L.probe_offset, c->d_origin.p + U.probe_offset,
+                    c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
+        c->launches++;
+    }
+    CU_OK(c, cudaEventRecord(c->ev[EV_PROBES], st));
+    CU_OK(c, cudaGetLastError());
+    return RC_OK;
+}
+
+rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
+{
+    if (!c || level >= c->N) return RC_ERR_INVALID_ARG;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const bool fused = !(c->cfg.flags & RC_CFG_SEPARATE_MERGE);
+    const bool top = (level == c->N - 1);
+    const DLevel& L = c->levels[level];
+    const DLevel* U = top ? nullptr : &c->levels[level + 1];
+    const float3 sky = make_float3(c->cfg.sky[0], c->cfg.sky[1], c->cfg.sky[2]);
+    uint2* tex = c->d_cascade.p + L.texel_offset;
+    const uint2* up = top ? nullptr : c->d_cascade.p + U->texel_offset;
+    launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
+                 c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, st);
+    c->launches++;
+    if (!fused && !top) {
+        launch_merge(L, *U, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
+        c->launches++;
+    }
+    CU_OK(c, cudaGetLastError());
+    return RC_OK;
+}
+
+rc_status rc_render_end(rc_ctx* c, void* stream)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CU_OK(c, cudaEventRecord(c->ev[EV_LEVELS], st));
+    const DLevel& L0 = c->levels[0];
+    launch_gather(c->cam, L0, c->tile, c->d_origin.p + L0.probe_offset, c->d_cascade.p + L0.texel_offset, c->d_dirs.p,
+                  c->d_depth.p, c->d_nrm.p, c->d_irr.p, st);
+    c->launches++;
+    CU_OK(c, cudaEventRecord(c->ev[EV_GATHER], st));
+    CU_OK(c, cudaGetLastError());
+    c->ev_recorded = true;
+    return RC_OK;
+}
+
+rc_status rc_render(rc_ctx* c, void* stream)
+{
+    rc_status s = rc_render_begin(c, stream);
+    if (s != RC_OK) return s;
+    for (int i = (int)c->N - 1; i >= 0; i--) {
+        s = rc_render_level(c, (uint32_t)i, stream);
+        if (s != RC_OK) return s;
+    }
+    return rc_render_end(c, stream);
+}
+
+rc_status rc_synchronize(rc_ctx* c)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    if (c->last_stream) CU_OK(c, cudaStreamSynchronize(c->last_stream));
+    CU_OK(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+rc_status rc_target_bytes(rc_ctx* c, rc_target which, size_t* bytes)
+{
+    if (!c || !bytes) return RC_ERR_INVALID_ARG;
+    const size_t npx = (size_t)c->tile.w * c->tile.h;
+    switch ((int)which) {
+    case RC_TARGET_IRRADIANCE: case RC_TARGET_DIRECT: case RC_TARGET_ALBEDO: *bytes = npx * 8; return RC_OK;
+    case RC_TARGET_DEPTH: case RC_TARGET_NORMAL: case RC_TARGET_PRIM: case RC_TARGET_COMPOSITE: case RC_TARGET_DIRECT_SRGB8:
+        *bytes = npx * 4; return RC_OK;
+    default: break;
+    }
+    if ((int)which >= RC_TARGET_CASCADE0 && (uint32_t)((int)which - RC_TARGET_CASCADE0) < c->N) {
+        *bytes = (size_t)c->level_info[(int)which - RC_TARGET_CASCADE0].texel_count * 8;
+        return RC_OK;
+    }
+    c->error = "unknown target";
+    return RC_ERR_INVALID_ARG;
+}
+
+rc_status rc_read_target(rc_ctx* c, rc_target which, void* host_dst, size_t bytes)
+{
+    if (!c || !host_dst) return RC_ERR_INVALID_ARG;
+    size_t need = 0;
+    rc_status s = rc_target_bytes(c, which, &need);
+    if (s != RC_OK) return s;
+    if (bytes < need) { c->error = "rc_read_target: buffer too small"; return RC_ERR_BUFFER_SIZE; }
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    const void* src = nullptr;
+    switch ((int)which) {
+    case RC_TARGET_IRRADIANCE: src = c->d_irr.p; break;
+    case RC_TARGET_DIRECT: src = c->d_direct.p; break;
+    case RC_TARGET_ALBEDO: src = c->d_albedo.p; break;
+    case RC_TARGET_DEPTH: src = c->d_depth.p; break;
+    case RC_TARGET_NORMAL: src = c->d_nrm.p; break;
+    case RC_TARGET_PRIM: src = c->d_prim.p; break;
+    case RC_TARGET_COMPOSITE: case RC_TARGET_DIRECT_SRGB8:
+        if (!c->composite_valid) {
+            launch_composite(c->tile, c->d_irr.p, c->d_albedo.p, c->d_direct.p, c->d_composite.p, c->d_direct_srgb.p, st);
+            c->composite_valid = true;
+        }
+        src = which == RC_TARGET_COMPOSITE ? (const void*)c->d_composite.p : (const void*)c->d_direct_srgb.p;
+        break;
+    default: src = c->d_cascade.p + c->levels[(int)which - RC_TARGET_CASCADE0].texel_offset; break;
+    }
+    CU_OK(c, cudaMemcpyAsync(host_dst, src, need, cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaStreamSynchronize(st));
+    return RC_OK;
+}
+
+rc_status rc_stage_times(rc_ctx* c, float* ms, uint32_t n)
+{
+    if (!c || !ms) return RC_ERR_INVALID_ARG;
+    if (!c->ev_recorded) { c->error = "rc_stage_times before rc_render"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    CU_OK(c, cudaEventSynchronize(c->ev[EV_GATHER]));
+    float t[RC_STAGE_COUNT] = {0};
+    cudaEventElapsedTime(&t[RC_STAGE_GBUFFER], c->ev[EV_START], c->ev[EV_GBUF]);
+    cudaEventElapsedTime(&t[RC_STAGE_PROBES], c->ev[EV_GBUF], c->ev[EV_PROBES]);
+    cudaEventElapsedTime(&t[RC_STAGE_MARCH], c->ev[EV_PROBES], c->ev[EV_LEVELS]);   // march (+ merge)
+    t[RC_STAGE_MERGE] = 0.f;
+    cudaEventElapsedTime(&t[RC_STAGE_GATHER], c->ev[EV_LEVELS], c->ev[EV_GATHER]);
+    cudaEventElapsedTime(&t[RC_STAGE_FRAME], c->ev[EV_START], c->ev[EV_GATHER]);
+    for (uint32_t i = 0; i < n && i < RC_STAGE_COUNT; i++) ms[i] = t[i];
+    return RC_OK;
+}
+
+rc_status rc_launch_count(rc_ctx* c, uint32_t* launches)
+{
+    if (!c || !launches) return RC_ERR_INVALID_ARG;
+    *launches = c->launches;
+    return RC_OK;
+}
+
+rc_status rc_get_levels(rc_ctx* c, rc_level_info* out, uint32_t max_levels, uint32_t* num_levels)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    if (num_levels) *num_levels = c->N;
+    if (out) for (uint32_t i = 0; i < c->N && i < max_levels; i++) out[i] = c->level_info[i];
+    return RC_OK;
+}
+
+rc_status rc_get_scene_info(rc_ctx* c, rc_scene_info* out)
+{
+    if (!c || !out) return RC_ERR_INVALID_ARG;
+    *out = c->host.info;
+    return RC_OK;
+}
+
+rc_status rc_get_tile(rc_ctx* c, uint32_t xywh[4])
+{
+    if (!c || !xywh) return RC_ERR_INVALID_ARG;
+    xywh[0] = (uint32_t)c->tile.x0; xywh[1] = (uint32_t)c->tile.y0; xywh[2] = (uint32_t)c->tile.w; xywh[3] = (uint32_t)c->tile.h;
+    return RC_OK;
+}
+
+rc_status rc_get_intervals(rc_ctx* c, float out3[3])
+{
+    if (!c || !out3) return RC_ERR_INVALID_ARG;
+    out3[0] = c->L0; out3[1] = c->t_far; out3[2] = c->offset;
+    return RC_OK;
+}
+
+rc_status rc_get_directions(rc_ctx* c, uint32_t level, float* out, size_t bytes)
+{
+    if (!c || !out || level >= c->N) return RC_ERR_INVALID_ARG;
+    const auto& d = c->dirs_host[level];
+    if (bytes < d.size() * sizeof(float)) { c->error = "rc_get_directions: buffer too small"; return RC_ERR_BUFFER_SIZE; }
+    memcpy(out, d.data(), d.size() * sizeof(float));
+    return RC_OK;
+}
+
+rc_status rc_get_model_stream(rc_ctx* c, uint32_t model, float* vertices, size_t vbytes, uint32_t* indices, size_t ibytes,
+                              uint32_t* num_vertices, uint32_t* num_indices)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    return scene_model_stream(c->host, c->error, model, vertices, vbytes, indices, ibytes, num_vertices, num_indices);
+}
+
+rc_status rc_get_model_material(rc_ctx* c, uint32_t model, void* out80, size_t bytes)
+{
+    if (!c || !out80 || model >= c->host.models.size()) return RC_ERR_INVALID_ARG;
+    if (bytes < 80) return RC_ERR_BUFFER_SIZE;
+    memcpy(out80, c->host.models[model].material80, 80);
+    return RC_OK;
+}
+
+/* ---- device-free scene ingest (≙ ObjScene::load on the CPU) ---- */
+rc_status rc_scene_load(const char* obj_path, uint32_t flags, rc_scene** out)
+{
+    if (!obj_path || !out) return RC_ERR_INVALID_ARG;
+    *out = nullptr;
+    rc_scene* s = new rc_scene();
+    rc_status st = load_host_scene(obj_path, flags, s);
+    if (st != RC_OK) { g_create_error = s->error; delete s; return st; }
+    *out = s;
+    return RC_OK;
+}
+
+void rc_scene_free(rc_scene* s) { delete s; }
+
+rc_status rc_scene_get_info(const rc_scene* s, rc_scene_info* out)
+{
+    if (!s || !out) return RC_ERR_INVALID_ARG;
+    *out = s->info;
+    return RC_OK;
+}
+
+rc_status rc_scene_model_stream(rc_scene* s, uint32_t model, float* vertices, size_t vbytes, uint32_t* indices, size_t ibytes,
+                                uint32_t* num_vertices, uint32_t* num_indices)
+{
+    if (!s) return RC_ERR_INVALID_ARG;
+    return scene_model_stream(*s, s->error, model, vertices, vbytes, indices, ibytes, num_vertices, num_indices);
+}
+
+rc_status rc_scene_model_material(const rc_scene* s, uint32_t model, void* out80, size_t bytes)
+{
+    if (!s || !out80 || model >= s->models.size()) return RC_ERR_INVALID_ARG;
+    if (bytes < 80) return RC_ERR_BUFFER_SIZE;
+    memcpy(out80, s->models[model].material80, 80);
+    return RC_OK;
+}
+
+rc_status rc_scene_model_name(const rc_scene* s, uint32_t model, char* out, size_t bytes)
+{
+    if (!s || !out || !bytes || model >= s->models.size()) return RC_ERR_INVALID_ARG;
+    snprintf(out, bytes, "%s", s->models[model].name.c_str());
+    return RC_OK;
+}
+
+rc_status rc_scene_model_texture(const rc_scene* s, uint32_t model, uint32_t which, uint8_t* rgba, size_t bytes,
+                                 uint32_t* width, uint32_t* height)
+{
+    if (!s || model >= s->models.size() || which > 1) return RC_ERR_INVALID_ARG;
+    const int slot = which ? s->models[model].tex_n : s->models[model].tex_c;
+    if (width) *width = slot < 0 ? 0u : s->tex[slot].w;
+    if (height) *height = slot < 0 ? 0u : s->tex[slot].h;
+    if (slot < 0 || !rgba) return RC_OK;
+    const size_t need = (size_t)s->tex[slot].w * s->tex[slot].h * 4;
+    if (bytes < need) return RC_ERR_BUFFER_SIZE;
+    memcpy(rgba, s->tex_data.data() + s->tex[slot].offset, need);
+    return RC_OK;
+}
+
+rc_status rc_trace_rays(rc_ctx* c, const float* rays, uint32_t n, float* hits)
+{
+    if (!c || !rays || !hits) return RC_ERR_INVALID_ARG;
+    if (!n) return RC_OK;
+    cudaSetDevice(c->device);
+    CU_OK(c, c->d_dbg_in.alloc((size_t)n * 8));
+    CU_OK(c, c->d_dbg_out.alloc((size_t)n * 4));
+    CU_OK(c, cudaMemcpyAsync(c->d_dbg_in.p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    launch_trace_rays(c->scene, c->d_dbg_in.p, n, c->d_dbg_out.p, c->stream);
+    CU_OK(c, cudaGetLastError());
+    CU_OK(c, cudaMemcpyAsync(hits, c->d_dbg_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+rc_status rc_shade_points(rc_ctx* c, const float* in, uint32_t n, float* out)
+{
+    if (!c || !in || !out) return RC_ERR_INVALID_ARG;
+    if (!n) return RC_OK;
+    cudaSetDevice(c->device);
+    CU_OK(c, c->d_dbg_in.alloc((size_t)n * 8));
+    CU_OK(c, c->d_dbg_out.alloc((size_t)n * 4));
+    CU_OK(c, cudaMemcpyAsync(c->d_dbg_in.p, in, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    launch_shade_points(c->scene, c->lights, c->d_dbg_in.p, n, c->d_dbg_out.p, c->stream);
+    CU_OK(c, cudaGetLastError());
+    CU_OK(c, cudaMemcpyAsync(out, c->d_dbg_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+rc_status rc_cascade_device_ptr(rc_ctx* c, uint32_t level, void** dev_ptr, size_t* bytes)
+{
+    if (!c || level >= c->N || !dev_ptr) return RC_ERR_INVALID_ARG;
+    *dev_ptr = c->d_cascade.p + c->levels[level].texel_offset;
+    if (bytes) *bytes = (size_t)c->level_info[level].texel_count * 8;
+    return RC_OK;
+}
+
+rc_status rc_irradiance_device_ptr(rc_ctx* c, void** dev_ptr, size_t* bytes)
+{
+    if (!c || !dev_ptr) return RC_ERR_INVALID_ARG;
+    *dev_ptr = c->d_irr.p;
+    if (bytes) *bytes = (size_t)c->tile.w * c->tile.h * 8;
+    return RC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// rc_device.cuh — device-side data layout, spec arithmetic (rc_spec.h S4-S7), BVH
+// traversal and fs_main restatement shared by the sm_100a kernels.
+// Compiled with --fmad=false: every fma below is explicit (rc_spec.h preamble).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rc_spec.h"
+
+namespace rc {
+
+// ------------------------------------------------------------------ layout in HBM
+struct DMaterial {          // 80 bytes: UniformMaterial (src/primitives.rs:37-46) + GI extras
+    float ka[4], kd[4], ks[4];
+    float ns;
+    uint32_t ebit;          // enable_bit (src/renderer.rs:422-423)
+    int32_t tex_c, tex_n;   // texture ids or -1 (Texture::empty)
+    float ke[4];
+};
+
+struct DTexture { uint64_t offset; uint32_t w, h; };
+
+struct DScene {
+    const float4* nodes;        // 4 x float4 per BVH node (bvh.h)
+    const float4* tri_geom;     // leaf order, 3 x float4 per triangle: (v0, id bits), (e1, 0), (e2, 0)
+    const float4* tri_eg;       // global-id order, 2 x float4: e1, e2 (geometric normal for probes)
+    const uint32_t* tris;       // [NT][3] global vertex ids, reversed winding (src/primitives.rs:369-376)
+    const uint32_t* tri_model;  // [NT]
+    const float* verts;         // [NV][17] interleaved stream (src/renderer.rs:371-410)
+    const DMaterial* mats;      // [models]
+    const DTexture* tex;
+    const uint8_t* tex_data;    // RGBA8 texels
+    const float* srgb;          // 256-entry sRGB decode table
+};
+
+struct DLights { float pos[RC_MAX_LIGHTS][4]; int n; uint32_t flags; };
+
+struct DCamera {                // rc_spec.h S4
+    float3 eye, dx, dy, dc;
+    int W, H;
+};
+
+struct DLevel {
+    int P, D, gw, gh;           // spacing, direction res, full-frame grid
+    int px0, py0, sw, sh;       // sub-grid held by this context
+    float t0, t1;
+    unsigned long long texel_offset;  // texels before this level in the cascade buffer
+    unsigned int probe_offset;        // probes before this level in the probe arrays
+};
+
+// ------------------------------------------------------------------ spec arithmetic
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 vsub(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 vadd(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 vscale(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 vneg(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float vdot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ float3 vcross(float3 a, float3 b)
+{
+    return f3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+__device__ __forceinline__ float3 vnormalize(float3 a) { float r = 1.0f / sqrtf(vdot(a, a)); return vscale(a, r); }
+__device__ __forceinline__ float3 vfma(float s, float3 d, float3 o) { return f3(fmaf(s, d.x, o.x), fmaf(s, d.y, o.y), fmaf(s, d.z, o.z)); }
+__device__ __forceinline__ float3 xyz(float4 a) { return f3(a.x, a.y, a.z); }
+
+// S4 primary ray through full-frame pixel (x, y)
+__device__ __forceinline__ float3 primary_dir(const DCamera& c, int x, int y)
+{
+    float nx = (float)(2 * x + 1) / (float)c.W - 1.0f;
+    float ny = 1.0f - (float)(2 * y + 1) / (float)c.H;
+    float3 q = f3(fmaf(nx, c.dx.x, fmaf(ny, c.dy.x, c.dc.x)), fmaf(nx, c.dx.y, fmaf(ny, c.dy.y, c.dc.y)),
+                  fmaf(nx, c.dx.z, fmaf(ny, c.dy.z, c.dc.z)));
+    return vnormalize(q);
+}
+
+// ------------------------------------------------------------------ closest hit (S5)
+struct Hit { float t, u, v; uint32_t prim; };
+
+__device__ __forceinline__ float safe_inv(float d)
+{
+    // |d| below 1e-20 would make 1/d overflow; a slab this parallel can only be crossed beyond any tmax
+    return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d));
+}
+
+__device__ __forceinline__ void tri_test(const float4* __restrict__ g, float3 o, float3 d, float tmin, float tmax, Hit& h)
+{
+    const float4 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2);
+    const float3 e1 = xyz(b), e2 = xyz(c);
+    const float3 p = vcross(d, e2);
+    const float det = vdot(e1, p);
+    if (!(det != 0.0f)) return;
+    const float inv = 1.0f / det;
+    const float3 s = vsub(o, xyz(a));
+    const float u = vdot(s, p) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return;
+    const float3 q = vcross(s, e1);
+    const float v = vdot(d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return;
+    const float t = vdot(e2, q) * inv;
+    const uint32_t id = __float_as_uint(a.w);
+    if (t >= tmin && t < tmax && (t < h.t || (t == h.t && id < h.prim))) { h.t = t; h.u = u; h.v = v; h.prim = id; }
+}
+
+// While-while traversal of the 2-wide BVH with a per-thread stack.  h.t doubles as the
+// current far bound (initialised to tmax); on return h.prim == ~0u means miss.
+__device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float tmin, float tmax)
+{
+    Hit h; h.t = tmax; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+    const float3 inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    const float3 noi = f3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+    int stack[48];
+    int sp = 0;
+    int cur = 0;
+    while (true) {
+        const float4* n = s.nodes + 4 * (size_t)cur;
+        const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+        // child 0 slabs
+        float ax = fmaf(q0.x, inv.x, noi.x), bx = fmaf(q0.w, inv.x, noi.x);
+        float ay = fmaf(q0.y, inv.y, noi.y), by = fmaf(q1.x, inv.y, noi.y);
+        float az = fmaf(q0.z, inv.z, noi.z), bz = fmaf(q1.y, inv.z, noi.z);
+        float n0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+        float f0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+        // child 1 slabs
+        ax = fmaf(q1.z, inv.x, noi.x); bx = fmaf(q2.y, inv.x, noi.x);
+        ay = fmaf(q1.w, inv.y, noi.y); by = fmaf(q2.z, inv.y, noi.y);
+        az = fmaf(q2.x, inv.z, noi.z); bz = fmaf(q2.w, inv.z, noi.z);
+        float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+        float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+        const bool hit0 = n0 <= f0, hit1 = n1 <= f1;   // <=: equal-t candidates stay reachable for the id tie-break
+        int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+        int next;
+        if (hit0 && hit1) {
+            if (n1 < n0) { int t = c0; c0 = c1; c1 = t; }
+            stack[sp++] = c1;
+            next = c0;
+        } else if (hit0) next = c0;
+        else if (hit1) next = c1;
+        else { if (sp == 0) break; next = stack[--sp]; }
+        bool done = false;
+        while (next < 0) {
+            const uint32_t leaf = (uint32_t)~next;
+            const uint32_t first = leaf >> 3, cnt = leaf & 7u;
+            for (uint32_t i = 0; i < cnt; i++) tri_test(s.tri_geom + 3 * (size_t)(first + i), o, d, tmin, tmax, h);
+            if (sp == 0) { done = true; break; }
+            next = stack[--sp];
+        }
+        if (done) break;
+        cur = next;
+    }
+    if (h.prim == 0xffffffffu) h.t = -1.0f;
+    return h;
+}
+
+// ------------------------------------------------------------------ shading (S7; src/shader.wgsl:76-100)
+__device__ __forceinline__ int mirror_idx(long long i, long long size)   // Vulkan MirrorRepeat
+{
+    long long m = i % (2 * size);
+    if (m < 0) m += 2 * size;
+    m -= size;
+    if (m < 0) m = -(1 + m);
+    return (int)((size - 1) - m);
+}
+
+__device__ __forceinline__ float3 sample_nearest(const DScene& s, int tex, float u, float v, bool srgb)
+{
+    if (tex < 0) return f3(0.f, 0.f, 0.f);   // Texture::empty (src/texture.rs:12-64)
+    const DTexture t = s.tex[tex];
+    float fu = floorf(u * (float)t.w), fv = floorf(v * (float)t.h);
+    if (!(fabsf(fu) < 1e9f)) fu = 0.0f;
+    if (!(fabsf(fv) < 1e9f)) fv = 0.0f;
+    const int ix = mirror_idx((long long)fu, t.w), iy = mirror_idx((long long)fv, t.h);
+    const uchar4 p = *reinterpret_cast<const uchar4*>(s.tex_data + t.offset + 4 * ((size_t)iy * t.w + ix));
+    if (srgb) return f3(__ldg(s.srgb + p.x), __ldg(s.srgb + p.y), __ldg(s.srgb + p.z));
+    return f3(p.x / 255.0f, p.y / 255.0f, p.z / 255.0f);
+}
+
+__device__ __forceinline__ float lerp3(float a0, float a1, float a2, float u, float v)
+{
+    const float w = (1.0f - u) - v;
+    return fmaf(a2, v, fmaf(a1, u, a0 * w));
+}
+
+__device__ __forceinline__ float clamp_rad(float x) { return fminf(fmaxf(x, 0.0f), 65504.0f); }   // NaN -> 0
+
+struct Shade { float3 rad, n, albedo, direct; };
+
+// fs_main at a hit with view vector Vd (= -ray direction); rad = Ke + (L + unlit) * albedo.
+__device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, uint32_t prim, float u, float v,
+                                           float3 P, float3 Vd)
+{
+    const uint32_t i0 = s.tris[3 * (size_t)prim], i1 = s.tris[3 * (size_t)prim + 1], i2 = s.tris[3 * (size_t)prim + 2];
+    const float* a = s.verts + 17 * (size_t)i0;
+    const float* b = s.verts + 17 * (size_t)i1;
+    const float* c = s.verts + 17 * (size_t)i2;
+    float at[17];
+#pragma unroll
+    for (int k = 3; k < 17; k++) at[k] = lerp3(__ldg(a + k), __ldg(b + k), __ldg(c + k), u, v);
+    const DMaterial& m = s.mats[s.tri_model[prim]];
+    uint32_t eb = m.ebit;
+    if (!(L.flags & 1u)) eb &= 1u;                                   // src/renderer.rs:623
+    const bool b0 = eb & 1u, b1 = (eb >> 1) & 1u;
+    const float tu = at[15], tv = 1.0f - at[16];                     // :78
+    const float3 albedo = b0 ? sample_nearest(s, m.tex_c, tu, tv, true) : f3(at[3], at[4], at[5]);   // :80
+    float3 Lc = f3(m.ka[0] * 0.05f * m.ka[3], m.ka[1] * 0.05f * m.ka[3], m.ka[2] * 0.05f * m.ka[3]);  // :82-83
+    const float3 Nv = f3(at[6], at[7], at[8]);
+    float3 raw;
+    if (b1) {
+        const float3 cs = sample_nearest(s, m.tex_n, tu, tv, false);
+        const float3 cf = f3(cs.x * 2.0f - 1.0f, cs.y * 2.0f - 1.0f, cs.z * 2.0f - 1.0f);             // :85
+        const float3 T = vnormalize(f3(at[9], at[10], at[11])), B = vnormalize(f3(at[12], at[13], at[14]));
+        raw = vnormalize(vadd(vadd(vscale(T, cf.x), vscale(B, cf.y)), vscale(Nv, cf.z)));             // :86
+    } else {
+        raw = vnormalize(Nv);
+    }
+    const float ndv = vdot(Vd, raw);                                 // :88
+    const float3 N = ndv < 0.0f ? vneg(raw) : raw;                   // :89
+    for (int li = 0; li < L.n; li++) {
+        const float3 lp = f3(L.pos[li][0], L.pos[li][1], L.pos[li][2]);
+        const float3 Ld = vnormalize(vsub(lp, P));                   // :91
+        const float ndl = fmaxf(vdot(Ld, N), 0.0f);                  // :92
+        const float kd = 0.7f * ndl * m.kd[3];
+        Lc = f3(fmaf(m.kd[0], kd, Lc.x), fmaf(m.kd[1], kd, Lc.y), fmaf(m.kd[2], kd, Lc.z));           // :93
+        const float3 Hd = vnormalize(vadd(Vd, Ld));                  // :95
+        const float st = powf(fmaxf(vdot(N, Hd), 0.0f), m.ns);       // :96
+        const float ks = st * m.ks[3] * (ndv > 1e-6f ? 1.0f : 0.0f); // :97
+        Lc = f3(fmaf(m.ks[0], ks, Lc.x), fmaf(m.ks[1], ks, Lc.y), fmaf(m.ks[2], ks, Lc.z));
+    }
+    const float pred = ((m.ka[0] - 1e-5f) + (m.kd[0] - 1e-5f) + (m.ks[0] - 1e-5f))
+                     + ((m.ka[1] - 1e-5f) + (m.kd[1] - 1e-5f) + (m.ks[1] - 1e-5f))
+                     + ((m.ka[2] - 1e-5f) + (m.kd[2] - 1e-5f) + (m.ks[2] - 1e-5f));                   // :99
+    const float unlit = pred <= 0.0f ? 1.0f : 0.0f;
+    Shade r;
+    r.direct = f3((Lc.x + unlit) * albedo.x, (Lc.y + unlit) * albedo.y, (Lc.z + unlit) * albedo.z);   // :100
+    r.rad = f3(clamp_rad(m.ke[0] + r.direct.x), clamp_rad(m.ke[1] + r.direct.y), clamp_rad(m.ke[2] + r.direct.z));
+    r.n = N;
+    r.albedo = albedo;
+    return r;
+}
+
+// ------------------------------------------------------------------ packing
+__device__ __forceinline__ uint2 pack_half4(float r, float g, float b, float a)
+{
+    __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    return o;
+}
+__device__ __forceinline__ float4 unpack_half4(uint2 p)
+{
+    const float2 lo = __half22float2(*reinterpret_cast<__half2*>(&p.x));
+    const float2 hi = __half22float2(*reinterpret_cast<__half2*>(&p.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// standard octahedral encode of the shading normal, 2 x snorm16 (G-buffer only)
+__device__ __forceinline__ uint32_t oct_encode(float3 n)
+{
+    const float s = fabsf(n.x) + fabsf(n.y) + fabsf(n.z);
+    float px = n.x / s, py = n.y / s;
+    if (n.z < 0.0f) {
+        const float qx = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f);
+        const float qy = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f);
+        px = qx; py = qy;
+    }
+    const int ix = __float2int_rn(fminf(fmaxf(px, -1.0f), 1.0f) * 32767.0f);
+    const int iy = __float2int_rn(fminf(fmaxf(py, -1.0f), 1.0f) * 32767.0f);
+    return ((uint32_t)(uint16_t)(int16_t)ix) | (((uint32_t)(uint16_t)(int16_t)iy) << 16);
+}
+__device__ __forceinline__ float3 oct_decode(uint32_t e)
+{
+    const float px = (float)(int16_t)(e & 0xffffu) / 32767.0f, py = (float)(int16_t)(e >> 16) / 32767.0f;
+    const float z = 1.0f - fabsf(px) - fabsf(py);
+    float x = px, y = py;
+    if (z < 0.0f) {
+        x = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f);
+        y = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f);
+    }
+    return vnormalize(f3(x, y, z));
+}
+
+// S8 plane-distance weight of probe k (origin ok.xyz, ok.w = valid) seen from (op, np)
+__device__ __forceinline__ float plane_weight(float3 np, float3 op, float4 ok)
+{
+    if (ok.w == 0.0f) return 0.0f;
+    const float3 delta = vsub(xyz(ok), op);
+    const float l2 = vdot(delta, delta), hh = vdot(np, delta);
+    return l2 > 0.0f ? 1.0f / (1.0f + RC_PLANE_K * (hh * hh) / l2) : 1.0f;
+}
+
+// S1: the two upper probes (clamped) and bilinear weights of probe index q along one axis
+__device__ __forceinline__ void upper_pair(int q, int gmax, int& i0, int& i1, float& w0, float& w1)
+{
+    int base;
+    if ((q & 1) == 0) { base = q / 2 - 1; w0 = 0.25f; w1 = 0.75f; }
+    else { base = (q - 1) / 2; w0 = 0.75f; w1 = 0.25f; }
+    i0 = min(max(base, 0), gmax - 1);
+    i1 = min(max(base + 1, 0), gmax - 1);
+}
+
+}  // namespace rc
