@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the radiance-cascade GI hot path on B200.
+
+A "step" is one GI frame (G-buffer, probe placement, per-level ray march fused with the
+cascade merge, irradiance gather) of a bundled scene along the deterministic orbit camera
+of SURVEY.md §8d.  Metric: G ray-samples/s (one ray sample = one (probe, direction, level)
+interval query) with ms/frame in `ms_per_step`.
+
+  python bench.py --gpus N --steps K --warmup W            # product (CUDA, C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the same spec
+
+N = 1 workload: BASELINE.json configs[1] — teapot, 1920x1080, single light.  N > 1: every rank
+renders its own frames of the orbit (multi-view batch, no data-path collective): weak scaling.
+The reference itself has no GI path and cannot be built here, so the CPU
+arm is the repo's C oracle (kind "port") on all host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gi_ray_samples_per_s"
+UNIT = "Gray-samples/s"
+WORKLOADS = {  # BASELINE.json configs
+    "teapot_1080p": ("teapot", 1920, 1080, "bench"),
+    "test_room_1080p": ("test_room", 1920, 1080, "room"),
+    "living_room_4k": ("living_room", 3840, 2160, "bench"),
+    "sonic_8k": ("sonic", 7680, 4320, "bench"),
+    "cube_512": ("cube", 512, 512, "bench"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def frame_inputs(rc, info, W, H, frame, lights_kind):
+    lo, hi = list(info.bbox_min), list(info.bbox_max)
+    pos, tgt, zn, zf = rc.scenes.orbit_camera(lo, hi, frame)
+    proj = rc.Projection.new(W, H, 45.0, zn, zf)
+    uc = rc.UniformCamera.look_at(pos, tgt, proj)
+    pts = rc.scenes.room_lights(lo, hi) if lights_kind == "room" else [rc.scenes.bench_light(lo, hi)]
+    return uc, pts
+
+
+def rays_per_frame(levels):
+    return int(sum(l.texel_count for l in levels))
+
+
+def algorithmic_bytes(levels, W, H):
+    """every level written once, every level but the top read once by the level
+    below, level 0 read by the gather, plus G-buffer (depth 4 + normal 4) read and irradiance (8) written."""
+    T = [int(l.texel_count) for l in levels]
+    casc = 8 * (sum(T) + sum(T[1:]) + T[0])
+    return casc, casc + W * H * (8 + 8)
+
+
+# ------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(workload, steps, warmup, sample_div):
+    """Times the C oracle (all host threads) on a bounded sample: the same scene, camera path,
+    lights and cascade parameters at 1/sample_div of the resolution per axis."""
+    import radiancecascade_b200 as rc
+    from oracle import gi_oracle as go
+    name, W, H, lk = WORKLOADS[workload]
+    w, h = W // sample_div, H // sample_div
+    osc = go.OracleScene(rc.scenes.scene_path(name))
+
+    class _Info:
+        bbox_min, bbox_max = osc.bbox_min, osc.bbox_max
+    p = osc.params(w, h, store_half=True)
+    lv = osc.levels(p)
+    rays = sum(l.gw * l.gh * l.D * l.D for l in lv)
+    times = []
+    for i in range(warmup + steps):
+        uc, pts = frame_inputs(rc, _Info, w, h, i, lk)
+        larr = np.array([[q[0], q[1], q[2], 1.0] for q in pts], dtype=np.float32)
+        t = time.perf_counter()
+        osc.render(p, uc.as_array(), larr)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return {"value": rays / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": go.num_threads(), "kind": "port",
+            "sample": f"{name} {w}x{h} (1/{sample_div} of {W}x{H} per axis), full cascade stack, "
+                      f"{steps} frame(s), oracle/rc_oracle.c with OpenMP",
+            "ms_per_step": ms, "rays_per_step": rays}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = args.workload or "teapot_1080p"
+    name, W, H, _ = WORKLOADS[wl]
+    cb = cpu_oracle_run(wl, args.steps, args.warmup, args.cpu_sample_div)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic camera path over the bundled scene",
+            "config": {"workload": f"{name} {W}x{H} (bounded sample: {cb['sample']})", "levels": 6, "probe_spacing0": 4, "dir_res0": 4},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference repository has no GI path and cannot be built here (no Rust/Vulkan); this arm is the "
+                    "repo's CPU oracle of the same specification"}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------- product arm
+def run_product(args):
+    import torch
+    import radiancecascade_b200 as rc
+    from radiancecascade_b200 import _ffi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = args.workload or "teapot_1080p"
+    name, W, H, lk = WORKLOADS[wl]
+    state = rc.AppState()
+    flags = _ffi.RC_CFG_SEPARATE_MERGE if args.separate_merge else 0
+    r = rc.DefaultRenderer.new(local, (W, H), state, rc.scenes.scene_path(name), rc.CascadeConfig(flags=flags))
+    info = r.scene_info()
+    levels = r.levels()
+    rays = rays_per_frame(levels)
+    casc_bytes, frame_bytes = algorithmic_bytes(levels, W, H)
+
+    stream = torch.cuda.Stream()
+    sh = stream.cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    host_out = torch.empty((H, W, 4), dtype=torch.float16, pin_memory=True)
+    host_ptr, host_bytes = host_out.data_ptr(), host_out.numel() * 2
+    import ctypes as C
+
+    def set_frame(i):
+        uc, pts = frame_inputs(rc, info, W, H, i * world + rank, lk)   # rank r renders its own views
+        state.uniform_camera = uc
+        state.light_position, state.extra_lights = pts[0], pts[1:]
+        r.update(state)
+
+    # ---- device-timed loop: per-step events, L2 flushed between steps --------------------
+    def device_loop(n, record):
+        evs = []
+        for i in range(n):
+            set_frame(i)
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                r.render(sh)
+                e1.record(stream)
+            evs.append((e0, e1))
+            if record is not None:
+                stream.synchronize()
+                record.append((r.stage_times(), r.level_times()))
+        stream.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    device_loop(max(args.warmup, 3), None)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stages = []
+    ms_steps = device_loop(args.steps, stages)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    total_ms = float(sum(ms_steps))
+    if dist:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * rays / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the public API: host camera in, host irradiance out ----------
+    def e2e_loop(n):
+        t0 = time.perf_counter()
+        for i in range(n):
+            set_frame(i)                       # host -> device: camera + lights (kernel parameter block)
+            r.render(sh)
+            st = r._lib.rc_read_target(r._h, _ffi.RC_TARGET_IRRADIANCE, C.c_void_p(host_ptr), host_bytes)   # D2H into pinned memory
+            if st != 0:
+                raise RuntimeError("rc_read_target failed")
+        return (time.perf_counter() - t0) * 1e3
+
+    e2e_loop(2)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_ms = e2e_loop(args.steps)
+    if dist:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * rays / (e2e_ms / args.steps * 1e-3) / 1e9
+    n_lights = 1 + len(state.extra_lights)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        st_mean = {k: float(np.mean([s[0][k] for s in stages])) for k in stages[0][0]}
+        lv_mean = [float(np.mean([s[1][i] for s in stages])) for i in range(len(levels))]
+        # dominant kernel: k_march (fused with the merge), one launch per level -> average launch
+        march_ms = st_mean["march"]
+        launches_per_frame = r.launch_count()
+        avg_march_launch_ms = march_ms / len(levels)
+        march_bytes_per_launch = (casc_bytes - 8 * int(levels[0].texel_count)) / len(levels)   # writes + upper reads
+        gather_bytes = 8 * int(levels[0].texel_count) + W * H * 16
+        roof = {"bound": "hbm", "kernel": "k_march<fused> (per-level ray march + merge; latency/issue-bound, BVH in L2)",
+                "achieved": march_bytes_per_launch / (avg_march_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "peak_source": peak_src, "traffic": None}
+        roof["frac"] = roof["achieved"] / peak
+        gather = {"kernel": "k_gather", "bound": "hbm", "achieved": gather_bytes / (st_mean["gather"] * 1e-3) / 1e9, "peak": peak,
+                  "unit": "GB/s", "bytes": gather_bytes}
+        gather["frac"] = gather["achieved"] / peak
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic orbit camera over the reference's bundled scene (scenes/%s.zip)" % name,
+            "config": {"workload": f"{name} {W}x{H}, {n_lights} light(s), full cascade stack", "levels": len(levels),
+                       "probe_spacing0": int(levels[0].spacing), "dir_res0": int(levels[0].dir_res),
+                       "rays_per_frame": rays, "triangles": int(info.num_triangles),
+                       "l2": "flushed between timed steps (256 MiB memset)",
+                       "parallelism": "1 GPU" if world == 1 else f"multi-view batch, one orbit view per rank x{world}",
+                       "merge": "separate kernels" if args.separate_merge else "fused into march"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": 80 + 16 * n_lights, "d2h_bytes_per_step": host_bytes},
+            "gpu_launches": launches_per_frame * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "roofline_gather": gather,
+            "frame_hbm": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "note": "whole frame vs HBM peak; march is not HBM-bound"},
+            "stage_ms": st_mean, "level_ms": lv_mean,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_oracle_run(wl, 1, 0, args.cpu_sample_div)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--separate-merge", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-div", type=int, default=4, help="CPU arm renders at 1/div of the resolution per axis")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -152,6 +152,8 @@ rc_status rc_target_bytes(rc_ctx* ctx, rc_target which, size_t* bytes);
 
 /* CUDA-event time of each stage of the last rendered frame, in ms. */
 rc_status rc_stage_times(rc_ctx* ctx, float* ms, uint32_t n);
+/* CUDA-event time of each cascade level's march(+merge) kernels in the last frame, ms[level]. */
+rc_status rc_level_times(rc_ctx* ctx, float* ms, uint32_t n);
 /* Number of kernels rc_render launches per frame. */
 rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
 

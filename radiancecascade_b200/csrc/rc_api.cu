@@ -110,7 +110,8 @@ struct rc_ctx {
     bool have_camera = false;
     bool composite_valid = false;
 
-    cudaEvent_t ev[16]{};
+    cudaEvent_t ev[8]{};
+    cudaEvent_t ev_level[RC_MAX_LEVELS + 1]{};   // ev_level[i] recorded after level i's kernels
     bool ev_recorded = false;
     uint32_t launches = 0;
     cudaStream_t last_stream = nullptr;
@@ -452,6 +453,7 @@ void destroy_ctx(rc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_level) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tri_geom.release(); c->d_tri_eg.release(); c->d_tris.release(); c->d_tri_model.release();
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
@@ -497,6 +499,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
     if (cudaSetDevice(c->device) != cudaSuccess) st = RC_ERR_CUDA;
     if (st == RC_OK && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) st = RC_ERR_CUDA;
     if (st == RC_OK) for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
+    if (st == RC_OK) for (auto& e : c->ev_level) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
     if (st != RC_OK) c->error = "CUDA context / stream creation failed";
     if (st == RC_OK) st = load_scene(c);
     if (st == RC_OK) st = setup_frame(c, cfg->width, cfg->height);
@@ -581,6 +584,7 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
         launch_merge(L, *U, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
         c->launches++;
     }
+    CU_OK(c, cudaEventRecord(c->ev_level[level], st));
     CU_OK(c, cudaGetLastError());
     return RC_OK;
 }
@@ -683,6 +687,21 @@ rc_status rc_stage_times(rc_ctx* c, float* ms, uint32_t n)
     cudaEventElapsedTime(&t[RC_STAGE_GATHER], c->ev[EV_LEVELS], c->ev[EV_GATHER]);
     cudaEventElapsedTime(&t[RC_STAGE_FRAME], c->ev[EV_START], c->ev[EV_GATHER]);
     for (uint32_t i = 0; i < n && i < RC_STAGE_COUNT; i++) ms[i] = t[i];
+    return RC_OK;
+}
+
+rc_status rc_level_times(rc_ctx* c, float* ms, uint32_t n)
+{
+    if (!c || !ms) return RC_ERR_INVALID_ARG;
+    if (!c->ev_recorded) { c->error = "rc_level_times before rc_render"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    CU_OK(c, cudaEventSynchronize(c->ev[EV_GATHER]));
+    for (uint32_t i = 0; i < n && i < c->N; i++) {
+        // levels run top-down: level i starts when level i+1 (or the probe stage) ended
+        cudaEvent_t begin = (i == c->N - 1) ? c->ev[EV_PROBES] : c->ev_level[i + 1];
+        ms[i] = 0.f;
+        cudaEventElapsedTime(&ms[i], begin, c->ev_level[i]);
+    }
     return RC_OK;
 }
 

@@ -263,6 +263,12 @@ class DefaultRenderer:
         self._check(self._lib.rc_stage_times(self._h, ms, len(_ffi.STAGES)))
         return dict(zip(_ffi.STAGES, [float(x) for x in ms]))
 
+    def level_times(self) -> List[float]:
+        n = len(self.levels())
+        ms = (C.c_float * n)()
+        self._check(self._lib.rc_level_times(self._h, ms, n))
+        return [float(x) for x in ms]
+
     def launch_count(self) -> int:
         n = C.c_uint32()
         self._check(self._lib.rc_launch_count(self._h, C.byref(n)))
