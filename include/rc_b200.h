@@ -152,8 +152,15 @@ rc_status rc_target_bytes(rc_ctx* ctx, rc_target which, size_t* bytes);
 
 /* CUDA-event time of each stage of the last rendered frame, in ms. */
 rc_status rc_stage_times(rc_ctx* ctx, float* ms, uint32_t n);
-/* CUDA-event time of each cascade level's march(+merge) kernels in the last frame, ms[level]. */
+/* CUDA-event time of each cascade level's march(+merge) kernels in the last frame, ms[level].
+ * Needs rc_set_tuning(ctx, "level_timing", 1): the events sit between the level kernels and
+ * switch off their programmatic-dependent-launch overlap, so they are off by default. */
 rc_status rc_level_times(rc_ctx* ctx, float* ms, uint32_t n);
+/* Runtime tuning knobs (A/B measurement; defaults are the measured best): "level_timing" 0/1,
+ * "march_persist" 0/1 (persistent ray-replacement march vs one ray per thread), "march_thresh"
+ * 1..32 (refill when fewer lanes are busy), "march_pdl" 0/1, "march_block" 64..512, "march_grid",
+ * "march_map<level>" 0 linear / 1 direction tile / 2 probe tile. */
+rc_status rc_set_tuning(rc_ctx* ctx, const char* key, int value);
 /* Number of kernels rc_render launches per frame. */
 rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
 

@@ -22,8 +22,15 @@ namespace {
 
 constexpr int kBlock = 256;
 
-__device__ __forceinline__ uint2 ldg_u2(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ uint4 ldg_u4(const uint4* p) { return __ldg(p); }
+// Plain (coherent, L1-allocating) 128-bit load: the merged upper level is written by the previous
+// kernel of the PDL chain while this kernel may already be running, so the non-coherent .nc path is not used for it.
+__device__ __forceinline__ uint4 ld_u4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
 // ------------------------------------------------------------------ G-buffer
 __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out)
@@ -49,37 +56,64 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLigh
     out.direct[o] = pack_half4(clamp_rad(sh.direct.x), clamp_rad(sh.direct.y), clamp_rad(sh.direct.z), 1.0f);
 }
 
-// ------------------------------------------------------------------ probes (S6)
-__global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel lv, float offset,
+// ------------------------------------------------------------------ probes (S6), all levels in one launch
+// A probe whose anchor pixel lies inside the tile reuses the G-buffer's primary hit (same ray,
+// same S4/S5 arithmetic -> bit-identical); only halo probes of a multi-GPU tile trace their own ray.
+__device__ __forceinline__ int level_of(const DLevelSet& ls, unsigned i)
+{
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < ls.n; k++) if (i >= ls.lv[k].probe_offset) l = k;
+    return l;
+}
+
+__global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, TileRect tile, float offset,
+                                                   const float* __restrict__ depth, const uint32_t* __restrict__ prim,
                                                    float4* __restrict__ origin, float4* __restrict__ normal)
 {
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= lv.sw * lv.sh) return;
+    const unsigned gi = blockIdx.x * kBlock + threadIdx.x;
+    if (gi >= total) return;
+    const DLevel& lv = ls.lv[level_of(ls, gi)];
+    const int i = (int)(gi - lv.probe_offset);
     const int px = lv.px0 + i % lv.sw, py = lv.py0 + i / lv.sw;
     const int ax = min(px * lv.P + lv.P / 2, cam.W - 1), ay = min(py * lv.P + lv.P / 2, cam.H - 1);
     const float3 d = primary_dir(cam, ax, ay);
-    const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
-    if (h.prim == 0xffffffffu) {
-        origin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        normal[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float t;
+    uint32_t id;
+    const int tx = ax - tile.x0, ty = ay - tile.y0;
+    if (tx >= 0 && tx < tile.w && ty >= 0 && ty < tile.h) {
+        const size_t o = (size_t)ty * tile.w + tx;
+        t = depth[o];
+        id = prim[o];
+    } else {
+        const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
+        t = h.t;
+        id = h.prim;
+    }
+    if (id == 0xffffffffu) {
+        origin[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        normal[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
-    const float3 hp = vfma(h.t, d, cam.eye);
-    const float3 e1 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim)), e2 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim + 1));
+    const float3 hp = vfma(t, d, cam.eye);
+    const float3 e1 = xyz(__ldg(s.tri_eg + 2 * (size_t)id)), e2 = xyz(__ldg(s.tri_eg + 2 * (size_t)id + 1));
     float3 ng = vnormalize(vcross(e1, e2));
     if (vdot(ng, d) > 0.0f) ng = vneg(ng);
     const float3 og = vfma(offset, ng, hp);
-    origin[i] = make_float4(og.x, og.y, og.z, 1.0f);
-    normal[i] = make_float4(ng.x, ng.y, ng.z, 0.0f);
+    origin[gi] = make_float4(og.x, og.y, og.z, 1.0f);
+    normal[gi] = make_float4(ng.x, ng.y, ng.z, 0.0f);
 }
 
-// ------------------------------------------------------------------ link (S1 + S8 weights)
-__global__ void __launch_bounds__(kBlock) k_link(DLevel lo, DLevel up, const float4* __restrict__ lo_origin,
-                                                 const float4* __restrict__ lo_normal, const float4* __restrict__ up_origin,
-                                                 uint4* __restrict__ link_idx, float4* __restrict__ link_w)
+// ------------------------------------------------------------------ link (S1 + S8 weights), levels 0..N-2 in one launch
+__global__ void __launch_bounds__(kBlock) k_link(DLevelSet ls, unsigned total, const float4* __restrict__ origin,
+                                                 const float4* __restrict__ normal, uint4* __restrict__ link_idx,
+                                                 float4* __restrict__ link_w)
 {
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= lo.sw * lo.sh) return;
+    const unsigned gi = blockIdx.x * kBlock + threadIdx.x;
+    if (gi >= total) return;
+    const int l = level_of(ls, gi);
+    const DLevel &lo = ls.lv[l], &up = ls.lv[l + 1];
+    const int i = (int)(gi - lo.probe_offset);
     const int px = lo.px0 + i % lo.sw, py = lo.py0 + i / lo.sw;
     int x0, x1, y0, y1;
     float wx0, wx1, wy0, wy1;
@@ -89,10 +123,11 @@ __global__ void __launch_bounds__(kBlock) k_link(DLevel lo, DLevel up, const flo
     const uint32_t k1 = (uint32_t)((y0 - up.py0) * up.sw + (x1 - up.px0));
     const uint32_t k2 = (uint32_t)((y1 - up.py0) * up.sw + (x0 - up.px0));
     const uint32_t k3 = (uint32_t)((y1 - up.py0) * up.sw + (x1 - up.px0));
-    const float4 og = lo_origin[i];
+    const float4* up_origin = origin + up.probe_offset;
+    const float4 og = origin[gi];
     float4 w = make_float4(-1.f, 0.f, 0.f, 0.f);
     if (og.w != 0.0f) {
-        const float3 op = xyz(og), np = xyz(lo_normal[i]);
+        const float3 op = xyz(og), np = xyz(normal[gi]);
         const float w0 = (wx0 * wy0) * plane_weight(np, op, __ldg(up_origin + k0));
         const float w1 = (wx1 * wy0) * plane_weight(np, op, __ldg(up_origin + k1));
         const float w2 = (wx0 * wy1) * plane_weight(np, op, __ldg(up_origin + k2));
@@ -100,8 +135,8 @@ __global__ void __launch_bounds__(kBlock) k_link(DLevel lo, DLevel up, const flo
         const float S = ((w0 + w1) + w2) + w3;
         if (S > 0.0f) w = make_float4(w0 / S, w1 / S, w2 / S, w3 / S);
     }
-    link_idx[i] = make_uint4(k0, k1, k2, k3);
-    link_w[i] = w;
+    link_idx[gi] = make_uint4(k0, k1, k2, k3);
+    link_w[gi] = w;
 }
 
 // far-field radiance of lower texel (dx, dy) from the merged upper level (S8)
@@ -115,8 +150,8 @@ __device__ __forceinline__ float4 far_field(const uint2* __restrict__ up_texels,
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint2* base = up_texels + idx[k] * UDD + (size_t)(2 * dy) * UD + 2 * dx;
-        const uint4 r0 = ldg_u4(reinterpret_cast<const uint4*>(base));        // children (2dx,2dy), (2dx+1,2dy)
-        const uint4 r1 = ldg_u4(reinterpret_cast<const uint4*>(base + UD));   // children (2dx,2dy+1), (2dx+1,2dy+1)
+        const uint4 r0 = ld_u4(base);        // children (2dx,2dy), (2dx+1,2dy)
+        const uint4 r1 = ld_u4(base + UD);   // children (2dx,2dy+1), (2dx+1,2dy+1)
         const float4 c0 = unpack_half4(make_uint2(r0.x, r0.y)), c1 = unpack_half4(make_uint2(r0.z, r0.w));
         const float4 c2 = unpack_half4(make_uint2(r1.x, r1.y)), c3 = unpack_half4(make_uint2(r1.z, r1.w));
         far.x = fmaf(wk[k], 0.25f * (((c0.x + c1.x) + c2.x) + c3.x), far.x);
@@ -130,22 +165,46 @@ __device__ __forceinline__ float4 far_field(const uint2* __restrict__ up_texels,
 // ------------------------------------------------------------------ march (+ fused merge)
 // One thread per texel in storage order: a warp = 32 consecutive directions of one probe
 // (level 0 with D0 = 4: two probes), so origins are shared and stores are one 256-byte segment.
-template <bool FUSED>
-__global__ void __launch_bounds__(kBlock) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky,
-                                                  const float4* __restrict__ origin, const float* __restrict__ dirs,
-                                                  uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
-                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
+// Thread -> texel mapping (the storage layout is always probe-major):
+//   MAP_LINEAR     storage order: a warp = 32 consecutive directions of one probe
+//   MAP_DIR_TILE   a warp = an 8x4 tile of directions of one probe (compact cone from a shared origin)
+//   MAP_PROBE_TILE a warp = one direction of an 8x4 tile of neighbouring probes (parallel rays, nearby origins)
+enum { MAP_LINEAR = 0, MAP_DIR_TILE = 1, MAP_PROBE_TILE = 2 };
+
+__device__ __forceinline__ bool decode_texel(const DLevel& lv, int map, size_t g, uint32_t& probe, uint32_t& d)
 {
-    const size_t DD = (size_t)lv.D * lv.D;
-    const size_t n = (size_t)lv.sw * lv.sh * DD;
-    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t probe = (uint32_t)(i / DD), d = (uint32_t)(i - (size_t)probe * DD);
-    const float4 og = __ldg(origin + probe);
-    if (og.w == 0.0f) { texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f); return; }   // invalid probe (S7)
-    const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
-    const float3 o = xyz(og);
-    const Hit h = trace(s, o, w, lv.t0, lv.t1);
+    const uint32_t DD = (uint32_t)(lv.D * lv.D);
+    if (map == MAP_PROBE_TILE) {
+        const uint32_t ntx = (uint32_t)(lv.sw + 7) >> 3, nty = (uint32_t)(lv.sh + 3) >> 2;
+        const size_t warp = g >> 5;
+        const uint32_t lane = (uint32_t)g & 31u;
+        const uint32_t ptile = (uint32_t)(warp / DD);
+        d = (uint32_t)(warp - (size_t)ptile * DD);
+        if (ptile >= ntx * nty) return false;
+        const uint32_t px = (ptile % ntx) * 8 + (lane & 7u), py = (ptile / ntx) * 4 + (lane >> 3);
+        if (px >= (uint32_t)lv.sw || py >= (uint32_t)lv.sh) return false;
+        probe = py * (uint32_t)lv.sw + px;
+        return true;
+    }
+    if (g >= (size_t)lv.sw * lv.sh * DD) return false;
+    probe = (uint32_t)(g / DD);
+    const uint32_t j = (uint32_t)(g - (size_t)probe * DD);
+    if (map == MAP_DIR_TILE) {
+        const uint32_t tile = j >> 5, lane = j & 31u, tpr = (uint32_t)lv.D >> 3;
+        d = ((tile / tpr) * 4 + (lane >> 3)) * (uint32_t)lv.D + (tile % tpr) * 8 + (lane & 7u);
+    } else {
+        d = j;
+    }
+    return true;
+}
+
+// S7 (+ S8 when fused): radiance of one texel from its closest hit, packed RGBA16F
+template <bool FUSED>
+__device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& L, const DLevel& lv, int UD, int top, float3 sky,
+                                                uint32_t probe, uint32_t d, float3 o, float3 w, const Hit& h,
+                                                const uint2* __restrict__ up_texels, const uint4* __restrict__ link_idx,
+                                                const float4* __restrict__ link_w)
+{
     float4 c;
     if (h.prim != 0xffffffffu) {
         const float3 P = vfma(h.t, w, o);
@@ -157,6 +216,10 @@ __global__ void __launch_bounds__(kBlock) k_march(DScene s, DLights L, DLevel lv
         c = make_float4(0.f, 0.f, 0.f, 1.0f);
     }
     if (FUSED && !top) {
+        // Programmatic dependent launch: this level's kernel may have started while level i+1's tail was
+        // still running; everything above (the whole ray march) is independent of it.  Wait here, right
+        // before the first read of level i+1's merged texels (no-op when launched without the PDL attribute).
+        cudaGridDependencySynchronize();
         // S8 applied to the float16-rounded raw texel (the same value the unfused path reads back)
         const float4 raw = unpack_half4(pack_half4(c.x, c.y, c.z, c.w));
         if (raw.w != 0.0f) {
@@ -168,7 +231,144 @@ __global__ void __launch_bounds__(kBlock) k_march(DScene s, DLights L, DLevel lv
             c = raw;   // a = 0: fma(0, far, raw) = raw exactly, the far field cannot contribute
         }
     }
-    texels[i] = pack_half4(c.x, c.y, c.z, c.w);
+    return pack_half4(c.x, c.y, c.z, c.w);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(512) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
+                                                  const float4* __restrict__ origin, const float* __restrict__ dirs,
+                                                  uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
+{
+    cudaTriggerProgrammaticLaunchCompletion();   // the next level's kernel may begin once every block got here
+    const size_t DD = (size_t)lv.D * lv.D;
+    uint32_t probe, d;
+    if (!decode_texel(lv, map, (size_t)blockIdx.x * blockDim.x + threadIdx.x, probe, d)) return;
+    const size_t i = (size_t)probe * DD + d;
+    const float4 og = __ldg(origin + probe);
+    if (og.w == 0.0f) { texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f); return; }   // invalid probe (S7)
+    const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+    const float3 o = xyz(og);
+    const Hit h = trace(s, o, w, lv.t0, lv.t1);
+    texels[i] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_texels, link_idx, link_w);
+}
+
+// ------------------------------------------------------------------ persistent march with ray replacement
+// One launch per level with a resident grid (148 SMs x blocks/SM).  Lanes fetch rays from a global
+// counter; when fewer than `thresh` lanes of a warp are still traversing, the finished lanes shade /
+// merge / store together and pull new rays (Aila & Laine's dynamic fetch with lane replacement): a
+// warp no longer idles 3/4 of its lanes behind its longest ray (ncu: 7.7-20.7 active lanes of 32 in
+// the one-ray-per-thread kernel).  Levels are chained with programmatic dependent launch: level i-1
+// starts filling SMs that level i's tail has vacated and only waits (cudaGridDependencySynchronize)
+// right before its first read of level i's merged texels.
+constexpr int kDone = (int)0x80000000;
+// Rays a warp takes from the global counter at a time.  A 1080p level is only ~440 rays per resident
+// warp, so the chunk must stay small for the tail to balance (512 made one chunk the critical path).
+constexpr unsigned long long kChunk = 64;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(128, 8) k_march_persist(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
+                                                          unsigned long long total, int thresh, unsigned int* __restrict__ counter,
+                                                          const float4* __restrict__ origin, const float* __restrict__ dirs,
+                                                          uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                          const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t DD = (size_t)lv.D * lv.D;
+    bool have = false, pend = false, exhausted = false, global_done = false, synced = !FUSED;
+    unsigned long long wnext = 0, wend = 0;   // warp-uniform chunk of ray indices
+    uint32_t probe = 0, d = 0;
+    float3 o = f3(0.f, 0.f, 0.f), w = o, inv = o, noi = o;
+    Hit h; h.t = 0.f; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+    int sp = 0, cur = kDone;
+    int stack[48];
+    for (;;) {
+        // (1) rays that finished in the last round: shade / merge / store together
+        if (__any_sync(FULL, pend)) {
+            if (!synced) { cudaGridDependencySynchronize(); synced = true; }   // level i+1 is complete and visible
+            if (pend) {
+                texels[(size_t)probe * DD + d] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_texels, link_idx, link_w);
+                pend = false;
+            }
+        }
+        // (2) refill free lanes: the warp owns a chunk [wnext, wend) of consecutive rays and takes a new
+        //     chunk from the global counter only when it runs dry (one same-address atomic per kChunk rays)
+        if (!exhausted) {
+            const unsigned freem = __ballot_sync(FULL, !have);
+            if (freem) {
+                if (wnext >= wend && !global_done) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = (unsigned long long)atomicAdd(counter, (unsigned)kChunk) ;
+                    base = __shfl_sync(FULL, base, 0);
+                    wnext = base;
+                    wend = base + kChunk < total ? base + kChunk : total;
+                    if (base >= total) { global_done = true; wnext = wend = 0; }
+                }
+                const unsigned rem = (unsigned)(wend - wnext);
+                const unsigned rank = (unsigned)__popc(freem & ((1u << lane) - 1u));
+                if (!have && rank < rem) {
+                    const unsigned long long g = wnext + rank;
+                    if (decode_texel(lv, map, (size_t)g, probe, d)) {
+                        const float4 og = __ldg(origin + probe);
+                        if (og.w == 0.0f) {
+                            texels[(size_t)probe * DD + d] = pack_half4(0.f, 0.f, 0.f, 1.f);   // invalid probe (S7)
+                        } else {
+                            o = xyz(og);
+                            w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+                            inv = f3(safe_inv(w.x), safe_inv(w.y), safe_inv(w.z));
+                            noi = f3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+                            h.t = lv.t1; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+                            sp = 0; cur = 0; have = true;
+                        }
+                    }
+                }
+                const unsigned want = (unsigned)__popc(freem);
+                wnext += want < rem ? want : rem;
+                if (global_done) exhausted = true;
+            }
+        }
+        // (3) traverse until too few lanes are left busy
+        unsigned act = __ballot_sync(FULL, have);
+        if (act == 0u) { if (exhausted) break; continue; }
+        const int lim = exhausted ? 1 : thresh;
+        do {
+            if (have) {
+                if (cur >= 0) {
+                    const float4* n = s.nodes + 4 * (size_t)cur;
+                    const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+                    float ax = fmaf(q0.x, inv.x, noi.x), bx = fmaf(q0.w, inv.x, noi.x);
+                    float ay = fmaf(q0.y, inv.y, noi.y), by = fmaf(q1.x, inv.y, noi.y);
+                    float az = fmaf(q0.z, inv.z, noi.z), bz = fmaf(q1.y, inv.z, noi.z);
+                    const float n0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), lv.t0));
+                    const float f0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+                    ax = fmaf(q1.z, inv.x, noi.x); bx = fmaf(q2.y, inv.x, noi.x);
+                    ay = fmaf(q1.w, inv.y, noi.y); by = fmaf(q2.z, inv.y, noi.y);
+                    az = fmaf(q2.x, inv.z, noi.z); bz = fmaf(q2.w, inv.z, noi.z);
+                    const float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), lv.t0));
+                    const float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+                    const bool hit0 = n0 <= f0, hit1 = n1 <= f1;
+                    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+                    if (hit0 && hit1) {
+                        if (n1 < n0) { const int t = c0; c0 = c1; c1 = t; }
+                        stack[sp++] = c1;
+                        cur = c0;
+                    } else if (hit0) cur = c0;
+                    else if (hit1) cur = c1;
+                    else cur = sp ? stack[--sp] : kDone;
+                }
+                if (cur < 0 && cur != kDone) {
+                    const uint32_t leaf = (uint32_t)~cur;
+                    const uint32_t first = leaf >> 3, cnt = leaf & 7u;
+                    for (uint32_t k = 0; k < cnt; k++) tri_test(s.tri_geom + 3 * (size_t)(first + k), o, w, lv.t0, lv.t1, h);
+                    cur = sp ? stack[--sp] : kDone;
+                }
+                if (cur == kDone) { have = false; pend = true; }
+            }
+            act = __ballot_sync(FULL, have);
+        } while (__popc(act) >= lim);
+    }
 }
 
 // ------------------------------------------------------------------ stand-alone merge (in place)
@@ -313,27 +513,74 @@ void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileR
     k_gbuffer<<<grid, kBlock, 0, st>>>(s, cam, L, tile, out);
 }
 
-void launch_probes(const DScene& s, const DCamera& cam, const DLevel& lv, float offset, float4* origin, float4* normal, cudaStream_t st)
+void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
+                   const float* depth, const uint32_t* prim, float4* origin, float4* normal, cudaStream_t st)
 {
-    k_probes<<<blocks_for((size_t)lv.sw * lv.sh), kBlock, 0, st>>>(s, cam, lv, offset, origin, normal);
+    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal);
 }
 
-void launch_link(const DLevel& lo, const DLevel& up, const float4* lo_origin, const float4* lo_normal,
-                 const float4* up_origin, uint4* link_idx, float4* link_w, cudaStream_t st)
+void launch_link(const DLevelSet& ls, unsigned total, const float4* origin, const float4* normal, uint4* link_idx,
+                 float4* link_w, cudaStream_t st)
 {
-    k_link<<<blocks_for((size_t)lo.sw * lo.sh), kBlock, 0, st>>>(lo, up, lo_origin, lo_normal, up_origin, link_idx, link_w);
+    if (total) k_link<<<blocks_for(total), kBlock, 0, st>>>(ls, total, origin, normal, link_idx, link_w);
 }
 
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
-                  const uint4* link_idx, const float4* link_w, bool fused, cudaStream_t st)
+                  const uint4* link_idx, const float4* link_w, bool fused, int map, int block, bool pdl, cudaStream_t st)
 {
-    const size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
+    if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;   // the 8x4 direction tile needs D % 8 == 0
+    size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
+    if (map == MAP_PROBE_TILE) n = (size_t)((lv.sw + 7) / 8) * ((lv.sh + 3) / 4) * lv.D * lv.D * 32;
     const int UD = up ? up->D : 0;
+    const int topi = top ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((n + block - 1) / block));
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && fused && !top) ? 1 : 0;   // only a kernel that waits on its predecessor may start early
     if (fused && !top)
-        k_march<true><<<blocks_for(n), kBlock, 0, st>>>(s, L, lv, UD, 0, sky, origin, dirs, texels, up_texels, link_idx, link_w);
+        cudaLaunchKernelEx(&cfg, k_march<true>, s, L, lv, UD, 0, sky, map, origin, dirs, texels, up_texels, link_idx, link_w);
     else
-        k_march<false><<<blocks_for(n), kBlock, 0, st>>>(s, L, lv, UD, top ? 1 : 0, sky, origin, dirs, texels, up_texels, link_idx, link_w);
+        cudaLaunchKernelEx(&cfg, k_march<false>, s, L, lv, UD, topi, sky, map, origin, dirs, texels, up_texels, link_idx, link_w);
+}
+
+void launch_march_persist(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
+                          const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
+                          const uint4* link_idx, const float4* link_w, bool fused, int map, int thresh, int grid_blocks,
+                          unsigned int* counter, bool pdl, cudaStream_t st)
+{
+    if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;
+    unsigned long long n = (unsigned long long)lv.sw * lv.sh * lv.D * lv.D;
+    if (map == MAP_PROBE_TILE) n = (unsigned long long)((lv.sw + 7) / 8) * ((lv.sh + 3) / 4) * lv.D * lv.D * 32ull;
+    const int UD = up ? up->D : 0;
+    const int topi = top ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid_blocks);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (fused && !top)
+        cudaLaunchKernelEx(&cfg, k_march_persist<true>, s, L, lv, UD, 0, sky, map, n, thresh, counter, origin, dirs, texels, up_texels, link_idx, link_w);
+    else
+        cudaLaunchKernelEx(&cfg, k_march_persist<false>, s, L, lv, UD, topi, sky, map, n, thresh, counter, origin, dirs, texels, up_texels, link_idx, link_w);
+}
+
+int march_persist_blocks_per_sm()
+{
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_march_persist<true>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_march_persist<false>, 128, 0);
+    return a < b ? a : b;
 }
 
 void launch_merge(const DLevel& lv, const DLevel& up, const float4* origin, uint2* texels, const uint2* up_texels,

@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -104,6 +105,7 @@ struct rc_ctx {
     DevBuf<uint2> d_albedo, d_direct, d_irr;
     DevBuf<uchar4> d_composite, d_direct_srgb;
     DevBuf<float> d_dbg_in, d_dbg_out;
+    DevBuf<unsigned int> d_counters;     // per-level ray-fetch counters of the persistent march
 
     DCamera cam{};
     DLights lights{};
@@ -115,6 +117,10 @@ struct rc_ctx {
     bool ev_recorded = false;
     uint32_t launches = 0;
     cudaStream_t last_stream = nullptr;
+    int march_map[RC_MAX_LEVELS];   // thread->texel mapping per level (kernels.cu MAP_*)
+    int march_block = 128;
+    int march_persist = 0, march_thresh = 8, march_grid = 0, march_pdl = 1;   // persistent variant measured slower
+    bool level_timing = false;
 
     bool fail(rc_status, const std::string& m) { error = m; return false; }
 };
@@ -460,7 +466,7 @@ void destroy_ctx(rc_ctx* c)
     c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release();
     c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_direct.release(); c->d_irr.release(); c->d_composite.release(); c->d_direct_srgb.release();
-    c->d_dbg_in.release(); c->d_dbg_out.release();
+    c->d_dbg_in.release(); c->d_dbg_out.release(); c->d_counters.release();
     delete c;
 }
 
@@ -504,6 +510,25 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
     if (st == RC_OK) st = load_scene(c);
     if (st == RC_OK) st = setup_frame(c, cfg->width, cfg->height);
     if (st != RC_OK) { g_create_error = c->error; destroy_ctx(c); return st; }
+    {   // tuning knobs (A/B runs): RC_MARCH_MAP = one char per level, L linear / D direction tile / P probe tile
+        const char* mm = getenv("RC_MARCH_MAP");
+        for (uint32_t i = 0; i < RC_MAX_LEVELS; i++) {
+            int def = 1;   // direction tiles
+            char ch = (mm && strlen(mm) > i) ? mm[i] : 0;
+            c->march_map[i] = ch == 'L' ? 0 : ch == 'D' ? 1 : ch == 'P' ? 2 : def;
+        }
+        const char* mb = getenv("RC_MARCH_BLOCK");
+        if (mb && (atoi(mb) == 64 || atoi(mb) == 128 || atoi(mb) == 256 || atoi(mb) == 512)) c->march_block = atoi(mb);
+        if (const char* e = getenv("RC_MARCH_PERSIST")) c->march_persist = atoi(e);
+        if (const char* e = getenv("RC_MARCH_THRESH")) c->march_thresh = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
+        if (const char* e = getenv("RC_MARCH_PDL")) c->march_pdl = atoi(e);
+        cudaDeviceProp prop;
+        int bps = march_persist_blocks_per_sm();
+        if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && bps > 0) c->march_grid = prop.multiProcessorCount * bps;
+        else c->march_persist = 0;
+        if (const char* e = getenv("RC_MARCH_GRID")) if (atoi(e) > 0) c->march_grid = atoi(e);
+        if (c->d_counters.alloc(RC_MAX_LEVELS) != cudaSuccess) c->march_persist = 0;
+    }
     c->lights.n = 1;    // AppState::light_position default [0,0,0] (src/app.rs)
     c->lights.flags = RC_UPD_ENABLE_NORMAL_MAP;
     *out = c;
@@ -544,21 +569,22 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     c->last_stream = st;
     c->launches = 0;
+    if (c->march_persist) CU_OK(c, cudaMemsetAsync(c->d_counters.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
     c->composite_valid = false;
     CU_OK(c, cudaEventRecord(c->ev[EV_START], st));
     GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_albedo.p, c->d_direct.p};
     launch_gbuffer(c->scene, c->cam, c->lights, c->tile, gb, st);
     c->launches++;
     CU_OK(c, cudaEventRecord(c->ev[EV_GBUF], st));
-    for (uint32_t i = 0; i < c->N; i++) {
-        const DLevel& L = c->levels[i];
-        launch_probes(c->scene, c->cam, L, c->offset, c->d_origin.p + L.probe_offset, c->d_normal.p + L.probe_offset, st);
-        c->launches++;
-    }
-    for (uint32_t i = 0; i + 1 < c->N; i++) {
-        const DLevel &L = c->levels[i], &U = c->levels[i + 1];
-        launch_link(L, U, c->d_origin.p + L.probe_offset, c->d_normal.p + L.probe_offset, c->d_origin.p + U.probe_offset,
-                    c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
+    DLevelSet ls;
+    ls.n = (int)c->N;
+    for (uint32_t i = 0; i < c->N; i++) ls.lv[i] = c->levels[i];
+    const DLevel& top = c->levels[c->N - 1];
+    const unsigned n_probes = top.probe_offset + (unsigned)(top.sw * top.sh);
+    launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p, st);
+    c->launches++;
+    if (c->N > 1) {
+        launch_link(ls, top.probe_offset, c->d_origin.p, c->d_normal.p, c->d_link_idx.p, c->d_link_w.p, st);
         c->launches++;
     }
     CU_OK(c, cudaEventRecord(c->ev[EV_PROBES], st));
@@ -577,15 +603,37 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     const float3 sky = make_float3(c->cfg.sky[0], c->cfg.sky[1], c->cfg.sky[2]);
     uint2* tex = c->d_cascade.p + L.texel_offset;
     const uint2* up = top ? nullptr : c->d_cascade.p + U->texel_offset;
-    launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
-                 c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, st);
+    if (c->march_persist)
+        launch_march_persist(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
+                             c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_thresh,
+                             c->march_grid, c->d_counters.p + level, c->march_pdl && fused && !top, st);
+    else
+        launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
+                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_block, c->march_pdl != 0, st);
     c->launches++;
     if (!fused && !top) {
         launch_merge(L, *U, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
         c->launches++;
     }
-    CU_OK(c, cudaEventRecord(c->ev_level[level], st));
+    // per-level events sit between the level kernels and would defeat their PDL overlap: opt-in only
+    if (c->level_timing) CU_OK(c, cudaEventRecord(c->ev_level[level], st));
     CU_OK(c, cudaGetLastError());
+    return RC_OK;
+}
+
+rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
+{
+    if (!c || !key) return RC_ERR_INVALID_ARG;
+    const std::string k = key;
+    if (k == "level_timing") c->level_timing = value != 0;
+    else if (k == "march_persist") c->march_persist = (value != 0 && c->march_grid > 0 && c->d_counters.p) ? 1 : 0;
+    else if (k == "march_thresh") c->march_thresh = value < 1 ? 1 : (value > 32 ? 32 : value);
+    else if (k == "march_pdl") c->march_pdl = value != 0;
+    else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
+    else if (k == "march_grid" && value > 0) c->march_grid = value;
+    else if (k.rfind("march_map", 0) == 0 && k.size() == 10 && k[9] >= '0' && k[9] <= '9' && value >= 0 && value <= 2)
+        c->march_map[k[9] - '0'] = value;
+    else { c->error = "rc_set_tuning: unknown key or bad value: " + k; return RC_ERR_INVALID_ARG; }
     return RC_OK;
 }
 
@@ -693,7 +741,7 @@ rc_status rc_stage_times(rc_ctx* c, float* ms, uint32_t n)
 rc_status rc_level_times(rc_ctx* c, float* ms, uint32_t n)
 {
     if (!c || !ms) return RC_ERR_INVALID_ARG;
-    if (!c->ev_recorded) { c->error = "rc_level_times before rc_render"; return RC_ERR_STATE; }
+    if (!c->ev_recorded || !c->level_timing) { c->error = "rc_level_times needs rc_set_tuning(level_timing, 1) and a rendered frame"; return RC_ERR_STATE; }
     cudaSetDevice(c->device);
     CU_OK(c, cudaEventSynchronize(c->ev[EV_GATHER]));
     for (uint32_t i = 0; i < n && i < c->N; i++) {

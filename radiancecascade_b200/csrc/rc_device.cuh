@@ -49,6 +49,8 @@ struct DLevel {
     unsigned int probe_offset;        // probes before this level in the probe arrays
 };
 
+struct DLevelSet { DLevel lv[RC_MAX_LEVELS]; int n; };
+
 // ------------------------------------------------------------------ spec arithmetic
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
 __device__ __forceinline__ float3 vsub(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -109,44 +111,46 @@ __device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float 
     Hit h; h.t = tmax; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
     const float3 inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     const float3 noi = f3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+    // True while-while (Aila & Laine): every lane descends inner nodes until it holds a leaf (or is
+    // done); the warp reconverges at the end of the node loop and tests triangles together.  The
+    // earlier "one node, then drain leaves" shape ran 57% of the kernel's warp-instructions — the
+    // triangle tests — with 1.5-3 active lanes (profiles/r1_a_*).
+    constexpr int kDoneLink = (int)0x80000000;   // never a real leaf code (first < 2^28)
     int stack[48];
     int sp = 0;
     int cur = 0;
-    while (true) {
-        const float4* n = s.nodes + 4 * (size_t)cur;
-        const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
-        // child 0 slabs
-        float ax = fmaf(q0.x, inv.x, noi.x), bx = fmaf(q0.w, inv.x, noi.x);
-        float ay = fmaf(q0.y, inv.y, noi.y), by = fmaf(q1.x, inv.y, noi.y);
-        float az = fmaf(q0.z, inv.z, noi.z), bz = fmaf(q1.y, inv.z, noi.z);
-        float n0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
-        float f0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
-        // child 1 slabs
-        ax = fmaf(q1.z, inv.x, noi.x); bx = fmaf(q2.y, inv.x, noi.x);
-        ay = fmaf(q1.w, inv.y, noi.y); by = fmaf(q2.z, inv.y, noi.y);
-        az = fmaf(q2.x, inv.z, noi.z); bz = fmaf(q2.w, inv.z, noi.z);
-        float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
-        float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
-        const bool hit0 = n0 <= f0, hit1 = n1 <= f1;   // <=: equal-t candidates stay reachable for the id tie-break
-        int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-        int next;
-        if (hit0 && hit1) {
-            if (n1 < n0) { int t = c0; c0 = c1; c1 = t; }
-            stack[sp++] = c1;
-            next = c0;
-        } else if (hit0) next = c0;
-        else if (hit1) next = c1;
-        else { if (sp == 0) break; next = stack[--sp]; }
-        bool done = false;
-        while (next < 0) {
-            const uint32_t leaf = (uint32_t)~next;
+    while (cur != kDoneLink) {
+        while (cur >= 0) {
+            const float4* n = s.nodes + 4 * (size_t)cur;
+            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+            // child 0 slabs
+            float ax = fmaf(q0.x, inv.x, noi.x), bx = fmaf(q0.w, inv.x, noi.x);
+            float ay = fmaf(q0.y, inv.y, noi.y), by = fmaf(q1.x, inv.y, noi.y);
+            float az = fmaf(q0.z, inv.z, noi.z), bz = fmaf(q1.y, inv.z, noi.z);
+            const float n0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+            const float f0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+            // child 1 slabs
+            ax = fmaf(q1.z, inv.x, noi.x); bx = fmaf(q2.y, inv.x, noi.x);
+            ay = fmaf(q1.w, inv.y, noi.y); by = fmaf(q2.z, inv.y, noi.y);
+            az = fmaf(q2.x, inv.z, noi.z); bz = fmaf(q2.w, inv.z, noi.z);
+            const float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+            const float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+            const bool hit0 = n0 <= f0, hit1 = n1 <= f1;   // <=: equal-t candidates stay reachable for the id tie-break
+            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            if (hit0 && hit1) {
+                if (n1 < n0) { const int t = c0; c0 = c1; c1 = t; }
+                stack[sp++] = c1;
+                cur = c0;
+            } else if (hit0) cur = c0;
+            else if (hit1) cur = c1;
+            else cur = sp ? stack[--sp] : kDoneLink;
+        }
+        while (cur < 0 && cur != kDoneLink) {
+            const uint32_t leaf = (uint32_t)~cur;
             const uint32_t first = leaf >> 3, cnt = leaf & 7u;
             for (uint32_t i = 0; i < cnt; i++) tri_test(s.tri_geom + 3 * (size_t)(first + i), o, d, tmin, tmax, h);
-            if (sp == 0) { done = true; break; }
-            next = stack[--sp];
+            cur = sp ? stack[--sp] : kDoneLink;
         }
-        if (done) break;
-        cur = next;
     }
     if (h.prim == 0xffffffffu) h.t = -1.0f;
     return h;

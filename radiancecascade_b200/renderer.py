@@ -269,6 +269,9 @@ class DefaultRenderer:
         self._check(self._lib.rc_level_times(self._h, ms, n))
         return [float(x) for x in ms]
 
+    def set_tuning(self, key: str, value: int) -> None:
+        self._check(self._lib.rc_set_tuning(self._h, key.encode(), int(value)))
+
     def launch_count(self) -> int:
         n = C.c_uint32()
         self._check(self._lib.rc_launch_count(self._h, C.byref(n)))
