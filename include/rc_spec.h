@@ -83,8 +83,11 @@
  *   position fma(t, w, origin); textures sampled at the NEAREST texel with
  *   MirrorRepeat addressing (the reference's min filter; a ray has no
  *   derivatives); sRGB decode through a 256-entry table computed in double;
- *   pow(x, Ns) with C powf semantics (pow(x,0) = 1); diffuse and specular summed
- *   over lights; no shadow rays (the reference has none).
+ *   pow(x, Ns) with C powf semantics (pow(x,0) = 1); max(x,0) with C fmaxf semantics
+ *   (a NaN operand yields 0: WGSL leaves max(NaN,0) to the implementation; the cube's
+ *   NaN tangents exercise this); every radiance component is finally clamped to
+ *   [0, 65504] with NaN -> 0; diffuse and specular summed over lights; no shadow
+ *   rays (the reference has none).
  *
  * ---- S8. merge (level i+1 -> i, i = N-2 .. 0) ------------------------------
  *   for the 4 upper probes k (S1) of probe p:
@@ -101,7 +104,12 @@
  *   pixel (x,y) with geometry: shading normal n = decode of the stored snorm16
  *   octahedral normal; h = hit point; the 4 level-0 probes k with weights as in S8
  *   using n_p := n, o_p := h.
- *   E = sum_k (w_k/S) * (4*pi/D0^2) * sum_d max(dot(n, w_d), 0) * c_k,d.rgb   (d in storage order, fma accumulation)
+ *   cs_d = max(dot(n, w_d), 0);  C = sum_d cs_d (d in storage order, plain adds);  q = C > 0 ? pi / C : 0
+ *   E = sum_k ((w_k/S) * q) * sum_d cs_d * c_k,d.rgb      (d in storage order, fma accumulation; k = 0..3, fma)
+ *   The cosine lobe is integrated with NORMALISED weights (q instead of 4*pi/D0^2): with D0 = 4
+ *   half of the upper-hemisphere texel centres lie on the equator and the plain midpoint rule
+ *   returns 0.75*pi for a uniform environment; normalising makes a constant radiance field L
+ *   gather to exactly pi*L for every normal (tests/test_oracle_gi.py).
  *   output float16 (E.rgb, 1); pixels without geometry: (0,0,0,0).
  *
  * ---- S10. tolerances ---------------------------------------------------------

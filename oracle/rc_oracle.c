@@ -671,7 +671,6 @@ void rco_gather(const rco_params* p, const float cam[20],
     float b[9]; rco_primary_basis(cam, b);
     v3 eye = V(cam[16], cam[17], cam[18]);
     int DD = L.D * L.D;
-    float dw = 4.0f * 3.14159274101257324219f / (float)DD;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int ty = 0; ty < p->tile_h; ty++) for (int tx = 0; tx < p->tile_w; tx++) {
         int x = p->tile_x0 + tx, y = p->tile_y0 + ty;
@@ -701,6 +700,11 @@ void rco_gather(const rco_params* p, const float cam[20],
         }
         float S = ((w[0] + w[1]) + w[2]) + w[3];
         float E[3] = { 0, 0, 0 };
+        /* S9: normalised cosine quadrature, q = pi / sum_d max(n.w_d, 0) */
+        float csum = 0.0f;
+        for (int di = 0; di < DD; di++)
+            csum = csum + fmaxf(vdot(n, V(dirs0[3 * di], dirs0[3 * di + 1], dirs0[3 * di + 2])), 0.0f);
+        const float dw = csum > 0.0f ? 3.14159274101257324219f / csum : 0.0f;
         if (S > 0.0f) {
             for (int k = 0; k < 4; k++) {
                 float wk = w[k] / S;

@@ -574,10 +574,10 @@ def fs_main(P, color, Nv, Tv, Bv, uv, umat, ebit, eye, lights, color_tex=None, n
         N = np.where(ndv[..., None] < 0, -raw, raw)                                     # :89
         for lp in np.asarray(lights, dtype=F).reshape(-1, 3):
             Ld = _normalize((lp - P).astype(F))                                         # :91
-            ndl = np.maximum(_dot(Ld, N), F(0.0))                                       # :92
+            ndl = np.fmax(_dot(Ld, N), F(0.0))      # :92  max() with C fmaxf semantics: NaN -> 0 (rc_spec.h S7)
             L = (L + ((Kd[:3] * F(0.7)).astype(F) * ndl[..., None] * Kd[3]).astype(F)).astype(F)  # :93
             Hd = _normalize((V + Ld).astype(F))                                         # :95
-            s = np.power(np.maximum(_dot(N, Hd), F(0.0)), F(Ns)).astype(F)              # :96
+            s = np.power(np.fmax(_dot(N, Hd), F(0.0)), F(Ns)).astype(F)                 # :96
             gate = (ndv > F(1e-6)).astype(F)
             L = (L + (Ks[:3] * s[..., None] * Ks[3] * gate[..., None]).astype(F)).astype(F)  # :97
         pred = ((Ka[:3] - F(1e-5)) + (Kd[:3] - F(1e-5)) + (Ks[:3] - F(1e-5))).astype(F)  # :99

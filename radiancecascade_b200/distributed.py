@@ -1,0 +1,150 @@
+"""Multi-GPU partitioning of the GI path: one process per GPU.
+
+Two ways to shard, both with a replicated scene (every bundled scene is < 4 MB on device):
+
+* multi-view batch — each rank renders whole frames of its own views; no data-path
+  collective at all (bench.py's default for N > 1, "weak" scaling);
+* screen-space tiles — one frame is cut into horizontal strips; each rank renders its
+  strip with the upper-cascade halo recomputed locally (rc_config.tile_*; bit-identical to
+  the single-GPU frame, tests/test_gpu_parity.py::test_tile_equals_full_frame_crop) and the
+  finished strips are exchanged with ONE collective, an NCCL all-gather of the RGBA16F
+  irradiance strips (66 MB in total at 4K) over NVLink/NVSwitch.
+
+The collective is torch.distributed plumbing; rendering is librc_b200.so.  On CPU (gloo)
+only the host-side logic below runs — there is no CPU rendering path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+Tile = Tuple[int, int, int, int]  # x0, y0, w, h
+
+
+def partition_strips(width: int, height: int, n: int, align: int = 4) -> List[Tile]:
+    """`n` horizontal strips covering the frame exactly; heights differ by at most `align`
+    rows (strip boundaries sit on multiples of `align`, the level-0 probe spacing, so that
+    neighbouring strips share as few level-0 probes as possible)."""
+    if n < 1 or height < n:
+        raise ValueError("cannot cut %d rows into %d strips" % (height, n))
+    units = -(-height // align)            # rows in units of `align`
+    if units < n:
+        align, units = 1, height
+    base, extra = divmod(units, n)
+    tiles, y = [], 0
+    for r in range(n):
+        rows = (base + (1 if r < extra else 0)) * align
+        rows = min(rows, height - y)
+        if r == n - 1:
+            rows = height - y
+        tiles.append((0, y, width, rows))
+        y += rows
+    assert y == height and all(t[3] > 0 for t in tiles)
+    return tiles
+
+
+def partition_grid(width: int, height: int, nx: int, ny: int, align: int = 4) -> List[Tile]:
+    """nx x ny tiles (row-major rank order); the 2-D cut halves the cumulative halo of strips
+    at 8 GPUs (4x2 tiles ~30 % redundant work vs ~56 % for 8 strips at 4K)."""
+    cols = [(t[1], t[3]) for t in partition_strips(1, width, nx, align)]
+    rows = [(t[1], t[3]) for t in partition_strips(1, height, ny, align)]
+    return [(cx, ry, cw, rh) for (ry, rh) in rows for (cx, cw) in cols]
+
+
+def halo_overhead(width: int, height: int, tiles: Sequence[Tile], p0: int = 4, levels: int = 6) -> float:
+    """Redundant work of halo recomputation: (probe-directions summed over tiles) / (full frame) - 1,
+    from the same footprint recursion librc_b200 uses (rc_spec.h S1)."""
+    from math import ceil
+
+    def rects(tile):
+        x0, y0, w, h = tile
+        out = []
+        xr = yr = None
+        for i in range(levels):
+            P = p0 << i
+            gw, gh = ceil(width / P), ceil(height / P)
+            if i == 0:
+                xr = (max(0, min((x0 - p0 // 2) // p0, gw - 1)), max(0, min((x0 + w - 1 - p0 // 2) // p0 + 1, gw - 1)))
+                yr = (max(0, min((y0 - p0 // 2) // p0, gh - 1)), max(0, min((y0 + h - 1 - p0 // 2) // p0 + 1, gh - 1)))
+            else:
+                lo = lambda q: q // 2 - 1 if q % 2 == 0 else (q - 1) // 2
+                xr = (max(0, min(lo(xr[0]), gw - 1)), max(0, min(lo(xr[1]) + 1, gw - 1)))
+                yr = (max(0, min(lo(yr[0]), gh - 1)), max(0, min(lo(yr[1]) + 1, gh - 1)))
+            out.append((xr[1] - xr[0] + 1) * (yr[1] - yr[0] + 1) * (4 ** i))
+        return out
+
+    full = sum(rects((0, 0, width, height)))
+    return sum(sum(rects(t)) for t in tiles) / full - 1.0
+
+
+class _DevicePtr:
+    """Zero-copy view of a device buffer owned by librc_b200 (consumed by torch.as_tensor)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def irradiance_tensor(renderer):
+    """torch view (float16 [h][w][4]) of the renderer's irradiance tile in HBM — no copy."""
+    import torch
+    ptr, nbytes = renderer.irradiance_device_ptr()
+    w, h = renderer.tile_size()
+    assert nbytes == w * h * 8
+    return torch.as_tensor(_DevicePtr(ptr, (h, w, 4), "<f2"), device="cuda")
+
+
+def assemble_strips(parts: Sequence[np.ndarray], tiles: Sequence[Tile], width: int, height: int) -> np.ndarray:
+    """Host-side assembly of per-rank tiles into the full frame (also the checker of the collective)."""
+    ch = parts[0].shape[-1]
+    out = np.zeros((height, width, ch), dtype=parts[0].dtype)
+    for p, (x0, y0, w, h) in zip(parts, tiles):
+        out[y0:y0 + h, x0:x0 + w] = p[:h, :w]
+    return out
+
+
+def all_gather_tiles(local, tiles: Sequence[Tile], width: int, height: int, group=None):
+    """The one collective of tiled mode: all-gather of the ranks' irradiance tiles.  `local` is a
+    torch tensor [h][w][4] on the backend's device (cuda for nccl, cpu for gloo).  Tiles are padded
+    to the largest tile so a single all_gather_into_tensor moves everything; returns the assembled
+    [height][width][4] tensor on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert world == len(tiles)
+    mh = max(t[3] for t in tiles)
+    mw = max(t[2] for t in tiles)
+    pad = torch.zeros((mh, mw, local.shape[-1]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0], :local.shape[1]] = local
+    # concatenated along dim 0 (the layout both nccl and gloo accept), viewed per rank below
+    gathered = torch.empty((world * mh, mw, local.shape[-1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, pad, group=group)
+    gathered = gathered.view(world, mh, mw, local.shape[-1])
+    full = torch.zeros((height, width, local.shape[-1]), dtype=local.dtype, device=local.device)
+    for r, (x0, y0, w, h) in enumerate(tiles):
+        full[y0:y0 + h, x0:x0 + w] = gathered[r, :h, :w]
+    return full
+
+
+class TiledRenderer:
+    """One rank's share of a tiled frame: a DefaultRenderer restricted to this rank's tile plus the
+    final all-gather.  Needs a CUDA device (no CPU fallback)."""
+
+    def __init__(self, rank: int, world: int, device: int, size: Tuple[int, int], state, path: str,
+                 cascade=None, grid: Optional[Tuple[int, int]] = None):
+        from .renderer import CascadeConfig, DefaultRenderer
+        W, H = size
+        self.tiles = partition_grid(W, H, *grid) if grid else partition_strips(W, H, world)
+        self.rank, self.world, self.size = rank, world, (W, H)
+        cc = cascade or CascadeConfig()
+        cc.tile = self.tiles[rank]
+        self.renderer = DefaultRenderer.new(device, (W, H), state, path, cc)
+
+    def render(self, state, stream: Optional[int] = None):
+        self.renderer.update(state)
+        self.renderer.render(stream)
+
+    def gather(self, group=None):
+        """NCCL all-gather of the finished tiles; returns the full frame (torch, cuda, float16)."""
+        self.renderer.synchronize()
+        return all_gather_tiles(irradiance_tensor(self.renderer), self.tiles, *self.size, group=group)

@@ -1,0 +1,109 @@
+"""Scene ingest: the product's C++ loader (rc_scene_*, device-free) against
+the numpy restatement of the reference (oracle/ref_ingest.py) and against the committed golden
+hashes (tests/golden/ingest_golden.json, tools/make_golden.py).  Bit-exact."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import radiancecascade_b200 as rc
+from oracle import ref_ingest as ri
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ingest_golden.json")))
+SCENES = sorted(rc.scenes.SCENES)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def same_bits(a, b):
+    return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_product_loader_matches_golden_and_oracle(name):
+    hs = rc.ObjScene.load(rc.scenes.scene_path(name))
+    info = hs.info()
+    g = GOLD[name]
+    assert info.num_models == len(g["models"])
+    assert info.num_vertices == g["total_vertices"] and info.num_triangles == g["total_triangles"]
+    assert [float(x) for x in info.bbox_min] == g["bbox_min"] and [float(x) for x in info.bbox_max] == g["bbox_max"]
+    assert bool(info.light_from_obj) == (g["light"] is not None)    # no bundled scene has a material named "Light"
+    osc, _ = ri.ObjScene.load(rc.scenes.scene_path(name))
+    for m, gm in enumerate(g["models"]):
+        v, i = hs.model_stream(m)
+        assert hs.model_name(m) == gm["name"]
+        assert (len(v), len(i)) == (gm["vertices"], gm["indices"])
+        assert sha(v) == gm["stream_sha256"], (name, m, "vertex stream")      # src/renderer.rs:371-410
+        assert sha(i) == gm["index_sha256"], (name, m, "index buffer")        # src/primitives.rs:369-376
+        assert same_bits(v, osc[m].vertex_stream())
+        um, eb, ke = hs.model_material(m)
+        assert [float(x) for x in um] == gm["uniform_material"] and eb == gm["enable_bit"]   # src/primitives.rs:37-73
+        assert [float(x) for x in ke] == gm["emission"]
+        for which, key in ((0, "color_texture_sha256"), (1, "normal_texture_sha256")):
+            t = hs.model_texture(m, which)
+            assert (None if t is None else sha(t)) == gm[key]                 # src/texture.rs:85-147 (to_rgba8)
+
+
+def test_survey_counts():
+    """Counts of SURVEY Appendix B; living_room additionally carries the 5,869 `l` elements that tobj's
+    triangulate turns into zero-area triangles (a,b,b) — the survey counted `f` lines only."""
+    want = {"cube": (277, 428, 1), "teapot": (8334, 15704, 2), "test_room": (248, 152, 2), "sonic": (10280, 17298, 13),
+            "living_room": (46167, 28656 + 5869, 41)}
+    for name, (nv, nt, nm) in want.items():
+        g = GOLD[name]
+        assert (g["total_vertices"], g["total_triangles"], len(g["models"])) == (nv, nt, nm)
+
+
+def test_winding_is_reversed_and_tbn_fallbacks():
+    osc, _ = ri.ObjScene.load(rc.scenes.scene_path("sonic"))     # no texcoords usable for most models, no mtllib
+    m = osc[0]
+    raw = m.model.indices.reshape(-1, 3)
+    assert np.array_equal(m.indices().reshape(-1, 3), raw[:, ::-1])
+    assert m.materials is None and ri.enable_bit(m.material()) == 0
+    um = ri.uniform_material(None)
+    assert um[12] == 1.0 and not um[:12].any()                  # Material::default(): Ns -> 1.0, all K absent
+    # teapot has no `vn`: the stream's normal column is the tbn normal (zip_longest Right branch)
+    tp, _ = ri.ObjScene.load(rc.scenes.scene_path("teapot"))
+    T, B, N = tp[0].tbn()
+    assert len(tp[0].normals()) == 0 and same_bits(tp[0].vertex_stream()[:, 6:9], N)
+
+
+def test_line_elements_make_degenerate_triangles():
+    lr, _ = ri.ObjScene.load(rc.scenes.scene_path("living_room"))
+    last = lr[-1]
+    ix = last.model.indices.reshape(-1, 3)
+    degenerate = (ix[:, 1] == ix[:, 2])
+    assert degenerate.sum() == 5869
+    assert len(last.texcoords()) == 0          # lengths disagree -> texcoords() returns [] (src/primitives.rs:356-367)
+
+
+def test_missing_mtl_is_an_error(tmp_path):
+    p = tmp_path / "a.obj"
+    p.write_text("mtllib nothere.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    with pytest.raises(rc.RcError):
+        rc.ObjScene.load(str(p))
+    with pytest.raises(FileNotFoundError):
+        ri.load_obj(str(p))
+
+
+def test_small_obj_semantics(tmp_path):
+    """Fan triangulation, negative indices, per-model re-indexing, usemtl split — product vs oracle."""
+    (tmp_path / "m.mtl").write_text("newmtl A\nKd 1 0 0\nnewmtl Light\nKa 1 1 1\nKe 2 2 2\n")
+    p = tmp_path / "s.obj"
+    p.write_text("mtllib m.mtl\no first\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 1.5 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvt 0.5 1\n"
+                 "usemtl A\nf 1/1 2/2 3/3 4/4 5/5\nusemtl Light\nf -5/1 -4/2 -3/3\no second\nf 1/1 3/3 4/4\n")
+    hs = rc.ObjScene.load(str(p))
+    osc, light = ri.ObjScene.load(str(p))
+    assert hs.info().num_models == len(osc) == 3
+    assert hs.info().light_from_obj == 1 and light is not None
+    assert np.allclose(list(hs.info().obj_light), light)
+    for m in range(3):
+        v, i = hs.model_stream(m)
+        assert same_bits(v, osc[m].vertex_stream()) and np.array_equal(i, osc[m].indices())
+    assert len(osc[0].indices()) == 9          # pentagon -> 3 fan triangles
+    assert hs.model_material(1)[2].tolist() == [2.0, 2.0, 2.0]   # Ke

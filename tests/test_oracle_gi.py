@@ -1,0 +1,146 @@
+"""The GI oracle (oracle/rc_oracle.c) against its golden fixture and against properties of the
+specification (include/rc_spec.h) that do not depend on any implementation."""
+import os
+
+import numpy as np
+import pytest
+
+import radiancecascade_b200 as rc
+from oracle import gi_oracle as go
+from oracle import ref_ingest as ri
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "gi_cube64.npz"))
+
+
+@pytest.fixture(scope="module")
+def cube():
+    return go.OracleScene(rc.scenes.scene_path("cube"))
+
+
+def test_golden_frame(cube):
+    p = cube.params(64, 64, store_half=True)
+    assert np.array_equal(np.array([p.L0, p.t_far, p.offset], np.float32), GOLD["intervals"])
+    lv = cube.levels(p)
+    assert np.array_equal(np.array([[l.P, l.D, l.gw, l.gh] for l in lv], np.int32), GOLD["levels"])
+    assert np.array_equal(np.array([[l.t0, l.t1] for l in lv], np.float32), GOLD["t_ranges"])
+    assert np.array_equal(cube.directions(4), GOLD["dirs0"]) and np.array_equal(cube.directions(8), GOLD["dirs1"])
+    out = cube.render(p, GOLD["cam"], GOLD["lights"])
+    assert np.array_equal(out["prim"], GOLD["prim"]) and np.array_equal(out["depth"], GOLD["depth"])
+    assert np.array_equal(out["normal"], GOLD["normal"])
+    assert np.array_equal(out["irradiance"].astype(np.float16), GOLD["irradiance"])
+    assert np.array_equal(out["cascades"][0].astype(np.float16), GOLD["cascade0"])
+
+
+def test_intervals_are_contiguous_and_scale_by_four(cube):
+    p = cube.params(256, 128)
+    lv = cube.levels(p)
+    assert lv[0].t0 == 0.0 and lv[-1].t1 == p.t_far
+    for a, b in zip(lv[:-1], lv[1:]):
+        assert a.t1 == b.t0                          # no gap, no overlap (S2)
+    lens = [l.t1 - l.t0 for l in lv[:-1]]
+    assert np.allclose(np.array(lens[1:]) / np.array(lens[:-1]), 4.0, rtol=1e-5)
+    for i, l in enumerate(lv):
+        assert (l.P, l.D) == (4 << i, 4 << i) and (l.gw, l.gh) == (-(-256 // l.P), -(-128 // l.P))
+
+
+@pytest.mark.parametrize("D", [4, 8, 16, 32])
+def test_directions_equal_area_and_nested(D):
+    d = go.OracleScene.directions(D).astype(np.float64).reshape(D, D, 3)
+    assert np.allclose(np.linalg.norm(d, axis=-1), 1.0, atol=1e-6)
+    assert np.abs(d.sum((0, 1))).max() < 1e-4                      # symmetric over the sphere
+    # equal area: the midpoint rule with the uniform weight 4*pi/D^2 integrates the cosine lobe about +z to
+    # pi*(1 - 4/D^2) — a whole ring of texel centres sits on the equator.  At D0 = 4 that is 0.75*pi, which is
+    # why S9 normalises the cosine weights instead of using 4*pi/D0^2.
+    cosw = np.maximum(d[..., 2], 0).sum() * 4 * np.pi / (D * D)
+    assert abs(cosw - np.pi * (1 - 4.0 / (D * D))) < 1e-5
+    c = go.OracleScene.directions(2 * D).astype(np.float64).reshape(2 * D, 2 * D, 3)
+    kids = c.reshape(D, 2, D, 2, 3).mean((1, 3))
+    kids /= np.linalg.norm(kids, axis=-1, keepdims=True)
+    assert (kids * d).sum(-1).min() > np.cos(1.5 * np.sqrt(4 * np.pi / (D * D)))   # children straddle their parent
+
+
+def test_bvh_equals_brute_force_including_ties(cube):
+    rng = np.random.default_rng(5)
+    n = 30000
+    o = rng.uniform(-2.5, 2.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    # rays aimed exactly at mesh vertices hit several triangles at the same t: the id tie-break must hold
+    verts = cube.verts[:, :3]
+    tgt = verts[rng.integers(0, len(verts), 4000)]
+    d[:4000] = tgt - o[:4000]
+    d[:4000] /= np.linalg.norm(d[:4000], axis=1, keepdims=True)
+    rays = np.concatenate([o, np.zeros((n, 1), np.float32), d, np.full((n, 1), 3e38, np.float32)], 1).astype(np.float32)
+    a, b = cube.trace(rays), cube.trace(rays, brute=True)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    hit = a[:, 0] >= 0
+    assert 0.2 < hit.mean() < 0.9 and np.all(a[hit, 1] >= 0) and np.all(a[hit, 1] + a[hit, 2] <= 1.0 + 1e-6)
+
+
+def test_interval_restriction(cube):
+    """A ray split into [0,t) and [t,inf) finds its hit in exactly one of the two pieces (S5: tmin <= t < tmax)."""
+    rng = np.random.default_rng(6)
+    n = 5000
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    d = -o / np.linalg.norm(o, axis=1, keepdims=True)
+    full = cube.trace(np.concatenate([o, np.zeros((n, 1)), d, np.full((n, 1), 3e38)], 1).astype(np.float32))
+    hit = full[:, 0] >= 0
+    assert hit.mean() > 0.5
+    t = full[:, 0].copy()
+    lo = cube.trace(np.concatenate([o, np.zeros((n, 1)), d, t[:, None]], 1).astype(np.float32))      # [0, t): excludes the hit
+    hi = cube.trace(np.concatenate([o, t[:, None], d, np.full((n, 1), 3e38)], 1).astype(np.float32))  # [t, inf): includes it
+    assert np.all(lo[hit, 0] < 0)
+    assert np.array_equal(hi[hit].view(np.uint32), full[hit].view(np.uint32))
+
+
+def test_merge_and_gather_are_linear_in_radiance(cube):
+    """S8/S9 are linear maps of the raw radiance: doubling the light term doubles E (ambient-free material not needed:
+    compare E(lights) - E(no light) scaling through two light positions superposed)."""
+    W = H = 48
+    p = cube.params(W, H, store_half=False)
+    pos, tgt, zn, zf = rc.scenes.orbit_camera(cube.bbox_min, cube.bbox_max, 9)
+    cam = ri.uniform_camera_look_at(pos, tgt, np.float32(np.radians(np.float32(45.0))), np.float32(1), zn, zf)
+    la = np.array([[0.0, 3.0, 0.5, 1.0]], np.float32)
+    lb = np.array([[2.5, -1.0, 2.0, 1.0]], np.float32)
+    Ea = cube.render(p, cam, la)["irradiance"][..., :3]
+    Eb = cube.render(p, cam, lb)["irradiance"][..., :3]
+    Eab = cube.render(p, cam, np.concatenate([la, lb]))["irradiance"][..., :3]
+    E0 = cube.render(p, cam, np.zeros((0, 4), np.float32))["irradiance"][..., :3]
+    # ambient is counted once; diffuse + specular add over lights (S7)
+    assert np.abs((Ea - E0) + (Eb - E0) - (Eab - E0)).max() <= 2e-5 * max(1.0, Eab.max())
+
+
+def test_uniform_environment_gathers_pi(cube):
+    """Gather of a constant radiance field: E = L * sum_d max(n.w_d, 0) * 4*pi/D0^2 -> ~pi*L (S9 quadrature)."""
+    W = H = 32
+    p = cube.params(W, H, store_half=False)
+    cam = GOLD["cam"]
+    gb = cube.gbuffer(p, cam, GOLD["lights"])
+    rect = go.level_rects(W, H, 4, 6, (0, 0, W, H))[0]
+    og = np.zeros((rect[2] * rect[3], 4), np.float32); nr = np.zeros_like(og)
+    import ctypes as C
+    go.lib().rco_probes(cube.handle, C.byref(p), go._p(np.ascontiguousarray(cam, np.float32)), C.c_int(0), C.c_int(0), C.c_int(0),
+                        C.c_int(rect[2]), C.c_int(rect[3]), go._p(og), go._p(nr))
+    d0 = cube.directions(4)
+    c0 = np.zeros((rect[2] * rect[3] * 16, 4), np.float32); c0[:, :3] = 2.0
+    E = np.zeros((H, W, 4), np.float32)
+    go.lib().rco_gather(C.byref(p), go._p(np.ascontiguousarray(cam, np.float32)), C.c_int(0), C.c_int(0), C.c_int(rect[2]), C.c_int(rect[3]),
+                        go._p(og), go._p(c0), go._p(d0), go._p(gb["depth"]), go._p(gb["normal"]), go._p(E))
+    geo = gb["depth"] >= 0
+    assert geo.mean() > 0.5
+    assert np.all(np.abs(E[geo][:, :3] / 2.0 - np.pi) < 0.6)      # 16-direction quadrature of the cosine lobe
+    assert np.all(E[~geo] == 0)
+
+
+def test_tile_rect_recursion_covers_the_merge_footprint():
+    for tile in [(0, 0, 192, 108), (64, 32, 128, 64), (150, 70, 42, 38), (0, 100, 192, 8)]:
+        rects = go.level_rects(192, 108, 4, 6, tile)
+        for i in range(5):
+            lx, ly, lw, lh = rects[i]
+            ux, uy, uw, uh = rects[i + 1]
+            gw, gh = -(-192 // (4 << (i + 1))), -(-108 // (4 << (i + 1)))
+            for q, (u0, un, g) in ((lx, (ux, uw, gw)), (lx + lw - 1, (ux, uw, gw)), (ly, (uy, uh, gh)), (ly + lh - 1, (uy, uh, gh))):
+                base = q // 2 - 1 if q % 2 == 0 else (q - 1) // 2
+                for k in (base, base + 1):
+                    k = max(0, min(k, g - 1))
+                    assert u0 <= k < u0 + un
