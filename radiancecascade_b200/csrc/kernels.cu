@@ -234,8 +234,11 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
     return pack_half4(c.x, c.y, c.z, c.w);
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(512) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
+// MINB = minimum resident 128-thread blocks per SM the register allocation must allow (8 -> 64 regs,
+// 12 -> 40 regs, 16 -> 32 regs): the kernel is latency-bound (ncu: ~30 % warps active, ~7 dependent node
+// loads per warp), so occupancy is traded against spills and measured.
+template <bool FUSED, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
                                                   const float4* __restrict__ origin, const float* __restrict__ dirs,
                                                   uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
                                                   const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
@@ -560,8 +563,9 @@ void launch_link(const DLevelSet& ls, unsigned total, const float4* origin, cons
 
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
-                  const uint4* link_idx, const float4* link_w, bool fused, int map, int block, bool pdl, cudaStream_t st)
+                  const uint4* link_idx, const float4* link_w, bool fused, int map, int occ, bool pdl, cudaStream_t st)
 {
+    const int block = 128;
     if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;   // the 8x4 direction tile needs D % 8 == 0
     size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
     if (map == MAP_PROBE_TILE) n = (size_t)((lv.sw + 7) / 8) * ((lv.sh + 3) / 4) * lv.D * lv.D * 32;
@@ -576,10 +580,15 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && fused && !top) ? 1 : 0;   // only a kernel that waits on its predecessor may start early
-    if (fused && !top)
-        cudaLaunchKernelEx(&cfg, k_march<true>, s, L, lv, UD, 0, sky, map, origin, dirs, texels, up_texels, link_idx, link_w);
-    else
-        cudaLaunchKernelEx(&cfg, k_march<false>, s, L, lv, UD, topi, sky, map, origin, dirs, texels, up_texels, link_idx, link_w);
+#define RC_LAUNCH_MARCH(F, M, T)                                                                                              \
+    cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_texels, link_idx, link_w)
+    const bool f = fused && !top;
+    const int t = f ? 0 : topi;
+    if (occ >= 16) { if (f) RC_LAUNCH_MARCH(true, 16, t); else RC_LAUNCH_MARCH(false, 16, t); }
+    else if (occ >= 12) { if (f) RC_LAUNCH_MARCH(true, 12, t); else RC_LAUNCH_MARCH(false, 12, t); }
+    else if (occ >= 10) { if (f) RC_LAUNCH_MARCH(true, 10, t); else RC_LAUNCH_MARCH(false, 10, t); }
+    else { if (f) RC_LAUNCH_MARCH(true, 8, t); else RC_LAUNCH_MARCH(false, 8, t); }
+#undef RC_LAUNCH_MARCH
 }
 
 void launch_march_persist(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,

@@ -118,7 +118,8 @@ struct rc_ctx {
     uint32_t launches = 0;
     cudaStream_t last_stream = nullptr;
     int march_map[RC_MAX_LEVELS];   // thread->texel mapping per level (kernels.cu MAP_*)
-    int march_block = 128;
+    int march_block = 128;   // blocks of 128 threads; march_occ = min resident blocks/SM the registers must allow
+    int march_occ = 10;      // measured best of 8/10/12/16
     int march_persist = 0, march_thresh = 8, march_grid = 0, march_pdl = 1;   // persistent variant measured slower
     bool level_timing = false;
 
@@ -520,6 +521,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         const char* mb = getenv("RC_MARCH_BLOCK");
         if (mb && (atoi(mb) == 64 || atoi(mb) == 128 || atoi(mb) == 256 || atoi(mb) == 512)) c->march_block = atoi(mb);
         if (const char* e = getenv("RC_MARCH_PERSIST")) c->march_persist = atoi(e);
+        if (const char* e = getenv("RC_MARCH_OCC")) c->march_occ = atoi(e);
         if (const char* e = getenv("RC_MARCH_THRESH")) c->march_thresh = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
         if (const char* e = getenv("RC_MARCH_PDL")) c->march_pdl = atoi(e);
         cudaDeviceProp prop;
@@ -609,7 +611,7 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
                              c->march_grid, c->d_counters.p + level, c->march_pdl && fused && !top, st);
     else
         launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
-                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_block, c->march_pdl != 0, st);
+                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, st);
     c->launches++;
     if (!fused && !top) {
         launch_merge(L, *U, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
@@ -629,6 +631,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "march_persist") c->march_persist = (value != 0 && c->march_grid > 0 && c->d_counters.p) ? 1 : 0;
     else if (k == "march_thresh") c->march_thresh = value < 1 ? 1 : (value > 32 ? 32 : value);
     else if (k == "march_pdl") c->march_pdl = value != 0;
+    else if (k == "march_occ" && value >= 8 && value <= 16) c->march_occ = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
     else if (k.rfind("march_map", 0) == 0 && k.size() == 10 && k[9] >= '0' && k[9] <= '9' && value >= 0 && value <= 2)
