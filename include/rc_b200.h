@@ -43,7 +43,7 @@ enum {
 /* rc_config.flags */
 #define RC_CFG_SEPARATE_MERGE 0x1u /* run march and merge as separate kernels (debug / A-B) instead of the fused path */
 #define RC_CFG_NO_TEXTURES    0x2u /* ignore map_Kd / map_Bump (as if the files were missing, src/primitives.rs:390-404) */
-#define RC_CFG_HALO_EXCHANGE  0x4u /* tile mode: upper-level halo probes are supplied by rc_halo_import instead of recomputed */
+#define RC_CFG_HALO_EXCHANGE  0x4u /* reserved: tile mode with exchanged (not recomputed) halos; today halos are always recomputed */
 
 /* rc_update flags.  bit0 ≙ AppState::enable_normal_map (src/app.rs:18, src/renderer.rs:620-631) */
 #define RC_UPD_ENABLE_NORMAL_MAP 0x1u
@@ -89,7 +89,7 @@ typedef enum rc_target {
     RC_TARGET_IRRADIANCE = 0, /* float16 RGBA  [tile_h][tile_w][4]  linear HDR irradiance E, a = 1 where geometry */
     RC_TARGET_DIRECT     = 1, /* float16 RGBA  [tile_h][tile_w][4]  fs_main output (linear), a = 1 where geometry */
     RC_TARGET_DEPTH      = 2, /* float32       [tile_h][tile_w]     primary-ray distance, < 0 where no geometry */
-    RC_TARGET_NORMAL     = 3, /* uint32        [tile_h][tile_w]     shading normal, 2 x snorm16 equal-area octahedral */
+    RC_TARGET_NORMAL     = 3, /* uint32        [tile_h][tile_w]     shading normal, 2 x snorm16 octahedral (standard mapping) */
     RC_TARGET_ALBEDO     = 4, /* float16 RGBA  [tile_h][tile_w][4]  linear albedo (`color` of fs_main) */
     RC_TARGET_PRIM       = 5, /* uint32        [tile_h][tile_w]     global triangle id, 0xffffffff where no geometry */
     RC_TARGET_COMPOSITE  = 6, /* uint8 BGRA    [tile_h][tile_w][4]  sRGB-encoded albedo*E/pi + direct (Bgra8UnormSrgb, src/window/app.rs:59-75) */
@@ -217,6 +217,11 @@ rc_status rc_scene_model_name(const rc_scene* scene, uint32_t model, char* out, 
 /* which: 0 colour map (map_Kd), 1 normal map (map_Bump); width = height = 0 when the model has none */
 rc_status rc_scene_model_texture(const rc_scene* scene, uint32_t model, uint32_t which, uint8_t* rgba, size_t bytes,
                                  uint32_t* width, uint32_t* height);
+
+/* ≙ image::ImageReader::open(path).decode().to_rgba8() as used by Scene::material and
+ * Texture::from_image (src/primitives.rs:391-404, src/texture.rs:85-93): built-in PNG and JPEG
+ * decoders.  Pass rgba = NULL to query the size. */
+rc_status rc_decode_image_file(const char* path, uint8_t* rgba, size_t bytes, uint32_t* width, uint32_t* height);
 
 rc_status rc_synchronize(rc_ctx* ctx);
 void rc_destroy(rc_ctx* ctx);

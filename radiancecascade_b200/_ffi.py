@@ -96,6 +96,7 @@ SYMBOLS = {
     "rc_scene_model_name": (C.c_int32, [_P, C.c_uint32, C.c_char_p, C.c_size_t]),
     "rc_scene_model_texture": (C.c_int32, [_P, C.c_uint32, C.c_uint32, _P, C.c_size_t,
                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "rc_decode_image_file": (C.c_int32, [C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rc_trace_rays": (C.c_int32, [_P, _P, C.c_uint32, _P]),
     "rc_shade_points": (C.c_int32, [_P, _P, C.c_uint32, _P]),
     "rc_cascade_device_ptr": (C.c_int32, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_size_t)]),

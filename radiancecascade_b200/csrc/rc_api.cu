@@ -852,6 +852,20 @@ rc_status rc_scene_model_material(const rc_scene* s, uint32_t model, void* out80
     return RC_OK;
 }
 
+rc_status rc_decode_image_file(const char* path, uint8_t* rgba, size_t bytes, uint32_t* width, uint32_t* height)
+{
+    if (!path) return RC_ERR_INVALID_ARG;
+    std::string why;
+    std::shared_ptr<Image> img = load_image_rgba8(path, &why);
+    if (!img) { g_create_error = why; return RC_ERR_SCENE_LOAD; }
+    if (width) *width = img->width;
+    if (height) *height = img->height;
+    if (!rgba) return RC_OK;
+    if (bytes < img->rgba.size()) return RC_ERR_BUFFER_SIZE;
+    memcpy(rgba, img->rgba.data(), img->rgba.size());
+    return RC_OK;
+}
+
 rc_status rc_scene_model_name(const rc_scene* s, uint32_t model, char* out, size_t bytes)
 {
     if (!s || !out || !bytes || model >= s->models.size()) return RC_ERR_INVALID_ARG;

@@ -112,6 +112,11 @@ def all_gather_tiles(local, tiles: Sequence[Tile], width: int, height: int, grou
     import torch.distributed as dist
     world = dist.get_world_size(group)
     assert world == len(tiles)
+    if all(t[0] == 0 and t[2] == width and t[3] == tiles[0][3] for t in tiles) and local.is_contiguous():
+        # equal full-width strips are exactly the row blocks of the frame: gather straight into it, no staging copies
+        full = torch.empty((height, width, local.shape[-1]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, local, group=group)
+        return full
     mh = max(t[3] for t in tiles)
     mw = max(t[2] for t in tiles)
     pad = torch.zeros((mh, mw, local.shape[-1]), dtype=local.dtype, device=local.device)

@@ -399,3 +399,17 @@ class ObjScene:
         out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
         self._lib.rc_scene_model_texture(self._h, model, which, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(w), C.byref(h))
         return out
+
+
+def decode_image_file(path: str) -> np.ndarray:
+    """RGBA8 pixels of a PNG / JPEG file through librc_b200's built-in decoders (csrc/image.cpp, csrc/jpeg.cpp)."""
+    lib = _ffi.load()
+    w, h = C.c_uint32(), C.c_uint32()
+    st = lib.rc_decode_image_file(path.encode(), None, 0, C.byref(w), C.byref(h))
+    if st != _ffi.RC_OK:
+        raise RcError(st, (lib.rc_last_error(None) or b"").decode())
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+    st = lib.rc_decode_image_file(path.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(w), C.byref(h))
+    if st != _ffi.RC_OK:
+        raise RcError(st, "rc_decode_image_file")
+    return out

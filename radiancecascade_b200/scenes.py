@@ -2,9 +2,10 @@
 
 The reference's assets live in scenes/*.zip (tools/pack_scenes.py).  `scene_path`
 extracts an archive next to it (scenes/_extracted/, git-ignored) and returns the
-.obj path to hand to rc_create.  JPEG textures are additionally decoded once
-with PIL into "<file>.rgba8" sidecars that librc_b200's loader picks up (its
-built-in decoders cover PNG; see csrc/image.cpp).
+.obj path to hand to rc_create.  librc_b200 decodes PNG and JPEG textures itself
+(csrc/image.cpp, csrc/jpeg.cpp); `sidecars=True` additionally writes PIL-decoded
+"<file>.rgba8" files, which the loader prefers when present (a way to inject
+externally decoded pixels; not used by the tests or the benchmark).
 """
 from __future__ import annotations
 
@@ -49,7 +50,7 @@ def _write_sidecar(img_path: str) -> None:
     os.replace(tmp, side)
 
 
-def scene_path(name: str, sidecars: bool = True) -> str:
+def scene_path(name: str, sidecars: bool = False) -> str:
     """Extract scenes/<name>.zip if needed; return the absolute .obj path."""
     if name not in SCENES:
         raise KeyError(f"unknown scene {name!r}; have {sorted(SCENES)}")
@@ -60,10 +61,12 @@ def scene_path(name: str, sidecars: bool = True) -> str:
         with zipfile.ZipFile(os.path.join(SCENE_DIR, name + ".zip")) as z:
             z.extractall(EXTRACT_DIR)
             members = z.namelist()
-        if sidecars:
-            for m in members:
-                if m.lower().endswith((".jpg", ".jpeg")):
+        for m in members:
+            if m.lower().endswith((".jpg", ".jpeg")):
+                if sidecars:
                     _write_sidecar(os.path.join(EXTRACT_DIR, m))
+                elif os.path.exists(os.path.join(EXTRACT_DIR, m) + ".rgba8"):
+                    os.remove(os.path.join(EXTRACT_DIR, m) + ".rgba8")
         with open(marker, "w") as fh:
             fh.write("ok\n")
     return obj

@@ -107,3 +107,64 @@ def test_small_obj_semantics(tmp_path):
         assert same_bits(v, osc[m].vertex_stream()) and np.array_equal(i, osc[m].indices())
     assert len(osc[0].indices()) == 9          # pentagon -> 3 fan triangles
     assert hs.model_material(1)[2].tolist() == [2.0, 2.0, 2.0]   # Ke
+
+
+def _pil_rgba(path):
+    from PIL import Image
+    with Image.open(path) as im:
+        return np.asarray(im.convert("RGBA"), dtype=np.uint8)
+
+
+def test_bundled_textures_decode_like_pil():
+    """Every texture file of the bundled scenes: built-in PNG / JPEG decoders (baseline and progressive)
+    against PIL (libjpeg-turbo / libpng) — bit-exact."""
+    from radiancecascade_b200.renderer import decode_image_file
+    n = 0
+    for name in SCENES:
+        root = os.path.dirname(rc.scenes.scene_path(name))
+        for d, _, files in os.walk(root):
+            for f in files:
+                if f.lower().endswith((".jpg", ".jpeg", ".png")):
+                    p = os.path.join(d, f)
+                    assert np.array_equal(decode_image_file(p), _pil_rgba(p)), p
+                    n += 1
+    assert n >= 20
+
+
+@pytest.mark.parametrize("mode,subsampling,progressive,size", [
+    ("RGB", 0, False, (67, 45)), ("RGB", 1, False, (67, 45)), ("RGB", 2, False, (67, 45)), ("RGB", 2, True, (130, 71)),
+    ("RGB", 1, True, (33, 90)), ("L", 0, False, (50, 50)), ("L", 0, True, (41, 23)), ("RGB", 2, False, (16, 16)), ("RGB", 2, False, (1, 1))])
+def test_synthetic_jpeg_variants(tmp_path, mode, subsampling, progressive, size):
+    """4:4:4 / 4:2:2 / 4:2:0, grayscale, progressive scans, odd sizes: code paths the bundled assets do not all reach."""
+    from PIL import Image
+    from radiancecascade_b200.renderer import decode_image_file
+    rng = np.random.default_rng(size[0] * 131 + size[1])
+    w, h = size
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 255 // max(w - 1, 1)), (yy * 255 // max(h - 1, 1)), ((xx + yy) * 7) % 256], -1).astype(np.int32)
+    img = np.clip(base + rng.integers(-40, 40, (h, w, 3)), 0, 255).astype(np.uint8)
+    im = Image.fromarray(img if mode == "RGB" else img[..., 0], mode)
+    p = str(tmp_path / "t.jpg")
+    kw = dict(quality=87, progressive=progressive)
+    if mode == "RGB":
+        kw["subsampling"] = subsampling
+    im.save(p, "JPEG", **kw)
+    assert np.array_equal(decode_image_file(p), _pil_rgba(p))
+
+
+def test_png_variants(tmp_path):
+    from PIL import Image
+    from radiancecascade_b200.renderer import decode_image_file
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    for mode, arr in (("RGBA", a), ("RGB", a[..., :3]), ("L", a[..., 0]), ("LA", a[..., :2])):
+        p = str(tmp_path / f"{mode}.png")
+        Image.fromarray(arr, mode).save(p)
+        assert np.array_equal(decode_image_file(p), _pil_rgba(p)), mode
+    pal = Image.fromarray(a[..., 0] % 7, "P")
+    pal.putpalette([i * 9 % 256 for i in range(768)])
+    p = str(tmp_path / "P.png")
+    pal.save(p, bits=4)
+    assert np.array_equal(decode_image_file(p), _pil_rgba(p))
+    with pytest.raises(rc.RcError):
+        decode_image_file(str(tmp_path / "missing.png"))
