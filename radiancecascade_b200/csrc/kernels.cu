@@ -35,9 +35,11 @@ __device__ __forceinline__ uint4 ld_u4(const void* p)
 // ------------------------------------------------------------------ G-buffer
 __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out)
 {
-    // 2-D tiles of 32x8 pixels keep a warp's primary rays in one screen row segment
-    const int tx = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ty = blockIdx.y * 8 + (threadIdx.x >> 5);
+    // a block covers 32x8 pixels; each warp an 8x4 pixel tile (compact frustum -> coherent traversal; four
+    // 32-byte row segments per store)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int ty = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
     if (tx >= tile.w || ty >= tile.h) return;
     const size_t o = (size_t)ty * tile.w + tx;
     const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
@@ -238,22 +240,96 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
 // 12 -> 40 regs, 16 -> 32 regs): the kernel is latency-bound (ncu: ~30 % warps active, ~7 dependent node
 // loads per warp), so occupancy is traded against spills and measured.
 template <bool FUSED, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
+__global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map, size_t total,
                                                   const float4* __restrict__ origin, const float* __restrict__ dirs,
                                                   uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
                                                   const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
 {
     cudaTriggerProgrammaticLaunchCompletion();   // the next level's kernel may begin once every block got here
     const size_t DD = (size_t)lv.D * lv.D;
-    uint32_t probe, d;
-    if (!decode_texel(lv, map, (size_t)blockIdx.x * blockDim.x + threadIdx.x, probe, d)) return;
-    const size_t i = (size_t)probe * DD + d;
-    const float4 og = __ldg(origin + probe);
-    if (og.w == 0.0f) { texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f); return; }   // invalid probe (S7)
-    const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+    // grid-stride: with a full-size grid this is one iteration; with a resident grid (rc_set_tuning
+    // "march_waves") each warp walks packets g, g + G, ... and no block turnover happens during the level
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        uint32_t probe, d;
+        if (!decode_texel(lv, map, g, probe, d)) continue;
+        const size_t i = (size_t)probe * DD + d;
+        const float4 og = __ldg(origin + probe);
+        if (og.w == 0.0f) { texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f); continue; }   // invalid probe (S7)
+        const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+        const float3 o = xyz(og);
+        const Hit h = trace(s, o, w, lv.t0, lv.t1);
+        texels[i] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_texels, link_idx, link_w);
+    }
+}
+
+// ------------------------------------------------------------------ march with block-level ray compaction
+// In open scenes most rays of the upper levels leave the scene bounds inside their interval: they need one
+// box test and the (uniform) merge, but in k_march they share warps with rays that traverse for hundreds of
+// instructions, so traversal code runs with ~10 of 32 lanes active.  Here every thread first tests its ray
+// against the root node's two child boxes; the misses finish immediately (merge + store, all such lanes
+// together), the survivors are packed — in order, via warp ballots and a block prefix — into the block's
+// first warps, which traverse with (nearly) full warps while the other warps have already exited.
+__device__ __forceinline__ bool root_overlap(const DScene& s, float3 o, float3 d, float tmin, float tmax)
+{
+    const float3 inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    const float3 noi = f3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+    const float4 q0 = __ldg(s.nodes), q1 = __ldg(s.nodes + 1), q2 = __ldg(s.nodes + 2);
+    float ax = fmaf(q0.x, inv.x, noi.x), bx = fmaf(q0.w, inv.x, noi.x);
+    float ay = fmaf(q0.y, inv.y, noi.y), by = fmaf(q1.x, inv.y, noi.y);
+    float az = fmaf(q0.z, inv.z, noi.z), bz = fmaf(q1.y, inv.z, noi.z);
+    const float n0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    const float f0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    ax = fmaf(q1.z, inv.x, noi.x); bx = fmaf(q2.y, inv.x, noi.x);
+    ay = fmaf(q1.w, inv.y, noi.y); by = fmaf(q2.z, inv.y, noi.y);
+    az = fmaf(q2.x, inv.z, noi.z); bz = fmaf(q2.w, inv.z, noi.z);
+    const float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    const float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    return n0 <= f0 || n1 <= f1;
+}
+
+template <bool FUSED, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_march_compact(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
+                                                             const float4* __restrict__ origin, const float* __restrict__ dirs,
+                                                             uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                             const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    __shared__ uint2 s_ray[128];      // (probe, direction) of the surviving rays, in thread order
+    __shared__ int s_warp[4];
+    const size_t DD = (size_t)lv.D * lv.D;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t probe = 0, d = 0;
+    bool survive = false;
+    Hit miss; miss.t = -1.f; miss.u = 0.f; miss.v = 0.f; miss.prim = 0xffffffffu;
+    if (decode_texel(lv, map, (size_t)blockIdx.x * 128 + threadIdx.x, probe, d)) {
+        const size_t i = (size_t)probe * DD + d;
+        const float4 og = __ldg(origin + probe);
+        if (og.w == 0.0f) {
+            texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f);   // invalid probe (S7)
+        } else {
+            const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+            const float3 o = xyz(og);
+            survive = root_overlap(s, o, w, lv.t0, lv.t1);
+            if (!survive) texels[i] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, miss, up_texels, link_idx, link_w);
+        }
+    }
+    // ordered compaction of the survivors
+    const unsigned m = __ballot_sync(0xffffffffu, survive);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int c = s_warp[k]; if (k < (int)warp) base += c; total += c; }
+    if (survive) s_ray[base + __popc(m & ((1u << lane) - 1u))] = make_uint2(probe, d);
+    __syncthreads();
+    if ((int)threadIdx.x >= total) return;
+    const uint2 r = s_ray[threadIdx.x];
+    const float4 og = __ldg(origin + r.x);
     const float3 o = xyz(og);
+    const float3 w = f3(__ldg(dirs + 3 * r.y), __ldg(dirs + 3 * r.y + 1), __ldg(dirs + 3 * r.y + 2));
     const Hit h = trace(s, o, w, lv.t0, lv.t1);
-    texels[i] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_texels, link_idx, link_w);
+    texels[(size_t)r.x * DD + r.y] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, r.x, r.y, o, w, h, up_texels, link_idx, link_w);
 }
 
 // ------------------------------------------------------------------ persistent march with ray replacement
@@ -563,7 +639,8 @@ void launch_link(const DLevelSet& ls, unsigned total, const float4* origin, cons
 
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
-                  const uint4* link_idx, const float4* link_w, bool fused, int map, int occ, bool pdl, cudaStream_t st)
+                  const uint4* link_idx, const float4* link_w, bool fused, int map, int occ, bool pdl, bool compact,
+                  int max_blocks, cudaStream_t st)
 {
     const int block = 128;
     if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;   // the 8x4 direction tile needs D % 8 == 0
@@ -572,7 +649,9 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     const int UD = up ? up->D : 0;
     const int topi = top ? 1 : 0;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((n + block - 1) / block));
+    size_t blocks = (n + block - 1) / block;
+    if (max_blocks > 0 && !compact && blocks > (size_t)max_blocks) blocks = (size_t)max_blocks;   // resident grid, grid-stride loop
+    cfg.gridDim = dim3((unsigned)blocks);
     cfg.blockDim = dim3((unsigned)block);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -581,7 +660,8 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && fused && !top) ? 1 : 0;   // only a kernel that waits on its predecessor may start early
 #define RC_LAUNCH_MARCH(F, M, T)                                                                                              \
-    cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_texels, link_idx, link_w)
+    (compact ? cudaLaunchKernelEx(&cfg, k_march_compact<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_texels, link_idx, link_w) \
+             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirs, texels, up_texels, link_idx, link_w))
     const bool f = fused && !top;
     const int t = f ? 0 : topi;
     if (occ >= 16) { if (f) RC_LAUNCH_MARCH(true, 16, t); else RC_LAUNCH_MARCH(false, 16, t); }

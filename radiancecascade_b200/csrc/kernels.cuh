@@ -21,7 +21,8 @@ void launch_link(const DLevelSet& ls, unsigned total, const float4* origin, cons
 // march level lv; fused != 0 also merges with the (already merged) upper level
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
-                  const uint4* link_idx, const float4* link_w, bool fused, int map, int occ, bool pdl, cudaStream_t st);
+                  const uint4* link_idx, const float4* link_w, bool fused, int map, int occ, bool pdl, bool compact,
+                  int max_blocks, cudaStream_t st);
 // persistent variant: resident grid, dynamic ray fetch with lane replacement, PDL-chained across levels
 void launch_march_persist(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                           const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,

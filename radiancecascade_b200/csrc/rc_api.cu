@@ -122,6 +122,9 @@ struct rc_ctx {
     int march_occ = 10;      // measured best of 8/10/12/16
     int march_persist = 0, march_thresh = 8, march_grid = 0, march_pdl = 1;   // persistent variant measured slower
     bool level_timing = false;
+    int march_compact = 0;   // bit i: level i uses the block-compacting march kernel
+    int march_waves = 0;     // > 0: march grid capped at SMs * occ * waves blocks (grid-stride loop); 0: one thread per ray
+    int sm_count = 148;
 
     bool fail(rc_status, const std::string& m) { error = m; return false; }
 };
@@ -522,11 +525,14 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (mb && (atoi(mb) == 64 || atoi(mb) == 128 || atoi(mb) == 256 || atoi(mb) == 512)) c->march_block = atoi(mb);
         if (const char* e = getenv("RC_MARCH_PERSIST")) c->march_persist = atoi(e);
         if (const char* e = getenv("RC_MARCH_OCC")) c->march_occ = atoi(e);
+        if (const char* e = getenv("RC_MARCH_COMPACT")) c->march_compact = (int)strtol(e, nullptr, 0);
+        if (const char* e = getenv("RC_MARCH_WAVES")) c->march_waves = atoi(e);
         if (const char* e = getenv("RC_MARCH_THRESH")) c->march_thresh = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
         if (const char* e = getenv("RC_MARCH_PDL")) c->march_pdl = atoi(e);
         cudaDeviceProp prop;
         int bps = march_persist_blocks_per_sm();
-        if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && bps > 0) c->march_grid = prop.multiProcessorCount * bps;
+        if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+        if (c->sm_count > 0 && bps > 0) c->march_grid = c->sm_count * bps;
         else c->march_persist = 0;
         if (const char* e = getenv("RC_MARCH_GRID")) if (atoi(e) > 0) c->march_grid = atoi(e);
         if (c->d_counters.alloc(RC_MAX_LEVELS) != cudaSuccess) c->march_persist = 0;
@@ -611,7 +617,8 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
                              c->march_grid, c->d_counters.p + level, c->march_pdl && fused && !top, st);
     else
         launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
-                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, st);
+                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, ((c->march_compact >> level) & 1) != 0,
+                     c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0, st);
     c->launches++;
     if (!fused && !top) {
         launch_merge(L, *U, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
@@ -632,6 +639,8 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "march_thresh") c->march_thresh = value < 1 ? 1 : (value > 32 ? 32 : value);
     else if (k == "march_pdl") c->march_pdl = value != 0;
     else if (k == "march_occ" && value >= 8 && value <= 16) c->march_occ = value;
+    else if (k == "march_compact" && value >= 0) c->march_compact = value;
+    else if (k == "march_waves" && value >= 0) c->march_waves = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
     else if (k.rfind("march_map", 0) == 0 && k.size() == 10 && k[9] >= '0' && k[9] <= '9' && value >= 0 && value <= 2)
