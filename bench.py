@@ -288,7 +288,14 @@ def run_product(args):
         gather_bytes = 8 * int(levels[0].texel_count) + W * H * 16
         roof = {"bound": "hbm", "kernel": "k_march<fused> (per-level ray march + merge; latency/issue-bound, BVH in L2)",
                 "achieved": march_bytes_per_launch / (avg_march_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "peak_source": peak_src, "traffic": None}
+                "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": march_bytes_per_launch,
+                "avg_launch_ms": avg_march_launch_ms}
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if wl == "teapot_1080p" and os.path.exists(tpath):      # dram bytes per launch from the committed ncu --set full capture
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            roof["traffic"] = tj["k_march_dram_bytes_per_launch"]
+            roof["traffic_source"] = tj["source"]
         roof["frac"] = roof["achieved"] / peak
         gather = {"kernel": "k_gather", "bound": "hbm", "achieved": gather_bytes / (st_mean["gather"] * 1e-3) / 1e9, "peak": peak,
                   "unit": "GB/s", "bytes": gather_bytes}

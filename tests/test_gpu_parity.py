@@ -256,3 +256,57 @@ def test_composite_and_direct_srgb_targets():
     assert np.all(d8[..., 3] == 255)
     comp = r.read_target(_ffi.RC_TARGET_COMPOSITE)
     assert np.all(comp[..., :3].astype(np.int32) >= d8[..., :3].astype(np.int32) - 1)   # albedo*E/pi >= 0 is added
+
+
+@pytest.mark.parametrize("name,W,H,P0,D0,N", [("cube", 101, 67, 4, 4, 6), ("teapot", 96, 64, 2, 4, 5), ("test_room", 120, 72, 8, 2, 4),
+                                              ("cube", 64, 64, 4, 6, 3), ("living_room", 80, 48, 4, 4, 1), ("sonic", 33, 47, 3, 4, 4)])
+def test_non_default_cascade_parameters(name, W, H, P0, D0, N):
+    """Ragged sizes (grids not multiples of the spacing), other spacings / direction counts / level counts, incl.
+    a non-power-of-two D0 and P0 and the single-level stack: layout tables bit-exact, irradiance within S10."""
+    st, cam, larr = frame_setup(name, W, H)
+    r = render_product(name, W, H, st, rc.CascadeConfig(probe_spacing0=P0, dir_res0=D0, num_levels=N))
+    osc = oracle_scene(name)
+    p = osc.params(W, H, P0=P0, D0=D0, N=N, store_half=True)
+    lv, olv = r.levels(), osc.levels(p)
+    assert len(lv) == N
+    for a, b in zip(lv, olv):
+        assert (a.spacing, a.dir_res, a.grid_w, a.grid_h) == (b.P, b.D, b.gw, b.gh)
+        assert np.float32(a.t_begin) == np.float32(b.t0) and np.float32(a.t_end) == np.float32(b.t1)
+    out = osc.render(p, cam, larr)
+    assert np.array_equal(r.read_target(_ffi.RC_TARGET_PRIM), out["prim"])
+    for i in range(N):
+        a, b = half_to_f32(r.read_cascade(i)), out["cascades"][i]
+        assert a.shape == b.shape
+        assert (np.abs(a - b) > 2e-3 * np.maximum(1.0, np.abs(b))).mean() < 2e-4, i
+    E, Eo = half_to_f32(r.read_target(_ffi.RC_TARGET_IRRADIANCE)), out["irradiance"]
+    peak = max(float(Eo[..., :3].max()), 1e-6)
+    assert np.abs(E[..., :3] - Eo[..., :3]).max() <= 1e-2 * peak
+
+
+def test_invalid_cascade_parameters_are_rejected():
+    st = rc.AppState()
+    for bad in (dict(dir_res0=3), dict(dir_res0=1), dict(num_levels=11), dict(dir_res0=4096, num_levels=3)):
+        with pytest.raises(rc.RcError) as e:
+            rc.DefaultRenderer.new(0, (64, 64), st, rc.scenes.scene_path("cube"), rc.CascadeConfig(**bad))
+        assert e.value.status == _ffi.RC_ERR_INVALID_ARG
+    with pytest.raises(rc.RcError):
+        rc.DefaultRenderer.new(0, (64, 64), st, rc.scenes.scene_path("cube"), rc.CascadeConfig(tile=(32, 32, 64, 64)))   # tile leaves the frame
+
+
+def test_normal_map_toggle_and_no_textures_flag():
+    """enable_normal_map (src/widget.rs:24-29 -> src/renderer.rs:620-631) and the missing-texture fallback."""
+    st, cam, larr = frame_setup("cube", 96, 96)
+    osc = oracle_scene("cube")
+    r = render_product("cube", 96, 96, st)
+    on = half_to_f32(r.read_target(_ffi.RC_TARGET_DIRECT))
+    st.enable_normal_map = False
+    r.update(st); r.render()
+    off = half_to_f32(r.read_target(_ffi.RC_TARGET_DIRECT))
+    assert np.abs(on - off).max() > 1e-3
+    gb = osc.gbuffer(osc.params(96, 96), cam, larr, flags=0)
+    assert np.all(np.abs(off - gb["direct"]) <= 2e-3 * np.maximum(1.0, np.abs(gb["direct"])))
+    st.enable_normal_map = True
+    r2 = render_product("cube", 96, 96, st, rc.CascadeConfig(flags=_ffi.RC_CFG_NO_TEXTURES))
+    alb = half_to_f32(r2.read_target(_ffi.RC_TARGET_ALBEDO))
+    geo = r2.read_target(_ffi.RC_TARGET_PRIM) != 0xFFFFFFFF
+    assert np.all(alb[geo][:, :3] == 1.0)      # colour falls back to the vertex colour default (1,1,1), src/renderer.rs:376-380
