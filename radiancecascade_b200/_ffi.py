@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librc_b200.so")
+LIB_PATH = os.environ.get("RC_B200_LIB") or os.path.join(_HERE, "librc_b200.so")   # override: A/B builds of the same ABI
 
 RC_OK = 0
 RC_ERR_INVALID_ARG, RC_ERR_SCENE_LOAD, RC_ERR_CUDA, RC_ERR_NO_DEVICE, RC_ERR_BUFFER_SIZE, RC_ERR_STATE = 1, 2, 3, 4, 5, 6

@@ -189,6 +189,20 @@ __device__ __forceinline__ bool decode_texel(const DLevel& lv, int map, size_t g
         return true;
     }
     if (g >= (size_t)lv.sw * lv.sh * DD) return false;
+    if ((lv.D & (lv.D - 1)) == 0) {
+        // D is a power of two (every default level): shifts instead of two 64/32-bit divisions (~60 SASS
+        // instructions, a third of the set-up cost of a ray that leaves the scene immediately)
+        const int ld = 31 - __clz(lv.D);
+        probe = (uint32_t)(g >> (2 * ld));
+        const uint32_t j = (uint32_t)g & (DD - 1u);
+        if (map == MAP_DIR_TILE) {
+            const uint32_t tile = j >> 5, lane = j & 31u, tsh = (uint32_t)(ld - 3), tmask = ((uint32_t)lv.D >> 3) - 1u;
+            d = (((tile >> tsh) * 4 + (lane >> 3)) << ld) + (tile & tmask) * 8 + (lane & 7u);
+        } else {
+            d = j;
+        }
+        return true;
+    }
     probe = (uint32_t)(g / DD);
     const uint32_t j = (uint32_t)(g - (size_t)probe * DD);
     if (map == MAP_DIR_TILE) {
@@ -225,7 +239,9 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
         // S8 applied to the float16-rounded raw texel (the same value the unfused path reads back)
         const float4 raw = unpack_half4(pack_half4(c.x, c.y, c.z, c.w));
         if (raw.w != 0.0f) {
-            const int dx = (int)(d % (uint32_t)lv.D), dy = (int)(d / (uint32_t)lv.D);
+            int dx, dy;
+            if ((lv.D & (lv.D - 1)) == 0) { dx = (int)(d & (uint32_t)(lv.D - 1)); dy = (int)(d >> (31 - __clz(lv.D))); }
+            else { dx = (int)(d % (uint32_t)lv.D); dy = (int)(d / (uint32_t)lv.D); }
             const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy);
             c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
             c.x = fminf(c.x, 65504.0f); c.y = fminf(c.y, 65504.0f); c.z = fminf(c.z, 65504.0f);

@@ -136,13 +136,13 @@ __device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float 
             const float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
             const float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
             const bool hit0 = n0 <= f0, hit1 = n1 <= f1;   // <=: equal-t candidates stay reachable for the id tie-break
-            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            if (hit0 && hit1) {
-                if (n1 < n0) { const int t = c0; c0 = c1; c1 = t; }
-                stack[sp++] = c1;
-                cur = c0;
-            } else if (hit0) cur = c0;
-            else if (hit1) cur = c1;
+            const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            // select-based step: one predicated push, one (rare) pop branch.  (prefetch.global.L1 of the deferred
+            // child was measured: +-1 %, not kept)
+            const bool first1 = hit1 && (!hit0 || n1 < n0);
+            const int nearc = first1 ? c1 : c0, farc = first1 ? c0 : c1;
+            if (hit0 && hit1) stack[sp++] = farc;
+            if (hit0 || hit1) cur = nearc;
             else cur = sp ? stack[--sp] : kDoneLink;
         }
         while (cur < 0 && cur != kDoneLink) {
@@ -197,38 +197,46 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
     const float* a = s.verts + 17 * (size_t)i0;
     const float* b = s.verts + 17 * (size_t)i1;
     const float* c = s.verts + 17 * (size_t)i2;
-    float at[17];
-#pragma unroll
-    for (int k = 3; k < 17; k++) at[k] = lerp3(__ldg(a + k), __ldg(b + k), __ldg(c + k), u, v);
+    // fs_main evaluates everything and masks with 0/1 factors; here an attribute is fetched and interpolated
+    // only when its factor is not 0 (the result is bit-identical: x*0 contributes exactly 0 for finite x, and
+    // the skipped terms are never NaN-producing for the cases gated below).
     const DMaterial& m = s.mats[s.tri_model[prim]];
     uint32_t eb = m.ebit;
     if (!(L.flags & 1u)) eb &= 1u;                                   // src/renderer.rs:623
     const bool b0 = eb & 1u, b1 = (eb >> 1) & 1u;
-    const float tu = at[15], tv = 1.0f - at[16];                     // :78
-    const float3 albedo = b0 ? sample_nearest(s, m.tex_c, tu, tv, true) : f3(at[3], at[4], at[5]);   // :80
+#define RC_ATTR(k) lerp3(__ldg(a + (k)), __ldg(b + (k)), __ldg(c + (k)), u, v)
+    float tu = 0.f, tv = 0.f;
+    if (b0 || b1) { tu = RC_ATTR(15); tv = 1.0f - RC_ATTR(16); }     // :78
+    const float3 albedo = b0 ? sample_nearest(s, m.tex_c, tu, tv, true) : f3(RC_ATTR(3), RC_ATTR(4), RC_ATTR(5));   // :80
     float3 Lc = f3(m.ka[0] * 0.05f * m.ka[3], m.ka[1] * 0.05f * m.ka[3], m.ka[2] * 0.05f * m.ka[3]);  // :82-83
-    const float3 Nv = f3(at[6], at[7], at[8]);
+    const float3 Nv = f3(RC_ATTR(6), RC_ATTR(7), RC_ATTR(8));
     float3 raw;
     if (b1) {
         const float3 cs = sample_nearest(s, m.tex_n, tu, tv, false);
         const float3 cf = f3(cs.x * 2.0f - 1.0f, cs.y * 2.0f - 1.0f, cs.z * 2.0f - 1.0f);             // :85
-        const float3 T = vnormalize(f3(at[9], at[10], at[11])), B = vnormalize(f3(at[12], at[13], at[14]));
+        const float3 T = vnormalize(f3(RC_ATTR(9), RC_ATTR(10), RC_ATTR(11))), B = vnormalize(f3(RC_ATTR(12), RC_ATTR(13), RC_ATTR(14)));
         raw = vnormalize(vadd(vadd(vscale(T, cf.x), vscale(B, cf.y)), vscale(Nv, cf.z)));             // :86
     } else {
         raw = vnormalize(Nv);
     }
+#undef RC_ATTR
     const float ndv = vdot(Vd, raw);                                 // :88
     const float3 N = ndv < 0.0f ? vneg(raw) : raw;                   // :89
+    // specular chain (normalize, powf) only when Ks can contribute: Ks present and non-zero, or Ns < 0
+    // (pow(0, Ns<0) = inf must still poison the result exactly as the plain formula does)
+    const bool spec = (m.ks[3] != 0.0f && (m.ks[0] != 0.0f || m.ks[1] != 0.0f || m.ks[2] != 0.0f)) || !(m.ns >= 0.0f);
     for (int li = 0; li < L.n; li++) {
         const float3 lp = f3(L.pos[li][0], L.pos[li][1], L.pos[li][2]);
         const float3 Ld = vnormalize(vsub(lp, P));                   // :91
         const float ndl = fmaxf(vdot(Ld, N), 0.0f);                  // :92
         const float kd = 0.7f * ndl * m.kd[3];
         Lc = f3(fmaf(m.kd[0], kd, Lc.x), fmaf(m.kd[1], kd, Lc.y), fmaf(m.kd[2], kd, Lc.z));           // :93
-        const float3 Hd = vnormalize(vadd(Vd, Ld));                  // :95
-        const float st = powf(fmaxf(vdot(N, Hd), 0.0f), m.ns);       // :96
-        const float ks = st * m.ks[3] * (ndv > 1e-6f ? 1.0f : 0.0f); // :97
-        Lc = f3(fmaf(m.ks[0], ks, Lc.x), fmaf(m.ks[1], ks, Lc.y), fmaf(m.ks[2], ks, Lc.z));
+        if (spec) {
+            const float3 Hd = vnormalize(vadd(Vd, Ld));                  // :95
+            const float st = powf(fmaxf(vdot(N, Hd), 0.0f), m.ns);       // :96
+            const float ks = st * m.ks[3] * (ndv > 1e-6f ? 1.0f : 0.0f); // :97
+            Lc = f3(fmaf(m.ks[0], ks, Lc.x), fmaf(m.ks[1], ks, Lc.y), fmaf(m.ks[2], ks, Lc.z));
+        }
     }
     const float pred = ((m.ka[0] - 1e-5f) + (m.kd[0] - 1e-5f) + (m.ks[0] - 1e-5f))
                      + ((m.ka[1] - 1e-5f) + (m.kd[1] - 1e-5f) + (m.ks[1] - 1e-5f))
