@@ -94,7 +94,7 @@
  *     delta = o_k - o_p; l2 = dot(delta,delta); h = dot(n_p, delta)
  *     g_k = l2 > 0 ? 1/(1 + RC_PLANE_K * (h*h)/l2) : 1
  *     w_k = bilinear_k * g_k * valid_k          (bilinear_k = wx*wy)
- *   S = ((w_0 + w_1) + w_2) + w_3;  if S <= 0: far = (0,0,0,1)  else
+ *   S = ((w_0 + w_1) + w_2) + w_3;  if S <= 0 (no valid upper probe): far = (sky, 0)  else
  *   far = sum_k (w_k/S) * 0.25*(((c_k0 + c_k1) + c_k2) + c_k3)   accumulated k = 0..3 with fma,
  *   c_kj = level i+1 texel of probe k, child j (j = 2*(cy) + cx), read back from float16
  *   merged.rgb = fma(raw.a, far.rgb, raw.rgb);  merged.a = raw.a * far.a;  stored as float16 (RN)

@@ -637,7 +637,7 @@ void rco_merge(const rco_params* p, int level,
         float S = ((w[0] + w[1]) + w[2]) + w[3];
         for (int dy = 0; dy < D; dy++) for (int dx = 0; dx < D; dx++) {
             float* t4 = base + 4 * ((size_t)dy * D + dx);
-            float far[4] = { 0, 0, 0, 1.0f };
+            float far[4] = { p->sky[0], p->sky[1], p->sky[2], 0.0f };   /* S8: no valid upper probe -> the sky */
             if (S > 0.0f) {
                 far[3] = 0.0f;
                 for (int k = 0; k < 4; k++) {

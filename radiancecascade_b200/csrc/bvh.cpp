@@ -31,7 +31,8 @@ struct Builder {
     float pad;
 
     static constexpr int kBins = 16;
-    static constexpr int kLeaf = 4;
+    int kLeaf = 4;          // largest leaf (<= 7: the leaf link stores the count in 3 bits)
+    float node_cost = 0.f;  // > 0: SAH termination — make a leaf of <= kLeaf triangles when splitting does not pay
 
     // Returns the child link (inner index or encoded leaf) for prims[first, first+count).
     int32_t build(uint32_t first, uint32_t count, Box& box_out, int depth)
@@ -42,7 +43,7 @@ struct Builder {
         for (uint32_t i = 0; i < count; i++) { box.grow(prims[first + i].box); cbox.grow(prims[first + i].c); }
         box_out = box;
         out->max_depth = std::max(out->max_depth, depth);
-        if (count <= kLeaf) return make_leaf(first, count);
+        if (count <= (uint32_t)(node_cost > 0.f ? 1 : kLeaf)) return make_leaf(first, count);
 
         int best_axis = -1, best_split = -1;
         float best_cost = FLT_MAX;
@@ -73,6 +74,10 @@ struct Builder {
                 float cost = la[b] * lc[b] + ra[b + 1] * rc_[b + 1];
                 if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = b; }
             }
+        }
+        if (node_cost > 0.f && count <= (uint32_t)kLeaf && best_axis >= 0) {
+            const float area = box.area();
+            if (area > 0.f && node_cost + best_cost / area >= (float)count) return make_leaf(first, count);
         }
         uint32_t mid;
         if (best_axis < 0) {
@@ -122,12 +127,14 @@ struct Builder {
 }  // namespace
 
 void build_bvh(const float* v0, const float* e1, const float* e2, const uint8_t* skip, uint32_t n_tris,
-               float pad, Bvh& out)
+               float pad, Bvh& out, int max_leaf, float node_cost)
 {
     out = Bvh();
     Builder b;
     b.out = &out;
     b.pad = pad;
+    b.kLeaf = max_leaf < 1 ? 1 : (max_leaf > 7 ? 7 : max_leaf);
+    b.node_cost = node_cost;
     b.prims.reserve(n_tris);
     for (uint32_t t = 0; t < n_tris; t++) {
         if (skip && skip[t]) continue;
@@ -155,7 +162,8 @@ void build_bvh(const float* v0, const float* e1, const float* e2, const uint8_t*
         b.write_node(0, empty, empty, ~0, ~0);
         return;
     }
-    if (n <= Builder::kLeaf) {
+    if (n <= (uint32_t)b.kLeaf) {
+        b.node_cost = 0.f;
         Box bx;
         int32_t c0 = b.build(0, n, bx, 1);
         b.write_node(0, bx, empty, c0, ~0);

@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(kBlock) k_link(DLevelSet ls, unsigned total, c
 }
 
 // far-field radiance of lower texel (dx, dy) from the merged upper level (S8)
-__device__ __forceinline__ float4 far_field(const uint2* __restrict__ up_texels, int UD, uint4 li, float4 lw, int dx, int dy)
+__device__ __forceinline__ float4 far_field(const uint2* __restrict__ up_texels, int UD, uint4 li, float4 lw, int dx, int dy, float3 sky)
 {
-    if (lw.x < 0.0f) return make_float4(0.f, 0.f, 0.f, 1.f);
+    if (lw.x < 0.0f) return make_float4(sky.x, sky.y, sky.z, 0.f);   // S8: no valid upper probe -> the sky
     float4 far = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t idx[4] = {li.x, li.y, li.z, li.w};
     const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
@@ -242,7 +242,7 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
             int dx, dy;
             if ((lv.D & (lv.D - 1)) == 0) { dx = (int)(d & (uint32_t)(lv.D - 1)); dy = (int)(d >> (31 - __clz(lv.D))); }
             else { dx = (int)(d % (uint32_t)lv.D); dy = (int)(d / (uint32_t)lv.D); }
-            const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy);
+            const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky);
             c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
             c.x = fminf(c.x, 65504.0f); c.y = fminf(c.y, 65504.0f); c.z = fminf(c.z, 65504.0f);
         } else {
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(128, 8) k_march_persist(DScene s, DLights L, D
 }
 
 // ------------------------------------------------------------------ stand-alone merge (in place)
-__global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, const float4* __restrict__ origin,
+__global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, float3 sky, const float4* __restrict__ origin,
                                                   uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
                                                   const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
 {
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, const float
     if (__ldg(origin + probe).w == 0.0f) return;
     const float4 raw = unpack_half4(texels[i]);
     const int dx = (int)(d % (uint32_t)lv.D), dy = (int)(d / (uint32_t)lv.D);
-    const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy);
+    const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky);
     float4 c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
     texels[i] = pack_half4(fminf(c.x, 65504.0f), fminf(c.y, 65504.0f), fminf(c.z, 65504.0f), c.w);
 }
@@ -721,11 +721,11 @@ int march_persist_blocks_per_sm()
     return a < b ? a : b;
 }
 
-void launch_merge(const DLevel& lv, const DLevel& up, const float4* origin, uint2* texels, const uint2* up_texels,
+void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const uint2* up_texels,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st)
 {
     const size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
-    k_merge<<<blocks_for(n), kBlock, 0, st>>>(lv, up.D, origin, texels, up_texels, link_idx, link_w);
+    k_merge<<<blocks_for(n), kBlock, 0, st>>>(lv, up.D, sky, origin, texels, up_texels, link_idx, link_w);
 }
 
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,

@@ -390,7 +390,11 @@ rc_status load_scene(rc_ctx* c)
     const uint32_t nt = h.info.num_triangles;
     const float diag = h.diag;
     Bvh bvh;
-    build_bvh(h.v0.data(), h.e1.data(), h.e2.data(), h.skip.data(), nt, 1e-4f * diag, bvh);
+    int max_leaf = 4;
+    float node_cost = 0.f;
+    if (const char* e = getenv("RC_BVH_LEAF")) max_leaf = atoi(e);
+    if (const char* e = getenv("RC_BVH_NODE_COST")) node_cost = (float)atof(e);
+    build_bvh(h.v0.data(), h.e1.data(), h.e2.data(), h.skip.data(), nt, 1e-4f * diag, bvh, max_leaf, node_cost);
     if (bvh.max_depth > 44) { c->error = "BVH deeper than the traversal stack"; return RC_ERR_SCENE_LOAD; }
     h.info.bvh_nodes = (uint32_t)bvh.nodes.size();
 
@@ -621,7 +625,7 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
                      c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0, st);
     c->launches++;
     if (!fused && !top) {
-        launch_merge(L, *U, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
+        launch_merge(L, *U, sky, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
         c->launches++;
     }
     // per-level events sit between the level kernels and would defeat their PDL overlap: opt-in only
