@@ -147,6 +147,12 @@ rc_status rc_render(rc_ctx* ctx, void* stream);
 /* Waits for the last rc_render and copies a target into host memory
  * (≙ reading back the colour attachment the caller owns). */
 rc_status rc_read_target(rc_ctx* ctx, rc_target which, void* host_dst, size_t bytes);
+/* Pipelined read-back of RC_TARGET_IRRADIANCE (double-buffered on the device): enqueues the copy of the
+ * frame just rendered on a separate copy stream and returns a ticket; the next rc_update / rc_render may be
+ * issued immediately and overlaps the copy.  rc_read_wait(ticket) blocks until host_dst is complete.
+ * host_dst should be page-locked, and at most two copies may be outstanding (one per buffer). */
+rc_status rc_read_target_async(rc_ctx* ctx, rc_target which, void* host_dst, size_t bytes, uint32_t* ticket);
+rc_status rc_read_wait(rc_ctx* ctx, uint32_t ticket);
 /* Size in bytes rc_read_target needs for `which`. */
 rc_status rc_target_bytes(rc_ctx* ctx, rc_target which, size_t* bytes);
 

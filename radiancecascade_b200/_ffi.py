@@ -74,6 +74,8 @@ SYMBOLS = {
     "rc_render_end": (C.c_int32, [_P, _P]),
     "rc_synchronize": (C.c_int32, [_P]),
     "rc_read_target": (C.c_int32, [_P, C.c_int, _P, C.c_size_t]),
+    "rc_read_target_async": (C.c_int32, [_P, C.c_int, _P, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "rc_read_wait": (C.c_int32, [_P, C.c_uint32]),
     "rc_target_bytes": (C.c_int32, [_P, C.c_int, C.POINTER(C.c_size_t)]),
     "rc_stage_times": (C.c_int32, [_P, C.POINTER(C.c_float), C.c_uint32]),
     "rc_level_times": (C.c_int32, [_P, C.POINTER(C.c_float), C.c_uint32]),

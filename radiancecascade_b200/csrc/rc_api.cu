@@ -102,7 +102,12 @@ struct rc_ctx {
     DevBuf<float> d_dirs;
     DevBuf<float> d_depth;
     DevBuf<uint32_t> d_prim, d_nrm;
-    DevBuf<uint2> d_albedo, d_direct, d_irr;
+    DevBuf<uint2> d_albedo, d_direct, d_irr, d_irr2;   // irradiance is double-buffered for rc_read_target_async
+    int irr_slot = 0;                    // buffer written by the last rc_render
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_frame_done = nullptr, ev_copy_done[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    uint2* irr() { return irr_slot ? d_irr2.p : d_irr.p; }
     DevBuf<uchar4> d_composite, d_direct_srgb;
     DevBuf<float> d_dbg_in, d_dbg_out;
     DevBuf<unsigned int> d_counters;     // per-level ray-fetch counters of the persistent march
@@ -283,6 +288,8 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
     CU_OK(c, c->d_albedo.alloc(npx));
     CU_OK(c, c->d_direct.alloc(npx));
     CU_OK(c, c->d_irr.alloc(npx));
+    CU_OK(c, c->d_irr2.alloc(npx));
+    c->copy_pending[0] = c->copy_pending[1] = false;
     CU_OK(c, c->d_composite.alloc(npx));
     CU_OK(c, c->d_direct_srgb.alloc(npx));
     c->cam.W = (int)W; c->cam.H = (int)H;
@@ -473,7 +480,11 @@ void destroy_ctx(rc_ctx* c)
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
     c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release();
     c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
-    c->d_direct.release(); c->d_irr.release(); c->d_composite.release(); c->d_direct_srgb.release();
+    c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_frame_done) cudaEventDestroy(c->ev_frame_done);
+    for (auto& e : c->ev_copy_done) if (e) cudaEventDestroy(e);
+    c->d_composite.release(); c->d_direct_srgb.release();
     c->d_dbg_in.release(); c->d_dbg_out.release(); c->d_counters.release();
     delete c;
 }
@@ -513,6 +524,9 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
     if (cudaSetDevice(c->device) != cudaSuccess) st = RC_ERR_CUDA;
     if (st == RC_OK && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) st = RC_ERR_CUDA;
     if (st == RC_OK) for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
+    if (st == RC_OK && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) st = RC_ERR_CUDA;
+    if (st == RC_OK && cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming) != cudaSuccess) st = RC_ERR_CUDA;
+    if (st == RC_OK) for (auto& e : c->ev_copy_done) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { st = RC_ERR_CUDA; break; }
     if (st == RC_OK) for (auto& e : c->ev_level) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
     if (st != RC_OK) c->error = "CUDA context / stream creation failed";
     if (st == RC_OK) st = load_scene(c);
@@ -658,9 +672,14 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
     if (!c) return RC_ERR_INVALID_ARG;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CU_OK(c, cudaEventRecord(c->ev[EV_LEVELS], st));
+    c->irr_slot ^= 1;
+    if (c->copy_pending[c->irr_slot]) {   // an asynchronous read-back of this buffer may still be in flight
+        CU_OK(c, cudaStreamWaitEvent(st, c->ev_copy_done[c->irr_slot], 0));
+        c->copy_pending[c->irr_slot] = false;
+    }
     const DLevel& L0 = c->levels[0];
     launch_gather(c->cam, L0, c->tile, c->d_origin.p + L0.probe_offset, c->d_cascade.p + L0.texel_offset, c->d_dirs.p,
-                  c->d_depth.p, c->d_nrm.p, c->d_irr.p, st);
+                  c->d_depth.p, c->d_nrm.p, c->irr(), st);
     c->launches++;
     CU_OK(c, cudaEventRecord(c->ev[EV_GATHER], st));
     CU_OK(c, cudaGetLastError());
@@ -717,7 +736,7 @@ rc_status rc_read_target(rc_ctx* c, rc_target which, void* host_dst, size_t byte
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     const void* src = nullptr;
     switch ((int)which) {
-    case RC_TARGET_IRRADIANCE: src = c->d_irr.p; break;
+    case RC_TARGET_IRRADIANCE: src = c->irr(); break;
     case RC_TARGET_DIRECT: src = c->d_direct.p; break;
     case RC_TARGET_ALBEDO: src = c->d_albedo.p; break;
     case RC_TARGET_DEPTH: src = c->d_depth.p; break;
@@ -725,7 +744,7 @@ rc_status rc_read_target(rc_ctx* c, rc_target which, void* host_dst, size_t byte
     case RC_TARGET_PRIM: src = c->d_prim.p; break;
     case RC_TARGET_COMPOSITE: case RC_TARGET_DIRECT_SRGB8:
         if (!c->composite_valid) {
-            launch_composite(c->tile, c->d_irr.p, c->d_albedo.p, c->d_direct.p, c->d_composite.p, c->d_direct_srgb.p, st);
+            launch_composite(c->tile, c->irr(), c->d_albedo.p, c->d_direct.p, c->d_composite.p, c->d_direct_srgb.p, st);
             c->composite_valid = true;
         }
         src = which == RC_TARGET_COMPOSITE ? (const void*)c->d_composite.p : (const void*)c->d_direct_srgb.p;
@@ -734,6 +753,32 @@ rc_status rc_read_target(rc_ctx* c, rc_target which, void* host_dst, size_t byte
     }
     CU_OK(c, cudaMemcpyAsync(host_dst, src, need, cudaMemcpyDeviceToHost, st));
     CU_OK(c, cudaStreamSynchronize(st));
+    return RC_OK;
+}
+
+rc_status rc_read_target_async(rc_ctx* c, rc_target which, void* host_dst, size_t bytes, uint32_t* ticket)
+{
+    if (!c || !host_dst || !ticket) return RC_ERR_INVALID_ARG;
+    if (which != RC_TARGET_IRRADIANCE) { c->error = "rc_read_target_async: only RC_TARGET_IRRADIANCE is double-buffered"; return RC_ERR_INVALID_ARG; }
+    const size_t need = (size_t)c->tile.w * c->tile.h * 8;
+    if (bytes < need) { c->error = "rc_read_target_async: buffer too small"; return RC_ERR_BUFFER_SIZE; }
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    const int slot = c->irr_slot;
+    CU_OK(c, cudaEventRecord(c->ev_frame_done, st));
+    CU_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_frame_done, 0));
+    CU_OK(c, cudaMemcpyAsync(host_dst, c->irr(), need, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU_OK(c, cudaEventRecord(c->ev_copy_done[slot], c->copy_stream));
+    c->copy_pending[slot] = true;
+    *ticket = (uint32_t)slot;
+    return RC_OK;
+}
+
+rc_status rc_read_wait(rc_ctx* c, uint32_t ticket)
+{
+    if (!c || ticket > 1) return RC_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    CU_OK(c, cudaEventSynchronize(c->ev_copy_done[ticket]));
     return RC_OK;
 }
 
@@ -941,7 +986,7 @@ rc_status rc_cascade_device_ptr(rc_ctx* c, uint32_t level, void** dev_ptr, size_
 rc_status rc_irradiance_device_ptr(rc_ctx* c, void** dev_ptr, size_t* bytes)
 {
     if (!c || !dev_ptr) return RC_ERR_INVALID_ARG;
-    *dev_ptr = c->d_irr.p;
+    *dev_ptr = c->irr();
     if (bytes) *bytes = (size_t)c->tile.w * c->tile.h * 8;
     return RC_OK;
 }

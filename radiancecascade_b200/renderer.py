@@ -240,6 +240,15 @@ class DefaultRenderer:
         self._check(self._lib.rc_read_target(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
+    def read_irradiance_async(self, host_ptr: int, nbytes: int) -> int:
+        """Pipelined read-back into page-locked memory at `host_ptr`; returns a ticket for read_wait()."""
+        t = C.c_uint32()
+        self._check(self._lib.rc_read_target_async(self._h, _ffi.RC_TARGET_IRRADIANCE, C.c_void_p(host_ptr), nbytes, C.byref(t)))
+        return t.value
+
+    def read_wait(self, ticket: int) -> None:
+        self._check(self._lib.rc_read_wait(self._h, ticket))
+
     def read_cascade(self, level: int) -> np.ndarray:
         return self.read_target(_ffi.RC_TARGET_CASCADE0 + level)
 

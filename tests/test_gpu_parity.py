@@ -310,3 +310,31 @@ def test_normal_map_toggle_and_no_textures_flag():
     alb = half_to_f32(r2.read_target(_ffi.RC_TARGET_ALBEDO))
     geo = r2.read_target(_ffi.RC_TARGET_PRIM) != 0xFFFFFFFF
     assert np.all(alb[geo][:, :3] == 1.0)      # colour falls back to the vertex colour default (1,1,1), src/renderer.rs:376-380
+
+
+def test_pipelined_readback_equals_blocking_readback():
+    """rc_read_target_async / rc_read_wait: frames read back while the next frame renders are identical to blocking reads."""
+    import torch
+    W, H = 160, 96
+    name = "cube"
+    st0, _, _ = frame_setup(name, W, H, frame=0)
+    r = rc.DefaultRenderer.new(0, (W, H), st0, rc.scenes.scene_path(name))
+    want = []
+    for f in range(5):
+        st, _, _ = frame_setup(name, W, H, frame=f)
+        r.update(st); r.render()
+        want.append(r.read_target(_ffi.RC_TARGET_IRRADIANCE).copy())
+    bufs = [torch.empty((H, W, 4), dtype=torch.float16, pin_memory=True) for _ in range(2)]
+    got, prev = [], None
+    for f in range(5):
+        st, _, _ = frame_setup(name, W, H, frame=f)
+        r.update(st); r.render()
+        t = r.read_irradiance_async(bufs[f & 1].data_ptr(), bufs[f & 1].numel() * 2)
+        if prev is not None:
+            r.read_wait(prev[0]); got.append(bufs[prev[1]].numpy().copy())
+        prev = (t, f & 1)
+    r.read_wait(prev[0]); got.append(bufs[prev[1]].numpy().copy())
+    assert len(got) == 5
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
+    assert not np.array_equal(want[0], want[3])      # the frames really differ
