@@ -488,8 +488,16 @@ __global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, float3 sky,
 __device__ __forceinline__ void gather_axis(int coord, int P, int gmax, int& i0, int& i1, float& w0, float& w1)
 {
     const int s = coord - P / 2;
-    const int base = (s >= 0) ? s / P : -((-s + P - 1) / P);
-    const float f = (float)(s - base * P) / (float)P;
+    int base, rem;
+    if ((P & (P - 1)) == 0) {           // power-of-two spacing: arithmetic shift == floor division
+        const int lp = 31 - __clz(P);
+        base = s >> lp;
+        rem = s & (P - 1);
+    } else {
+        base = (s >= 0) ? s / P : -((-s + P - 1) / P);
+        rem = s - base * P;
+    }
+    const float f = (float)rem / (float)P;
     i0 = min(max(base, 0), gmax - 1);
     i1 = min(max(base + 1, 0), gmax - 1);
     w0 = 1.0f - f; w1 = f;
@@ -501,13 +509,15 @@ __device__ __forceinline__ void gather_axis(int coord, int P, int gmax, int& i0,
 // banks), then every pixel reads its 4 probes from there.  The direct-from-L1 version spent ~9 L1
 // wavefronts per 128-bit load (lanes of a warp touch 9 different lines) and ran at 15 % (1080p) / 7.5 %
 // (4K) of the HBM roofline (profiles/r1_a_*).
+// DDT = D0*D0 when known at compile time (16 for the default D0 = 4: loops unroll, divisions become shifts), 0 = generic.
+template <int DDT>
 __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileRect tile, const float4* __restrict__ origin0,
                                                    const uint2* __restrict__ texels0, const float* __restrict__ dirs0,
                                                    const float* __restrict__ depth, const uint32_t* __restrict__ normal,
                                                    uint2* __restrict__ out, int max_probes)
 {
     extern __shared__ uint4 s_mem[];
-    const int DD = l0.D * l0.D, H2 = DD >> 1, stride = H2 + 1;
+    const int DD = DDT ? DDT : l0.D * l0.D, H2 = DD >> 1, stride = H2 + 1;
     uint4* s_tex = s_mem;                                                   // [max_probes][stride]
     float4* s_org = reinterpret_cast<float4*>(s_mem + (size_t)max_probes * stride);   // [max_probes]
     float* s_dirs = reinterpret_cast<float*>(s_org + max_probes);          // [DD][3]
@@ -520,15 +530,17 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
     gather_axis(X1, l0.P, l0.gw, unused, cmax, fu0, fu1);
     gather_axis(Y0, l0.P, l0.gh, rmin, unused, fu0, fu1);
     gather_axis(Y1, l0.P, l0.gh, unused, rmax, fu0, fu1);
-    const int ncols = cmax - cmin + 1, np = ncols * (rmax - rmin + 1);
+    const int ncols = cmax - cmin + 1, nrows = rmax - rmin + 1;
     const uint4* tex4 = reinterpret_cast<const uint4*>(texels0);
-    for (int i = threadIdx.x; i < np * H2; i += kBlock) {
-        const int p = i / H2, j = i - p * H2;
-        const size_t g = (size_t)(rmin + p / ncols - l0.py0) * l0.sw + (cmin + p % ncols - l0.px0);
-        s_tex[p * stride + j] = ld_u4(tex4 + g * H2 + j);
+    // one warp per probe row: consecutive lanes copy consecutive 16-byte pieces of consecutive probes
+    for (int pr = threadIdx.x >> 5; pr < nrows; pr += kBlock / 32) {
+        const size_t rowbase = (size_t)(rmin + pr - l0.py0) * l0.sw + (cmin - l0.px0);
+        for (int idx = threadIdx.x & 31; idx < ncols * H2; idx += 32) {
+            const int pc = idx / H2, j = idx - pc * H2;     // H2 is a compile-time power of two when DDT != 0
+            s_tex[(pr * ncols + pc) * stride + j] = ld_u4(tex4 + (rowbase + pc) * H2 + j);
+        }
+        for (int pc = threadIdx.x & 31; pc < ncols; pc += 32) s_org[pr * ncols + pc] = origin0[rowbase + pc];
     }
-    for (int i = threadIdx.x; i < np; i += kBlock)
-        s_org[i] = origin0[(size_t)(rmin + i / ncols - l0.py0) * l0.sw + (cmin + i % ncols - l0.px0)];
     for (int k = threadIdx.x; k < 3 * DD; k += kBlock) s_dirs[k] = dirs0[k];
     __syncthreads();
 
@@ -557,6 +569,7 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
     // S9: one cosine per direction, shared by the four probes; normalised quadrature q = pi / sum(cos)
     float3 acc[4] = {f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f)};
     float csum = 0.0f;
+#pragma unroll
     for (int di = 0; di < DD; di += 2) {
         const float ca = fmaxf(vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])), 0.0f);
         const float cb = fmaxf(vdot(n, f3(s_dirs[3 * di + 3], s_dirs[3 * di + 4], s_dirs[3 * di + 5])), 0.0f);
@@ -735,12 +748,16 @@ void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const fl
     const int DD = l0.D * l0.D;
     const int max_probes = ((32 + l0.P - 1) / l0.P + 2) * ((8 + l0.P - 1) / l0.P + 2);
     const size_t smem = (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
+    if (DD == 16) {
+        k_gather<16><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes);
+        return;
+    }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    k_gather<<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes);
+    k_gather<0><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes);
 }
 
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
