@@ -52,6 +52,12 @@
  *   q = fma(nx, Dx, fma(ny, Dy, Dc)) per component;  dir = q * (1/sqrt(dot(q,q)))
  *   dot(a,b) = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x)).
  *   closest hit over t in [0, FLT_MAX).  depth target = t (ray distance), -1 on miss.
+ *   albedo / direct targets = fs_main at the hit with V = -dir and the reference's sampler
+ *   (src/texture.rs:132-140: MirrorRepeat, mag Linear, min Nearest, one mip): the texture footprint
+ *   is the difference between the texcoords of the +x / +y neighbour pixels' rays on the hit
+ *   triangle's plane (S5 barycentrics without the inside tests) and this pixel's;
+ *   rho = max(|d(uv)/dx * size|, |d(uv)/dy * size|); rho <= 1 -> bilinear after the sRGB decode
+ *   (texel centres at integer + 0.5), otherwise, or when a neighbour ray is parallel to the plane, nearest.
  *
  * ---- S5. ray / triangle (two-sided Moller-Trumbore; cull_mode None,
  *          src/renderer.rs:332-343) ------------------------------------------

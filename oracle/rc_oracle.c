@@ -294,6 +294,51 @@ static v3 sample_nearest(const rco_scene* s, int tex, float u, float v, int srgb
     return V(p[0] / 255.0f, p[1] / 255.0f, p[2] / 255.0f);
 }
 
+/* The reference's sampler (src/texture.rs:132-140): MirrorRepeat, mag Linear, min Nearest, one mip level.
+ * duv = texture-coordinate differences to the +x / +y neighbour pixels; rho = max(|duv_x * size|, |duv_y * size|);
+ * magnification (linear, after the sRGB decode) iff rho <= 1, else — and whenever duv is NULL (a GI ray) — nearest. */
+static v3 texel_at(const rco_scene* s, int tex, long x, long y, int srgb)
+{
+    long w = s->tex_wh[2 * tex], h = s->tex_wh[2 * tex + 1];
+    const uint8_t* p = s->tex_data + s->tex_off[tex] + 4 * ((size_t)mirror_idx(y, h) * w + mirror_idx(x, w));
+    if (srgb) return V(s->srgb[p[0]], s->srgb[p[1]], s->srgb[p[2]]);
+    return V(p[0] / 255.0f, p[1] / 255.0f, p[2] / 255.0f);
+}
+
+static v3 sample_tex(const rco_scene* s, int tex, float u, float v, int srgb, const float* duv)
+{
+    if (tex < 0 || !duv) return sample_nearest(s, tex, u, v, srgb);
+    float w = (float)s->tex_wh[2 * tex], h = (float)s->tex_wh[2 * tex + 1];
+    float ax = duv[0] * w, ay = duv[1] * h, bx = duv[2] * w, by = duv[3] * h;
+    float rho = fmaxf(sqrtf(ax * ax + ay * ay), sqrtf(bx * bx + by * by));
+    if (!(rho <= 1.0f)) return sample_nearest(s, tex, u, v, srgb);
+    float fu = u * w - 0.5f, fv = v * h - 0.5f;
+    if (!(fabsf(fu) < 1e9f)) fu = 0.0f;
+    if (!(fabsf(fv) < 1e9f)) fv = 0.0f;
+    float iu = floorf(fu), iv = floorf(fv), a = fu - iu, b = fv - iv;
+    long x0 = (long)iu, y0 = (long)iv;
+    v3 c00 = texel_at(s, tex, x0, y0, srgb), c10 = texel_at(s, tex, x0 + 1, y0, srgb);
+    v3 c01 = texel_at(s, tex, x0, y0 + 1, srgb), c11 = texel_at(s, tex, x0 + 1, y0 + 1, srgb);
+    float ia = 1.0f - a, ib = 1.0f - b;
+    v3 top = V(c00.x * ia + c10.x * a, c00.y * ia + c10.y * a, c00.z * ia + c10.z * a);
+    v3 bot = V(c01.x * ia + c11.x * a, c01.y * ia + c11.y * a, c01.z * ia + c11.z * a);
+    return V(top.x * ib + bot.x * b, top.y * ib + bot.y * b, top.z * ib + bot.z * b);
+}
+
+/* S5 arithmetic without the inside tests: barycentrics of ray (o,d) on the plane of triangle t */
+static int plane_bary(const rco_scene* s, uint32_t t, v3 o, v3 d, float* u, float* v)
+{
+    v3 e1 = s->e1[t], e2 = s->e2[t];
+    v3 p = vcross(d, e2);
+    float det = vdot(e1, p);
+    if (!(det != 0.0f)) return 0;
+    float inv = 1.0f / det;
+    v3 sv = vsub(o, s->v0[t]);
+    *u = vdot(sv, p) * inv;
+    *v = vdot(d, vcross(sv, e1)) * inv;
+    return 1;
+}
+
 typedef struct { int n; float pos[8][3]; uint32_t flags; } rco_lights;
 
 /* S7 attribute interpolation: fma(a2, v, fma(a1, u, a0*((1-u)-v))) */
@@ -307,8 +352,8 @@ static inline float clamp_rad(float x) { return fminf(fmaxf(x, 0.0f), 65504.0f);
 
 /* fs_main (src/shader.wgsl:76-100) at a hit, view vector Vd = -ray dir.
  * Returns Ke + (L + unlit)*albedo in rad, and the shading normal / albedo / lit colour. */
-static void rco_shade(const rco_scene* s, uint32_t prim, float u, float v, v3 P, v3 Vd,
-                      const rco_lights* lights, v3* rad, v3* nshade, v3* albedo_out, v3* direct_out)
+static void rco_shade_fp(const rco_scene* s, uint32_t prim, float u, float v, v3 P, v3 Vd,
+                         const rco_lights* lights, v3* rad, v3* nshade, v3* albedo_out, v3* direct_out, const float* fp)
 {
     const uint32_t* ix = s->tris + 3 * (size_t)prim;
     const float *a = s->verts + 17 * (size_t)ix[0], *b = s->verts + 17 * (size_t)ix[1], *c = s->verts + 17 * (size_t)ix[2];
@@ -320,13 +365,22 @@ static void rco_shade(const rco_scene* s, uint32_t prim, float u, float v, v3 P,
     if (!(lights->flags & 1u)) eb &= 1u;          /* normal-map toggle (src/renderer.rs:623) */
     int b0 = eb & 1, b1 = (eb >> 1) & 1;
     float tu = at[15], tv = 1.0f - at[16];                                  /* :78 */
+    float duv_store[4];
+    const float* duv = NULL;
+    if (fp) {   /* texture footprint of a primary ray: neighbours' texcoords minus this pixel's */
+        duv_store[0] = lerp3(a[15], b[15], c[15], fp[0], fp[1]) - tu;
+        duv_store[1] = (1.0f - lerp3(a[16], b[16], c[16], fp[0], fp[1])) - tv;
+        duv_store[2] = lerp3(a[15], b[15], c[15], fp[2], fp[3]) - tu;
+        duv_store[3] = (1.0f - lerp3(a[16], b[16], c[16], fp[2], fp[3])) - tv;
+        duv = duv_store;
+    }
     v3 color = V(at[3], at[4], at[5]);
-    v3 albedo = b0 ? sample_nearest(s, s->tex_id[2 * m], tu, tv, 1) : color; /* :80 */
+    v3 albedo = b0 ? sample_tex(s, s->tex_id[2 * m], tu, tv, 1, duv) : color; /* :80 */
     v3 L = V(um[0] * 0.05f * um[3], um[1] * 0.05f * um[3], um[2] * 0.05f * um[3]);   /* :82-83 */
     v3 Nv = V(at[6], at[7], at[8]);
     v3 raw;
     if (b1) {
-        v3 cs = sample_nearest(s, s->tex_id[2 * m + 1], tu, tv, 0);
+        v3 cs = sample_tex(s, s->tex_id[2 * m + 1], tu, tv, 0, duv);
         v3 cf = V(cs.x * 2.0f - 1.0f, cs.y * 2.0f - 1.0f, cs.z * 2.0f - 1.0f);      /* :85 */
         v3 T = vnormalize(V(at[9], at[10], at[11])), B = vnormalize(V(at[12], at[13], at[14]));
         v3 mix = vadd(vadd(vscale(T, cf.x), vscale(B, cf.y)), vscale(Nv, cf.z));  /* :86, Nv not normalised */
@@ -357,6 +411,12 @@ static void rco_shade(const rco_scene* s, uint32_t prim, float u, float v, v3 P,
     if (nshade) *nshade = N;
     if (albedo_out) *albedo_out = albedo;
     if (direct_out) *direct_out = lit;
+}
+
+static void rco_shade(const rco_scene* s, uint32_t prim, float u, float v, v3 P, v3 Vd,
+                      const rco_lights* lights, v3* rad, v3* nshade, v3* albedo_out, v3* direct_out)
+{
+    rco_shade_fp(s, prim, u, v, P, Vd, lights, rad, nshade, albedo_out, direct_out, NULL);   /* GI hit: nearest filter (S7) */
 }
 
 /* in: [n][8] = prim bits, u, v, pad, view origin xyz, pad -> out [n][4] rgb of Ke + fs_main, a = 0 */
@@ -507,7 +567,12 @@ void rco_gbuffer(const rco_scene* s, const rco_params* p, const float cam[20], c
             continue;
         }
         v3 P = vfma(h.t, d, eye), rad, ns, al, di;
-        rco_shade(s, h.prim, h.u, h.v, P, vneg(d), &L, &rad, &ns, &al, &di);
+        float fp[4];
+        const float* fpp = NULL;
+        if (s->ebit[s->tri_model[h.prim]] != 0u &&
+            plane_bary(s, h.prim, eye, primary_dir(p, b, x + 1, y), &fp[0], &fp[1]) &&
+            plane_bary(s, h.prim, eye, primary_dir(p, b, x, y + 1), &fp[2], &fp[3])) fpp = fp;
+        rco_shade_fp(s, h.prim, h.u, h.v, P, vneg(d), &L, &rad, &ns, &al, &di, fpp);
         depth[o] = h.t; prim[o] = h.prim; normal[o] = oct_encode(ns);
         float av[3] = { al.x, al.y, al.z }, dv[3] = { di.x, di.y, di.z };
         for (int k = 0; k < 3; k++) {

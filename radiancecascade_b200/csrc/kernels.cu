@@ -50,7 +50,17 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLigh
         return;
     }
     const float3 P = vfma(h.t, d, cam.eye);
-    const Shade sh = shade_hit(s, L, h.prim, h.u, h.v, P, vneg(d));
+    // texture footprint: where the +x / +y neighbour pixels' rays meet this triangle's plane (S4)
+    float fp[4];
+    const float* fpp = nullptr;
+    if (s.mats[s.tri_model[h.prim]].ebit != 0u) {   // only textured materials need a footprint
+        const float* v0p = s.verts + 17 * (size_t)s.tris[3 * (size_t)h.prim];
+        const float3 v0 = f3(__ldg(v0p), __ldg(v0p + 1), __ldg(v0p + 2));
+        const float3 e1 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim)), e2 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim + 1));
+        const float3 dx = primary_dir(cam, tile.x0 + tx + 1, tile.y0 + ty), dy = primary_dir(cam, tile.x0 + tx, tile.y0 + ty + 1);
+        if (plane_bary(v0, e1, e2, cam.eye, dx, fp[0], fp[1]) && plane_bary(v0, e1, e2, cam.eye, dy, fp[2], fp[3])) fpp = fp;
+    }
+    const Shade sh = shade_hit(s, L, h.prim, h.u, h.v, P, vneg(d), fpp);
     out.depth[o] = h.t;
     out.prim[o] = h.prim;
     out.normal[o] = oct_encode(sh.n);

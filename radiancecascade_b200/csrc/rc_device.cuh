@@ -179,6 +179,54 @@ __device__ __forceinline__ float3 sample_nearest(const DScene& s, int tex, float
     return f3(p.x / 255.0f, p.y / 255.0f, p.z / 255.0f);
 }
 
+__device__ __forceinline__ float3 fetch_texel(const DScene& s, const DTexture& t, long long ix, long long iy, bool srgb)
+{
+    const int x = mirror_idx(ix, t.w), y = mirror_idx(iy, t.h);
+    const uchar4 p = *reinterpret_cast<const uchar4*>(s.tex_data + t.offset + 4 * ((size_t)y * t.w + x));
+    if (srgb) return f3(__ldg(s.srgb + p.x), __ldg(s.srgb + p.y), __ldg(s.srgb + p.z));
+    return f3(p.x / 255.0f, p.y / 255.0f, p.z / 255.0f);
+}
+
+// The reference's sampler (src/texture.rs:132-140): MirrorRepeat, mag Linear, min Nearest, one mip.  `duv` holds the
+// texture-coordinate differences to the pixel's +x and +y neighbours (du/dx, dv/dx, du/dy, dv/dy); the filter is
+// chosen as the API specifies: rho = max(|d(uv)/dx * size|, |d(uv)/dy * size|), magnification iff log2(rho) <= 0.
+// Linear filtering happens after the sRGB decode.  duv == nullptr (GI hit: a ray has no derivatives) -> nearest (S7).
+__device__ __forceinline__ float3 sample_tex(const DScene& s, int tex, float u, float v, bool srgb, const float* duv)
+{
+    if (tex < 0 || duv == nullptr) return sample_nearest(s, tex, u, v, srgb);
+    const DTexture t = s.tex[tex];
+    const float w = (float)t.w, h = (float)t.h;
+    const float ax = duv[0] * w, ay = duv[1] * h, bx = duv[2] * w, by = duv[3] * h;
+    const float rho = fmaxf(sqrtf(ax * ax + ay * ay), sqrtf(bx * bx + by * by));
+    if (!(rho <= 1.0f)) return sample_nearest(s, tex, u, v, srgb);      // minification (or undefined derivatives)
+    float fu = u * w - 0.5f, fv = v * h - 0.5f;
+    if (!(fabsf(fu) < 1e9f)) fu = 0.0f;
+    if (!(fabsf(fv) < 1e9f)) fv = 0.0f;
+    const float iu = floorf(fu), iv = floorf(fv);
+    const float a = fu - iu, b = fv - iv;
+    const long long x0 = (long long)iu, y0 = (long long)iv;
+    const float3 c00 = fetch_texel(s, t, x0, y0, srgb), c10 = fetch_texel(s, t, x0 + 1, y0, srgb);
+    const float3 c01 = fetch_texel(s, t, x0, y0 + 1, srgb), c11 = fetch_texel(s, t, x0 + 1, y0 + 1, srgb);
+    const float ia = 1.0f - a, ib = 1.0f - b;
+    const float3 top = f3(c00.x * ia + c10.x * a, c00.y * ia + c10.y * a, c00.z * ia + c10.z * a);
+    const float3 bot = f3(c01.x * ia + c11.x * a, c01.y * ia + c11.y * a, c01.z * ia + c11.z * a);
+    return f3(top.x * ib + bot.x * b, top.y * ib + bot.y * b, top.z * ib + bot.z * b);
+}
+
+// barycentrics of the point where ray (o, d) meets the plane of triangle (v0, e1, e2) — S5 arithmetic without the
+// inside tests; used for the texture footprint of primary rays
+__device__ __forceinline__ bool plane_bary(float3 v0, float3 e1, float3 e2, float3 o, float3 d, float& u, float& v)
+{
+    const float3 p = vcross(d, e2);
+    const float det = vdot(e1, p);
+    if (!(det != 0.0f)) return false;
+    const float inv = 1.0f / det;
+    const float3 sv = vsub(o, v0);
+    u = vdot(sv, p) * inv;
+    v = vdot(d, vcross(sv, e1)) * inv;
+    return true;
+}
+
 __device__ __forceinline__ float lerp3(float a0, float a1, float a2, float u, float v)
 {
     const float w = (1.0f - u) - v;
@@ -190,8 +238,10 @@ __device__ __forceinline__ float clamp_rad(float x) { return fminf(fmaxf(x, 0.0f
 struct Shade { float3 rad, n, albedo, direct; };
 
 // fs_main at a hit with view vector Vd (= -ray direction); rad = Ke + (L + unlit) * albedo.
+// fp (optional): barycentrics (u,v) of the +x and +y neighbour pixels' rays on this triangle's plane -> texture
+// footprint for the sampler's mag/min decision (G-buffer pass only).
 __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, uint32_t prim, float u, float v,
-                                           float3 P, float3 Vd)
+                                           float3 P, float3 Vd, const float* fp = nullptr)
 {
     const uint32_t i0 = s.tris[3 * (size_t)prim], i1 = s.tris[3 * (size_t)prim + 1], i2 = s.tris[3 * (size_t)prim + 2];
     const float* a = s.verts + 17 * (size_t)i0;
@@ -206,13 +256,25 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
     const bool b0 = eb & 1u, b1 = (eb >> 1) & 1u;
 #define RC_ATTR(k) lerp3(__ldg(a + (k)), __ldg(b + (k)), __ldg(c + (k)), u, v)
     float tu = 0.f, tv = 0.f;
-    if (b0 || b1) { tu = RC_ATTR(15); tv = 1.0f - RC_ATTR(16); }     // :78
-    const float3 albedo = b0 ? sample_nearest(s, m.tex_c, tu, tv, true) : f3(RC_ATTR(3), RC_ATTR(4), RC_ATTR(5));   // :80
+    float duv_store[4];
+    const float* duv = nullptr;
+    if (b0 || b1) {
+        tu = RC_ATTR(15); tv = 1.0f - RC_ATTR(16);                   // :78
+        if (fp) {
+            const float ux = lerp3(__ldg(a + 15), __ldg(b + 15), __ldg(c + 15), fp[0], fp[1]);
+            const float vx = 1.0f - lerp3(__ldg(a + 16), __ldg(b + 16), __ldg(c + 16), fp[0], fp[1]);
+            const float uy = lerp3(__ldg(a + 15), __ldg(b + 15), __ldg(c + 15), fp[2], fp[3]);
+            const float vy = 1.0f - lerp3(__ldg(a + 16), __ldg(b + 16), __ldg(c + 16), fp[2], fp[3]);
+            duv_store[0] = ux - tu; duv_store[1] = vx - tv; duv_store[2] = uy - tu; duv_store[3] = vy - tv;
+            duv = duv_store;
+        }
+    }
+    const float3 albedo = b0 ? sample_tex(s, m.tex_c, tu, tv, true, duv) : f3(RC_ATTR(3), RC_ATTR(4), RC_ATTR(5));   // :80
     float3 Lc = f3(m.ka[0] * 0.05f * m.ka[3], m.ka[1] * 0.05f * m.ka[3], m.ka[2] * 0.05f * m.ka[3]);  // :82-83
     const float3 Nv = f3(RC_ATTR(6), RC_ATTR(7), RC_ATTR(8));
     float3 raw;
     if (b1) {
-        const float3 cs = sample_nearest(s, m.tex_n, tu, tv, false);
+        const float3 cs = sample_tex(s, m.tex_n, tu, tv, false, duv);
         const float3 cf = f3(cs.x * 2.0f - 1.0f, cs.y * 2.0f - 1.0f, cs.z * 2.0f - 1.0f);             // :85
         const float3 T = vnormalize(f3(RC_ATTR(9), RC_ATTR(10), RC_ATTR(11))), B = vnormalize(f3(RC_ATTR(12), RC_ATTR(13), RC_ATTR(14)));
         raw = vnormalize(vadd(vadd(vscale(T, cf.x), vscale(B, cf.y)), vscale(Nv, cf.z)));             // :86
