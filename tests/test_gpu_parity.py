@@ -338,3 +338,32 @@ def test_pipelined_readback_equals_blocking_readback():
     for a, b in zip(got, want):
         assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
     assert not np.array_equal(want[0], want[3])      # the frames really differ
+
+
+def test_scene_without_geometry_renders_background(tmp_path):
+    """An OBJ with no faces: every pixel is background, every probe invalid; nothing crashes, E = 0."""
+    p = tmp_path / "nofaces.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\n")
+    st = rc.AppState()
+    st.uniform_camera = rc.UniformCamera.look_at((0, 0, 5), (0, 0, 0), rc.Projection.new(64, 48, 45.0, 0.1, 100.0))
+    r = rc.DefaultRenderer.new(0, (64, 48), st, str(p), rc.CascadeConfig(interval0=0.01, t_far=10.0))
+    r.update(st); r.render()
+    assert np.all(r.read_target(_ffi.RC_TARGET_PRIM) == 0xFFFFFFFF)
+    assert np.all(r.read_target(_ffi.RC_TARGET_DEPTH) == -1.0)
+    assert not r.read_target(_ffi.RC_TARGET_IRRADIANCE).any()
+
+
+def test_single_triangle_scene_matches_oracle(tmp_path):
+    p = tmp_path / "tri.obj"
+    p.write_text("v -1 -1 0\nv 1 -1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0.5 1\nf 1/1 2/2 3/3\n")
+    st = rc.AppState()
+    st.uniform_camera = rc.UniformCamera.look_at((0.3, 0.2, 3), (0, 0, 0), rc.Projection.new(80, 60, 45.0, 0.1, 100.0))
+    st.light_position = (0.0, 0.5, 2.0)
+    r = rc.DefaultRenderer.new(0, (80, 60), st, str(p))
+    r.update(st); r.render()
+    osc = go.OracleScene(str(p))
+    out = osc.render(osc.params(80, 60, store_half=True), st.uniform_camera.as_array(), np.array([[0.0, 0.5, 2.0, 1.0]], np.float32))
+    assert np.array_equal(r.read_target(_ffi.RC_TARGET_PRIM), out["prim"])
+    assert np.array_equal(r.read_target(_ffi.RC_TARGET_DEPTH), out["depth"])
+    E, Eo = half_to_f32(r.read_target(_ffi.RC_TARGET_IRRADIANCE)), out["irradiance"]
+    assert np.abs(E - Eo).max() <= 1e-2 * max(float(Eo.max()), 1e-6) + 1e-6

@@ -168,3 +168,23 @@ def test_png_variants(tmp_path):
     assert np.array_equal(decode_image_file(p), _pil_rgba(p))
     with pytest.raises(rc.RcError):
         decode_image_file(str(tmp_path / "missing.png"))
+
+
+def test_empty_and_degenerate_scenes(tmp_path):
+    """Edge cases of the loader: no faces at all, only a line element, a face with a missing vertex."""
+    p = tmp_path / "nofaces.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\n")
+    hs = rc.ObjScene.load(str(p))             # tobj emits one (empty) model for the trailing object
+    osc, _ = ri.ObjScene.load(str(p))
+    assert hs.info().num_models == len(osc) == 1 and hs.info().num_triangles == 0 and hs.info().num_vertices == 0
+    p = tmp_path / "line.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nl 1 2\nf 1 2 3\n")
+    hs = rc.ObjScene.load(str(p))
+    osc, _ = ri.ObjScene.load(str(p))
+    v, i = hs.model_stream(0)
+    assert np.array_equal(i, osc[0].indices()) and len(i) == 6       # (a,b,b) reversed -> (b,b,a), then the triangle
+    assert same_bits(v, osc[0].vertex_stream())
+    p = tmp_path / "oob.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nf 1 2 7\n")
+    with pytest.raises(rc.RcError):
+        rc.ObjScene.load(str(p))              # tobj: FaceVertexOutOfBounds -> the reference's unwrap() panics
