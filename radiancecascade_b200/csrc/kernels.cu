@@ -476,6 +476,21 @@ __global__ void __launch_bounds__(128, 8) k_march_persist(DScene s, DLights L, D
     }
 }
 
+// ------------------------------------------------------------------ top level without geometry in range
+// With the default intervals the top level starts at 1.33 x the scene diagonal: from a probe on a surface every
+// point of such a ray lies outside the scene's bounding box, so the march is a guaranteed miss and the level is
+// filled with (sky, 1) — (0,0,0,1) for invalid probes — at streaming speed (128-bit stores, two texels per thread).
+__global__ void __launch_bounds__(kBlock) k_fill_top(DLevel lv, float3 sky, const float4* __restrict__ origin, uint4* __restrict__ texels2)
+{
+    const size_t half = ((size_t)lv.D * lv.D) >> 1;
+    const size_t n2 = (size_t)lv.sw * lv.sh * half;
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n2) return;
+    const bool valid = __ldg(origin + (i / half)).w != 0.0f;
+    const uint2 t = valid ? pack_half4(sky.x, sky.y, sky.z, 1.0f) : pack_half4(0.f, 0.f, 0.f, 1.0f);
+    texels2[i] = make_uint4(t.x, t.y, t.x, t.y);
+}
+
 // ------------------------------------------------------------------ stand-alone merge (in place)
 __global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, float3 sky, const float4* __restrict__ origin,
                                                   uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
@@ -742,6 +757,12 @@ int march_persist_blocks_per_sm()
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_march_persist<true>, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_march_persist<false>, 128, 0);
     return a < b ? a : b;
+}
+
+void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, cudaStream_t st)
+{
+    const size_t n2 = (size_t)lv.sw * lv.sh * (((size_t)lv.D * lv.D) >> 1);
+    k_fill_top<<<blocks_for(n2), kBlock, 0, st>>>(lv, sky, origin, reinterpret_cast<uint4*>(texels));
 }
 
 void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const uint2* up_texels,

@@ -29,6 +29,8 @@ void launch_march_persist(const DScene& s, const DLights& L, const DLevel& lv, c
                           const uint4* link_idx, const float4* link_w, bool fused, int map, int thresh, int grid_blocks,
                           unsigned int* counter, bool pdl, cudaStream_t st);
 int march_persist_blocks_per_sm();
+// top level whose interval lies entirely outside the scene bounds: fill with (sky, 1) instead of marching
+void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, cudaStream_t st);
 void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const uint2* up_texels,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st);
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,

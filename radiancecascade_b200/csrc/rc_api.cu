@@ -128,6 +128,7 @@ struct rc_ctx {
     int march_persist = 0, march_thresh = 8, march_grid = 0, march_pdl = 1;   // persistent variant measured slower
     bool level_timing = false;
     int march_compact = 0;   // bit i: level i uses the block-compacting march kernel
+    int fill_top = 1;        // fill a top level that cannot hit anything instead of marching it (exact)
     int march_waves = 0;     // > 0: march grid capped at SMs * occ * waves blocks (grid-stride loop); 0: one thread per ray
     int sm_count = 148;
 
@@ -629,6 +630,15 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     const float3 sky = make_float3(c->cfg.sky[0], c->cfg.sky[1], c->cfg.sky[2]);
     uint2* tex = c->d_cascade.p + L.texel_offset;
     const uint2* up = top ? nullptr : c->d_cascade.p + U->texel_offset;
+    // S7 shortcut, exact: a ray that starts on a surface (inside the scene's box grown by the probe offset) is
+    // farther than the box diagonal from every triangle once t > diag + 2*offset -> the whole level misses
+    if (top && c->fill_top && L.t0 > c->host.diag * 1.001f + 2.0f * c->offset && (((size_t)L.texel_offset) & 1) == 0) {
+        launch_fill_top(L, sky, c->d_origin.p + L.probe_offset, tex, st);
+        c->launches++;
+        if (c->level_timing) CU_OK(c, cudaEventRecord(c->ev_level[level], st));
+        CU_OK(c, cudaGetLastError());
+        return RC_OK;
+    }
     if (c->march_persist)
         launch_march_persist(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
                              c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_thresh,
@@ -659,6 +669,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "march_occ" && value >= 8 && value <= 16) c->march_occ = value;
     else if (k == "march_compact" && value >= 0) c->march_compact = value;
     else if (k == "march_waves" && value >= 0) c->march_waves = value;
+    else if (k == "fill_top") c->fill_top = value != 0;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
     else if (k.rfind("march_map", 0) == 0 && k.size() == 10 && k[9] >= '0' && k[9] <= '9' && value >= 0 && value <= 2)
