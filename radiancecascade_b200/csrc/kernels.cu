@@ -33,6 +33,19 @@ __device__ __forceinline__ uint4 ld_u4(const void* p)
 }
 
 // ------------------------------------------------------------------ G-buffer
+// Per frame the GI path needs primary visibility only: distance, triangle id, barycentrics and the two-sided
+// shading normal.  fs_main's colour outputs (the reference's whole frame, src/shader.wgsl:76-100) are not an input
+// of any GI stage, so they are evaluated on demand by k_direct (deferred shading) when a DIRECT / ALBEDO /
+// COMPOSITE target is read.
+__device__ __forceinline__ bool pixel_footprint(const DScene& s, const DCamera& cam, uint32_t prim, int x, int y, float* fp)
+{
+    const float* v0p = s.verts + 17 * (size_t)s.tris[3 * (size_t)prim];
+    const float3 v0 = f3(__ldg(v0p), __ldg(v0p + 1), __ldg(v0p + 2));
+    const float3 e1 = xyz(__ldg(s.tri_eg + 2 * (size_t)prim)), e2 = xyz(__ldg(s.tri_eg + 2 * (size_t)prim + 1));
+    const float3 dx = primary_dir(cam, x + 1, y), dy = primary_dir(cam, x, y + 1);
+    return plane_bary(v0, e1, e2, cam.eye, dx, fp[0], fp[1]) && plane_bary(v0, e1, e2, cam.eye, dy, fp[2], fp[3]);
+}
+
 __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out)
 {
     // a block covers 32x8 pixels; each warp an 8x4 pixel tile (compact frustum -> coherent traversal; four
@@ -45,27 +58,41 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLigh
     const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
     const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
     if (h.prim == 0xffffffffu) {
-        out.depth[o] = -1.0f; out.prim[o] = 0xffffffffu; out.normal[o] = 0u;
-        out.albedo[o] = make_uint2(0u, 0u); out.direct[o] = make_uint2(0u, 0u);
+        out.depth[o] = -1.0f; out.prim[o] = 0xffffffffu; out.normal[o] = 0u; out.bary[o] = make_float2(0.f, 0.f);
         return;
     }
     const float3 P = vfma(h.t, d, cam.eye);
-    // texture footprint: where the +x / +y neighbour pixels' rays meet this triangle's plane (S4)
+    // a normal-mapped material needs the texture footprint for the sampler's mag/min decision (S4)
     float fp[4];
     const float* fpp = nullptr;
-    if (s.mats[s.tri_model[h.prim]].ebit != 0u) {   // only textured materials need a footprint
-        const float* v0p = s.verts + 17 * (size_t)s.tris[3 * (size_t)h.prim];
-        const float3 v0 = f3(__ldg(v0p), __ldg(v0p + 1), __ldg(v0p + 2));
-        const float3 e1 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim)), e2 = xyz(__ldg(s.tri_eg + 2 * (size_t)h.prim + 1));
-        const float3 dx = primary_dir(cam, tile.x0 + tx + 1, tile.y0 + ty), dy = primary_dir(cam, tile.x0 + tx, tile.y0 + ty + 1);
-        if (plane_bary(v0, e1, e2, cam.eye, dx, fp[0], fp[1]) && plane_bary(v0, e1, e2, cam.eye, dy, fp[2], fp[3])) fpp = fp;
-    }
-    const Shade sh = shade_hit(s, L, h.prim, h.u, h.v, P, vneg(d), fpp);
+    if ((s.mats[s.tri_model[h.prim]].ebit & 2u) && (L.flags & 1u) && pixel_footprint(s, cam, h.prim, tile.x0 + tx, tile.y0 + ty, fp)) fpp = fp;
+    const Shade sh = shade_hit<true>(s, L, h.prim, h.u, h.v, P, vneg(d), fpp);
     out.depth[o] = h.t;
     out.prim[o] = h.prim;
     out.normal[o] = oct_encode(sh.n);
-    out.albedo[o] = pack_half4(clamp_rad(sh.albedo.x), clamp_rad(sh.albedo.y), clamp_rad(sh.albedo.z), 1.0f);
-    out.direct[o] = pack_half4(clamp_rad(sh.direct.x), clamp_rad(sh.direct.y), clamp_rad(sh.direct.z), 1.0f);
+    out.bary[o] = make_float2(h.u, h.v);
+}
+
+// fs_main for every covered pixel from the stored visibility (on demand; not part of the per-frame GI path)
+__global__ void __launch_bounds__(kBlock) k_direct(DScene s, DCamera cam, DLights L, TileRect tile, const float* __restrict__ depth,
+                                                   const uint32_t* __restrict__ prim, const float2* __restrict__ bary,
+                                                   uint2* __restrict__ albedo, uint2* __restrict__ direct)
+{
+    const int tx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ty = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (tx >= tile.w || ty >= tile.h) return;
+    const size_t o = (size_t)ty * tile.w + tx;
+    const uint32_t id = prim[o];
+    if (id == 0xffffffffu) { albedo[o] = make_uint2(0u, 0u); direct[o] = make_uint2(0u, 0u); return; }
+    const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
+    const float3 P = vfma(depth[o], d, cam.eye);
+    const float2 uv = bary[o];
+    float fp[4];
+    const float* fpp = nullptr;
+    if (s.mats[s.tri_model[id]].ebit != 0u && pixel_footprint(s, cam, id, tile.x0 + tx, tile.y0 + ty, fp)) fpp = fp;
+    const Shade sh = shade_hit<false>(s, L, id, uv.x, uv.y, P, vneg(d), fpp);
+    albedo[o] = pack_half4(clamp_rad(sh.albedo.x), clamp_rad(sh.albedo.y), clamp_rad(sh.albedo.z), 1.0f);
+    direct[o] = pack_half4(clamp_rad(sh.direct.x), clamp_rad(sh.direct.y), clamp_rad(sh.direct.z), 1.0f);
 }
 
 // ------------------------------------------------------------------ probes (S6), all levels in one launch
@@ -677,6 +704,13 @@ void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileR
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
     k_gbuffer<<<grid, kBlock, 0, st>>>(s, cam, L, tile, out);
+}
+
+void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
+                   const float2* bary, uint2* albedo, uint2* direct, cudaStream_t st)
+{
+    dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
+    k_direct<<<grid, kBlock, 0, st>>>(s, cam, L, tile, depth, prim, bary, albedo, direct);
 }
 
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,

@@ -5,12 +5,15 @@
 namespace rc {
 
 struct GBufferOut {
-    float* depth; uint32_t* prim; uint32_t* normal; uint2* albedo; uint2* direct;
+    float* depth; uint32_t* prim; uint32_t* normal; float2* bary;
 };
 
 struct TileRect { int x0, y0, w, h; };
 
 void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, cudaStream_t st);
+// deferred fs_main: albedo / direct colour from the stored visibility (on demand)
+void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
+                   const float2* bary, uint2* albedo, uint2* direct, cudaStream_t st);
 // all levels' probes in one launch; anchors inside the tile reuse the G-buffer hit
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, cudaStream_t st);

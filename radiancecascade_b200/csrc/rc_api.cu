@@ -115,7 +115,10 @@ struct rc_ctx {
     DCamera cam{};
     DLights lights{};
     bool have_camera = false;
-    bool composite_valid = false;
+    bool composite_valid = false, direct_valid = false;
+    DevBuf<float2> d_bary;               // barycentrics of the primary hit
+    DCamera cam_rendered{};              // camera / lights of the last rendered frame (deferred direct pass)
+    DLights lights_rendered{};
 
     cudaEvent_t ev[8]{};
     cudaEvent_t ev_level[RC_MAX_LEVELS + 1]{};   // ev_level[i] recorded after level i's kernels
@@ -286,6 +289,7 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
     CU_OK(c, c->d_depth.alloc(npx));
     CU_OK(c, c->d_prim.alloc(npx));
     CU_OK(c, c->d_nrm.alloc(npx));
+    CU_OK(c, c->d_bary.alloc(npx));
     CU_OK(c, c->d_albedo.alloc(npx));
     CU_OK(c, c->d_direct.alloc(npx));
     CU_OK(c, c->d_irr.alloc(npx));
@@ -481,7 +485,7 @@ void destroy_ctx(rc_ctx* c)
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
     c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release();
     c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
-    c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
+    c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_frame_done) cudaEventDestroy(c->ev_frame_done);
     for (auto& e : c->ev_copy_done) if (e) cudaEventDestroy(e);
@@ -598,8 +602,11 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     c->launches = 0;
     if (c->march_persist) CU_OK(c, cudaMemsetAsync(c->d_counters.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
     c->composite_valid = false;
+    c->direct_valid = false;
+    c->cam_rendered = c->cam;
+    c->lights_rendered = c->lights;
     CU_OK(c, cudaEventRecord(c->ev[EV_START], st));
-    GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_albedo.p, c->d_direct.p};
+    GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p};
     launch_gbuffer(c->scene, c->cam, c->lights, c->tile, gb, st);
     c->launches++;
     CU_OK(c, cudaEventRecord(c->ev[EV_GBUF], st));
@@ -746,6 +753,15 @@ rc_status rc_read_target(rc_ctx* c, rc_target which, void* host_dst, size_t byte
     cudaSetDevice(c->device);
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     const void* src = nullptr;
+    const int w_ = (int)which;
+    if ((w_ == RC_TARGET_DIRECT || w_ == RC_TARGET_ALBEDO || w_ == RC_TARGET_COMPOSITE || w_ == RC_TARGET_DIRECT_SRGB8) && !c->direct_valid) {
+        if (!c->ev_recorded) { c->error = "rc_read_target before rc_render"; return RC_ERR_STATE; }
+        // deferred fs_main (src/shader.wgsl:76-100) from the stored visibility of the last rendered frame
+        launch_direct(c->scene, c->cam_rendered, c->lights_rendered, c->tile, c->d_depth.p, c->d_prim.p, c->d_bary.p,
+                      c->d_albedo.p, c->d_direct.p, st);
+        CU_OK(c, cudaGetLastError());
+        c->direct_valid = true;
+    }
     switch ((int)which) {
     case RC_TARGET_IRRADIANCE: src = c->irr(); break;
     case RC_TARGET_DIRECT: src = c->d_direct.p; break;

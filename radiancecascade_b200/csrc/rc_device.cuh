@@ -240,6 +240,8 @@ struct Shade { float3 rad, n, albedo, direct; };
 // fs_main at a hit with view vector Vd (= -ray direction); rad = Ke + (L + unlit) * albedo.
 // fp (optional): barycentrics (u,v) of the +x and +y neighbour pixels' rays on this triangle's plane -> texture
 // footprint for the sampler's mag/min decision (G-buffer pass only).
+// NORMAL_ONLY: stop after the two-sided shading normal (all the per-frame G-buffer pass needs).
+template <bool NORMAL_ONLY = false>
 __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, uint32_t prim, float u, float v,
                                            float3 P, float3 Vd, const float* fp = nullptr)
 {
@@ -258,7 +260,7 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
     float tu = 0.f, tv = 0.f;
     float duv_store[4];
     const float* duv = nullptr;
-    if (b0 || b1) {
+    if ((b0 && !NORMAL_ONLY) || b1) {
         tu = RC_ATTR(15); tv = 1.0f - RC_ATTR(16);                   // :78
         if (fp) {
             const float ux = lerp3(__ldg(a + 15), __ldg(b + 15), __ldg(c + 15), fp[0], fp[1]);
@@ -269,7 +271,8 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
             duv = duv_store;
         }
     }
-    const float3 albedo = b0 ? sample_tex(s, m.tex_c, tu, tv, true, duv) : f3(RC_ATTR(3), RC_ATTR(4), RC_ATTR(5));   // :80
+    float3 albedo = f3(0.f, 0.f, 0.f);
+    if (!NORMAL_ONLY) albedo = b0 ? sample_tex(s, m.tex_c, tu, tv, true, duv) : f3(RC_ATTR(3), RC_ATTR(4), RC_ATTR(5));   // :80
     float3 Lc = f3(m.ka[0] * 0.05f * m.ka[3], m.ka[1] * 0.05f * m.ka[3], m.ka[2] * 0.05f * m.ka[3]);  // :82-83
     const float3 Nv = f3(RC_ATTR(6), RC_ATTR(7), RC_ATTR(8));
     float3 raw;
@@ -284,6 +287,7 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
 #undef RC_ATTR
     const float ndv = vdot(Vd, raw);                                 // :88
     const float3 N = ndv < 0.0f ? vneg(raw) : raw;                   // :89
+    if (NORMAL_ONLY) { Shade r; r.rad = r.albedo = r.direct = f3(0.f, 0.f, 0.f); r.n = N; return r; }
     // specular chain (normalize, powf) only when Ks can contribute: Ks present and non-zero, or Ns < 0
     // (pow(0, Ns<0) = inf must still poison the result exactly as the plain formula does)
     const bool spec = (m.ks[3] != 0.0f && (m.ks[0] != 0.0f || m.ks[1] != 0.0f || m.ks[2] != 0.0f)) || !(m.ns >= 0.0f);
