@@ -2,7 +2,7 @@
 //
 //   k_gbuffer   primary visibility + fs_main per pixel            (rc_spec.h S4, src/shader.wgsl:76-100)
 //   k_probes    probe placement per cascade level                 (S6)
-//   k_link      per-probe upper-probe slots and bilateral weights (S1, S8)
+//   k_link_entry per-probe upper-probe slots and bilateral weights (S1, S8) + per-probe BVH entry frontiers
 //   k_march     per-level interval ray march, optionally fused with the merge from level i+1 (S7, S8)
 //   k_merge     stand-alone merge (A/B against the fused path)    (S8)
 //   k_gather    final irradiance gather                           (S9)
@@ -144,11 +144,10 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
 }
 
 // ------------------------------------------------------------------ link (S1 + S8 weights), levels 0..N-2 in one launch
-__global__ void __launch_bounds__(kBlock) k_link(DLevelSet ls, unsigned total, const float4* __restrict__ origin,
-                                                 const float4* __restrict__ normal, uint4* __restrict__ link_idx,
-                                                 float4* __restrict__ link_w)
+__device__ __forceinline__ void link_one(const DLevelSet& ls, unsigned gi, unsigned total, const float4* __restrict__ origin,
+                                         const float4* __restrict__ normal, uint4* __restrict__ link_idx,
+                                         float4* __restrict__ link_w)
 {
-    const unsigned gi = blockIdx.x * kBlock + threadIdx.x;
     if (gi >= total) return;
     const int l = level_of(ls, gi);
     const DLevel &lo = ls.lv[l], &up = ls.lv[l + 1];
@@ -178,27 +177,147 @@ __global__ void __launch_bounds__(kBlock) k_link(DLevelSet ls, unsigned total, c
     link_w[gi] = w;
 }
 
-// far-field radiance of lower texel (dx, dy) from the merged upper level (S8)
-__device__ __forceinline__ float4 far_field(const uint2* __restrict__ up_texels, int UD, uint4 li, float4 lw, int dx, int dy, float3 sky)
+// ------------------------------------------------------------------ entry frontier (per probe, levels < n_levels)
+// All D^2 rays of a probe share their origin and their interval [t0, t1): every triangle any of them can hit
+// lies within the ball B(origin, t1).  One thread per probe walks the BVH with that ball and records a small
+// frontier of subtrees (<= RC_ENTRY_SLOTS links) that covers every leaf whose box meets the ball; the probe's
+// rays start their traversal there (trace(..., entry)) instead of at the root.  Closest hits are defined as
+// min (t, triangle id) over ALL triangles (S5), so a conservative superset leaves results bit-identical.
+// Expansion rule (expected node visits per ray, p = chance a ray meets a child's box):
+//   replacing node X by its ball-meeting children saves the visit of X and costs (1 - p) per child; a child
+//   that contains the origin has p = 1, a child that does not has p < 1/2.  Hence: expand when at most one
+//   child meets the ball, or when one of two contains the origin; otherwise keep X.
+__device__ __forceinline__ float box_dist2(float3 lo, float3 hi, float3 o)
+{
+    const float dx = fmaxf(fmaxf(lo.x - o.x, o.x - hi.x), 0.0f);
+    const float dy = fmaxf(fmaxf(lo.y - o.y, o.y - hi.y), 0.0f);
+    const float dz = fmaxf(fmaxf(lo.z - o.z, o.z - hi.z), 0.0f);
+    return dx * dx + dy * dy + dz * dz;   // NaN / 1e30 "empty" boxes compare false against any radius
+}
+
+// One thread per GROUP of g x g neighbouring probes of a level (g = 2 at the dense lower levels, where the
+// probes of a group lie well within one interval length of each other): the ball is grown to hold every
+// member's ball and the frontier is written to each member's slot, so the march kernel indexes it by probe.
+// Depth-first with the origin-holding child first; the frontier (emitted + pending) never exceeds
+// RC_ENTRY_SLOTS, so one 8-entry array serves as output list (from the bottom) and stack (from the top).
+__device__ __forceinline__ void entry_one(const DScene& s, const DLevelSet& ls, const EntryPlan& plan, unsigned gi,
+                                          const float4* __restrict__ origin, int4* __restrict__ entry)
+{
+    if (gi >= plan.group_offset[plan.n]) return;
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < plan.n; k++) if (gi >= plan.group_offset[k]) l = k;
+    const DLevel& lv = ls.lv[l];
+    const int g = plan.g[l], ngx = (lv.sw + g - 1) / g;
+    const int grp = (int)(gi - plan.group_offset[l]);
+    const int bx = (grp % ngx) * g, by = (grp / ngx) * g;
+    // bounding ball of the members' balls (g <= 2: the members' origins stay in registers)
+    float3 c = f3(0.f, 0.f, 0.f);
+    int nvalid = 0;
+    float4 mo[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = k & 1, j = k >> 1;
+        mo[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < g && j < g && bx + i < lv.sw && by + j < lv.sh) mo[k] = __ldg(origin + lv.probe_offset + (size_t)(by + j) * lv.sw + (bx + i));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (mo[k].w != 0.0f) { c = vadd(c, xyz(mo[k])); nvalid++; }
+    constexpr int F = RC_ENTRY_SLOTS;
+    int a[F];
+    int nout = 0, npend = 0;
+    if (nvalid) {
+        c = vscale(c, 1.0f / (float)nvalid);
+        float spread2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (mo[k].w != 0.0f) { const float3 dl = vsub(xyz(mo[k]), c); spread2 = fmaxf(spread2, vdot(dl, dl)); }
+        const float r = (lv.t1 + sqrtf(spread2)) * 1.001f;   // |w| = 1 +- 2e-7; boxes carry their own 1e-4*diag pad
+        const float r2 = r * r;
+        a[F - 1] = 0; npend = 1;                             // the root
+        while (npend) {
+            const int X = a[F - npend]; npend--;
+            const float4* nd = s.nodes + 4 * (size_t)X;
+            const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+            const float d0 = box_dist2(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), c);
+            const float d1 = box_dist2(f3(q1.z, q1.w, q2.x), f3(q2.y, q2.z, q2.w), c);
+            const bool m0 = d0 <= r2, m1 = d1 <= r2;
+            const bool in0 = m0 && d0 == 0.0f, in1 = m1 && d1 == 0.0f;
+            if (m0 && m1 && (!(in0 || in1) || nout + npend + 2 > F)) { a[nout++] = X; continue; }   // keep X
+            const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            // leaves are final; inner children go on the stack, the origin-holding one on top
+            if (m0 && c0 < 0) a[nout++] = c0;
+            if (m1 && c1 < 0) a[nout++] = c1;
+            const bool p0 = m0 && c0 >= 0, p1 = m1 && c1 >= 0;
+            if (p0 && p1) {
+                const bool first1 = in1 && !in0;
+                npend++; a[F - npend] = first1 ? c0 : c1;
+                // the deferred sibling is popped many iterations later: have its node in L1 by then
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(s.nodes + 4 * (size_t)(first1 ? c0 : c1)));
+                npend++; a[F - npend] = first1 ? c1 : c0;
+            } else if (p0) { npend++; a[F - npend] = c0; }
+            else if (p1) { npend++; a[F - npend] = c1; }
+        }
+    }
+    for (int k = nout; k < F; k++) a[k] = kDoneLinkC;
+    const int4 ea = make_int4(a[0], a[1], a[2], a[3]), eb = make_int4(a[4], a[5], a[6], a[7]);
+    for (int j = 0; j < g; j++)
+        for (int i = 0; i < g; i++) {
+            if (bx + i >= lv.sw || by + j >= lv.sh) continue;
+            const size_t pi = lv.probe_offset + (size_t)(by + j) * lv.sw + (bx + i);
+            entry[2 * pi] = ea;
+            entry[2 * pi + 1] = eb;
+        }
+}
+
+// k_link and k_entry are independent (both read only the probe origins) and each is a single short, latency-bound
+// wave: one launch runs them side by side (blocks [0, link_blocks) link, the rest build entry frontiers).
+__global__ void __launch_bounds__(kBlock) k_link_entry(DScene s, DLevelSet ls, EntryPlan plan, unsigned link_total, unsigned link_blocks,
+                                                       const float4* __restrict__ origin, const float4* __restrict__ normal,
+                                                       uint4* __restrict__ link_idx, float4* __restrict__ link_w, int4* __restrict__ entry)
+{
+    if (blockIdx.x < link_blocks) link_one(ls, blockIdx.x * kBlock + threadIdx.x, link_total, origin, normal, link_idx, link_w);
+    else entry_one(s, ls, plan, (blockIdx.x - link_blocks) * kBlock + threadIdx.x, origin, entry);
+}
+
+// far-field radiance of lower texel (dx, dy) from the merged upper level (S8).
+// `up_avg` holds, per upper probe and LOWER direction, a_k = 0.25*(((c0 + c1) + c2) + c3) of the four child texels
+// (float16 values summed in float32, exactly the S8 expression) — written once by the kernel that finalised
+// level i+1 (k_march's warp-shuffle epilogue / k_fill_top / k_child_avg).  Each upper texel is needed by 16 lower
+// probes; averaging at the producer replaces 8 x 16-byte loads, 32 half2 conversions and 16 adds per lower texel
+// by 4 x 16-byte loads here.
+__device__ __forceinline__ float4 far_field(const float4* __restrict__ up_avg, int D, uint4 li, float4 lw, int dx, int dy, float3 sky)
 {
     if (lw.x < 0.0f) return make_float4(sky.x, sky.y, sky.z, 0.f);   // S8: no valid upper probe -> the sky
     float4 far = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t idx[4] = {li.x, li.y, li.z, li.w};
     const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
-    const size_t UDD = (size_t)UD * UD;
+    const size_t DD = (size_t)D * D, off = (size_t)dy * D + dx;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const uint2* base = up_texels + idx[k] * UDD + (size_t)(2 * dy) * UD + 2 * dx;
-        const uint4 r0 = ld_u4(base);        // children (2dx,2dy), (2dx+1,2dy)
-        const uint4 r1 = ld_u4(base + UD);   // children (2dx,2dy+1), (2dx+1,2dy+1)
-        const float4 c0 = unpack_half4(make_uint2(r0.x, r0.y)), c1 = unpack_half4(make_uint2(r0.z, r0.w));
-        const float4 c2 = unpack_half4(make_uint2(r1.x, r1.y)), c3 = unpack_half4(make_uint2(r1.z, r1.w));
-        far.x = fmaf(wk[k], 0.25f * (((c0.x + c1.x) + c2.x) + c3.x), far.x);
-        far.y = fmaf(wk[k], 0.25f * (((c0.y + c1.y) + c2.y) + c3.y), far.y);
-        far.z = fmaf(wk[k], 0.25f * (((c0.z + c1.z) + c2.z) + c3.z), far.z);
-        far.w = fmaf(wk[k], 0.25f * (((c0.w + c1.w) + c2.w) + c3.w), far.w);
+        const float4 a = __ldg(up_avg + idx[k] * DD + off);
+        far.x = fmaf(wk[k], a.x, far.x);
+        far.y = fmaf(wk[k], a.y, far.y);
+        far.z = fmaf(wk[k], a.z, far.z);
+        far.w = fmaf(wk[k], a.w, far.w);
     }
     return far;
+}
+
+// Child average of one finalised texel quad, computed where the texels are produced: the 2x2 children of a
+// lower direction sit in lanes l, l^1, l^ystep, l^(1|ystep) of the warp (ystep = 8 for the 8x4 direction tile
+// and for LINEAR with D = 8; = D for LINEAR with D <= 16).  Every lane must call this (full-mask shuffles);
+// the lane with even dx and even dy returns true and owns the result.
+__device__ __forceinline__ bool child_avg_shfl(uint2 t, int ystep, int dx, int dy, float4& avg)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint2 tx = make_uint2(__shfl_xor_sync(FULL, t.x, 1), __shfl_xor_sync(FULL, t.y, 1));
+    const uint2 ty = make_uint2(__shfl_xor_sync(FULL, t.x, ystep), __shfl_xor_sync(FULL, t.y, ystep));
+    const uint2 txy = make_uint2(__shfl_xor_sync(FULL, t.x, ystep | 1), __shfl_xor_sync(FULL, t.y, ystep | 1));
+    if ((dx | dy) & 1) return false;
+    const float4 c0 = unpack_half4(t), c1 = unpack_half4(tx), c2 = unpack_half4(ty), c3 = unpack_half4(txy);
+    avg = make_float4(0.25f * (((c0.x + c1.x) + c2.x) + c3.x), 0.25f * (((c0.y + c1.y) + c2.y) + c3.y),
+                      0.25f * (((c0.z + c1.z) + c2.z) + c3.z), 0.25f * (((c0.w + c1.w) + c2.w) + c3.w));
+    return true;
 }
 
 // ------------------------------------------------------------------ march (+ fused merge)
@@ -255,7 +374,7 @@ __device__ __forceinline__ bool decode_texel(const DLevel& lv, int map, size_t g
 template <bool FUSED>
 __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& L, const DLevel& lv, int UD, int top, float3 sky,
                                                 uint32_t probe, uint32_t d, float3 o, float3 w, const Hit& h,
-                                                const uint2* __restrict__ up_texels, const uint4* __restrict__ link_idx,
+                                                const float4* __restrict__ up_avg, const uint4* __restrict__ link_idx,
                                                 const float4* __restrict__ link_w)
 {
     float4 c;
@@ -279,7 +398,7 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
             int dx, dy;
             if ((lv.D & (lv.D - 1)) == 0) { dx = (int)(d & (uint32_t)(lv.D - 1)); dy = (int)(d >> (31 - __clz(lv.D))); }
             else { dx = (int)(d % (uint32_t)lv.D); dy = (int)(d / (uint32_t)lv.D); }
-            const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky);
+            const float4 far = far_field(up_avg, lv.D, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky);
             c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
             c.x = fminf(c.x, 65504.0f); c.y = fminf(c.y, 65504.0f); c.z = fminf(c.z, 65504.0f);
         } else {
@@ -295,25 +414,69 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
 template <bool FUSED, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map, size_t total,
                                                   const float4* __restrict__ origin, const float* __restrict__ dirs,
-                                                  uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
-                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
+                                                  uint2* __restrict__ texels, const float4* __restrict__ up_avg,
+                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
+                                                  const int4* __restrict__ entry, float4* __restrict__ avg_out, int ystep)
 {
     cudaTriggerProgrammaticLaunchCompletion();   // the next level's kernel may begin once every block got here
     const size_t DD = (size_t)lv.D * lv.D;
-    // grid-stride: with a full-size grid this is one iteration; with a resident grid (rc_set_tuning
-    // "march_waves") each warp walks packets g, g + G, ... and no block turnover happens during the level
+    // grid-stride over whole warps (the child-average epilogue shuffles with a full mask): with a full-size grid
+    // this is one iteration; with a resident grid (rc_set_tuning "march_waves") each warp walks packets g, g + G, ...
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
-        uint32_t probe, d;
-        if (!decode_texel(lv, map, g, probe, d)) continue;
-        const size_t i = (size_t)probe * DD + d;
-        const float4 og = __ldg(origin + probe);
-        if (og.w == 0.0f) { texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f); continue; }   // invalid probe (S7)
-        const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
-        const float3 o = xyz(og);
-        const Hit h = trace(s, o, w, lv.t0, lv.t1);
-        texels[i] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_texels, link_idx, link_w);
+    const unsigned lane = threadIdx.x & 31u;
+    for (size_t g0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); g0 < total; g0 += stride) {
+        uint32_t probe = 0, d = 0;
+        const bool in_range = decode_texel(lv, map, g0 + lane, probe, d);
+        uint2 t = pack_half4(0.f, 0.f, 0.f, 1.f);   // invalid probe (S7)
+        if (in_range) {
+            const float4 og = __ldg(origin + probe);
+            if (og.w != 0.0f) {
+                const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+                const float3 o = xyz(og);
+                const Hit h = trace(s, o, w, lv.t0, lv.t1, entry ? entry + 2 * (size_t)probe : nullptr);
+                t = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_avg, link_idx, link_w);
+            }
+            texels[(size_t)probe * DD + d] = t;
+        }
+        if (avg_out) {   // this kernel finalises the level: leave the child averages for the level below (far_field)
+            const int ld = 31 - __clz(lv.D);   // launch_march only passes avg_out for power-of-two D
+            const int dx = (int)(d & (uint32_t)(lv.D - 1)), dy = (int)(d >> ld);
+            float4 avg;
+            if (child_avg_shfl(t, ystep, dx, dy, avg) && in_range)
+                avg_out[(size_t)probe * (DD >> 2) + (size_t)(dy >> 1) * (lv.D >> 1) + (dx >> 1)] = avg;
+        }
     }
+}
+
+// ------------------------------------------------------------------ all levels in ONE launch (small frames)
+// The ray marches of the N levels are independent of each other — only the merge runs top-down.  On a small
+// frame (1080p, open scene: ~0.5 M real rays per level = 2-3 waves of blocks) each per-level kernel spends
+// most of its time in its own tail (ncu: 27-39 % of warp slots active against 62.5 % allocated).  Marching
+// every level's rays in one grid leaves a single tail; the merges then run as cheap streaming kernels
+// (k_merge; fused == separate bit-for-bit, tests/test_gpu_parity.py::test_fused_equals_separate).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_march_all(DScene s, DLights L, DLevelSet ls, MarchPlan plan, float3 sky,
+                                                        const float4* __restrict__ origin, const float* __restrict__ dirs,
+                                                        uint2* __restrict__ cascade, const int4* __restrict__ entry)
+{
+    int k = 0;
+#pragma unroll 1
+    for (int j = 1; j < plan.n; j++) if (blockIdx.x >= plan.block_offset[j]) k = j;
+    const int level = plan.level[k];
+    const DLevel& lv = ls.lv[level];
+    const size_t DD = (size_t)lv.D * lv.D;
+    const size_t g = (size_t)(blockIdx.x - plan.block_offset[k]) * blockDim.x + threadIdx.x;
+    uint32_t probe, d;
+    if (!decode_texel(lv, plan.map[k], g, probe, d)) return;
+    uint2* texels = cascade + lv.texel_offset;
+    const size_t i = (size_t)probe * DD + d;
+    const float4 og = __ldg(origin + lv.probe_offset + probe);
+    if (og.w == 0.0f) { texels[i] = pack_half4(0.f, 0.f, 0.f, 1.f); return; }   // invalid probe (S7)
+    const float* dl = dirs + plan.dir_offset[k];
+    const float3 w = f3(__ldg(dl + 3 * d), __ldg(dl + 3 * d + 1), __ldg(dl + 3 * d + 2));
+    const float3 o = xyz(og);
+    const Hit h = trace(s, o, w, lv.t0, lv.t1, plan.use_entry[k] ? entry + 2 * ((size_t)lv.probe_offset + probe) : nullptr);
+    texels[i] = finalize_texel<false>(s, L, lv, 0, plan.top[k], sky, probe, d, o, w, h, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------ march with block-level ray compaction
@@ -344,7 +507,7 @@ __device__ __forceinline__ bool root_overlap(const DScene& s, float3 o, float3 d
 template <bool FUSED, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_march_compact(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
                                                              const float4* __restrict__ origin, const float* __restrict__ dirs,
-                                                             uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                             uint2* __restrict__ texels, const float4* __restrict__ up_avg,
                                                              const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
 {
     cudaTriggerProgrammaticLaunchCompletion();
@@ -364,7 +527,7 @@ __global__ void __launch_bounds__(128, MINB) k_march_compact(DScene s, DLights L
             const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
             const float3 o = xyz(og);
             survive = root_overlap(s, o, w, lv.t0, lv.t1);
-            if (!survive) texels[i] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, miss, up_texels, link_idx, link_w);
+            if (!survive) texels[i] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, miss, up_avg, link_idx, link_w);
         }
     }
     // ordered compaction of the survivors
@@ -382,7 +545,7 @@ __global__ void __launch_bounds__(128, MINB) k_march_compact(DScene s, DLights L
     const float3 o = xyz(og);
     const float3 w = f3(__ldg(dirs + 3 * r.y), __ldg(dirs + 3 * r.y + 1), __ldg(dirs + 3 * r.y + 2));
     const Hit h = trace(s, o, w, lv.t0, lv.t1);
-    texels[(size_t)r.x * DD + r.y] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, r.x, r.y, o, w, h, up_texels, link_idx, link_w);
+    texels[(size_t)r.x * DD + r.y] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, r.x, r.y, o, w, h, up_avg, link_idx, link_w);
 }
 
 // ------------------------------------------------------------------ persistent march with ray replacement
@@ -402,7 +565,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(128, 8) k_march_persist(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map,
                                                           unsigned long long total, int thresh, unsigned int* __restrict__ counter,
                                                           const float4* __restrict__ origin, const float* __restrict__ dirs,
-                                                          uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                          uint2* __restrict__ texels, const float4* __restrict__ up_avg,
                                                           const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
 {
     cudaTriggerProgrammaticLaunchCompletion();
@@ -421,7 +584,7 @@ __global__ void __launch_bounds__(128, 8) k_march_persist(DScene s, DLights L, D
         if (__any_sync(FULL, pend)) {
             if (!synced) { cudaGridDependencySynchronize(); synced = true; }   // level i+1 is complete and visible
             if (pend) {
-                texels[(size_t)probe * DD + d] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_texels, link_idx, link_w);
+                texels[(size_t)probe * DD + d] = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_avg, link_idx, link_w);
                 pend = false;
             }
         }
@@ -507,7 +670,8 @@ __global__ void __launch_bounds__(128, 8) k_march_persist(DScene s, DLights L, D
 // With the default intervals the top level starts at 1.33 x the scene diagonal: from a probe on a surface every
 // point of such a ray lies outside the scene's bounding box, so the march is a guaranteed miss and the level is
 // filled with (sky, 1) — (0,0,0,1) for invalid probes — at streaming speed (128-bit stores, two texels per thread).
-__global__ void __launch_bounds__(kBlock) k_fill_top(DLevel lv, float3 sky, const float4* __restrict__ origin, uint4* __restrict__ texels2)
+__global__ void __launch_bounds__(kBlock) k_fill_top(DLevel lv, float3 sky, const float4* __restrict__ origin, uint4* __restrict__ texels2,
+                                                     float4* __restrict__ avg_out)
 {
     const size_t half = ((size_t)lv.D * lv.D) >> 1;
     const size_t n2 = (size_t)lv.sw * lv.sh * half;
@@ -516,11 +680,32 @@ __global__ void __launch_bounds__(kBlock) k_fill_top(DLevel lv, float3 sky, cons
     const bool valid = __ldg(origin + (i / half)).w != 0.0f;
     const uint2 t = valid ? pack_half4(sky.x, sky.y, sky.z, 1.0f) : pack_half4(0.f, 0.f, 0.f, 1.0f);
     texels2[i] = make_uint4(t.x, t.y, t.x, t.y);
+    // child averages of four equal texels: 0.25*(((c + c) + c) + c) == c exactly (c <= 65504); one per two threads
+    if (avg_out && !(i & 1)) avg_out[i >> 1] = unpack_half4(t);
+}
+
+// Child averages of a finalised level from its texels — for the paths whose march kernel cannot produce them in
+// its epilogue (separate-merge mode, the persistent / compacting / batched variants, probe-tile mapping, odd D).
+__global__ void __launch_bounds__(kBlock) k_child_avg(DLevel lv, const uint2* __restrict__ texels, float4* __restrict__ avg_out)
+{
+    const int HD = lv.D >> 1;
+    const size_t per_probe = (size_t)HD * HD;
+    const size_t n = (size_t)lv.sw * lv.sh * per_probe;
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const size_t probe = i / per_probe;
+    const int r = (int)(i - probe * per_probe), hy = r / HD, hx = r - hy * HD;
+    const uint2* base = texels + probe * (size_t)lv.D * lv.D + (size_t)(2 * hy) * lv.D + 2 * hx;
+    const uint4 r0 = ld_u4(base), r1 = ld_u4(base + lv.D);
+    const float4 c0 = unpack_half4(make_uint2(r0.x, r0.y)), c1 = unpack_half4(make_uint2(r0.z, r0.w));
+    const float4 c2 = unpack_half4(make_uint2(r1.x, r1.y)), c3 = unpack_half4(make_uint2(r1.z, r1.w));
+    avg_out[i] = make_float4(0.25f * (((c0.x + c1.x) + c2.x) + c3.x), 0.25f * (((c0.y + c1.y) + c2.y) + c3.y),
+                             0.25f * (((c0.z + c1.z) + c2.z) + c3.z), 0.25f * (((c0.w + c1.w) + c2.w) + c3.w));
 }
 
 // ------------------------------------------------------------------ stand-alone merge (in place)
 __global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, float3 sky, const float4* __restrict__ origin,
-                                                  uint2* __restrict__ texels, const uint2* __restrict__ up_texels,
+                                                  uint2* __restrict__ texels, const float4* __restrict__ up_avg,
                                                   const uint4* __restrict__ link_idx, const float4* __restrict__ link_w)
 {
     const size_t DD = (size_t)lv.D * lv.D;
@@ -531,7 +716,7 @@ __global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, float3 sky,
     if (__ldg(origin + probe).w == 0.0f) return;
     const float4 raw = unpack_half4(texels[i]);
     const int dx = (int)(d % (uint32_t)lv.D), dy = (int)(d / (uint32_t)lv.D);
-    const float4 far = far_field(up_texels, UD, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky);
+    const float4 far = far_field(up_avg, lv.D, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky);
     float4 c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
     texels[i] = pack_half4(fminf(c.x, 65504.0f), fminf(c.y, 65504.0f), fminf(c.z, 65504.0f), c.w);
 }
@@ -719,19 +904,42 @@ void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, uns
     k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal);
 }
 
-void launch_link(const DLevelSet& ls, unsigned total, const float4* origin, const float4* normal, uint4* link_idx,
-                 float4* link_w, cudaStream_t st)
+// lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do
+// not share a warp under this mapping (then the caller runs launch_child_avg after the level)
+int march_avg_ystep(int D, int map)
 {
-    if (total) k_link<<<blocks_for(total), kBlock, 0, st>>>(ls, total, origin, normal, link_idx, link_w);
+    if (D < 2 || (D & (D - 1))) return 0;
+    if (map == MAP_DIR_TILE && !(D & 7)) return 8;
+    if (map == MAP_LINEAR && D <= 16) return D;
+    return 0;
+}
+
+void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total, int entry_levels, const float4* origin,
+                       const float4* normal, uint4* link_idx, float4* link_w, int4* entry, cudaStream_t st)
+{
+    EntryPlan plan{};
+    plan.n = entry_levels;
+    unsigned groups = 0;
+    for (int l = 0; l < entry_levels; l++) {
+        const DLevel& lv = ls.lv[l];
+        plan.g[l] = l < 2 ? 2 : 1;
+        plan.group_offset[l] = groups;
+        groups += (unsigned)(((lv.sw + plan.g[l] - 1) / plan.g[l]) * ((lv.sh + plan.g[l] - 1) / plan.g[l]));
+    }
+    plan.group_offset[entry_levels] = groups;
+    const unsigned lb = blocks_for(link_total), eb = blocks_for(groups);
+    if (lb + eb) k_link_entry<<<lb + eb, kBlock, 0, st>>>(s, ls, plan, link_total, lb, origin, normal, link_idx, link_w, entry);
 }
 
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
-                  const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
-                  const uint4* link_idx, const float4* link_w, bool fused, int map, int occ, bool pdl, bool compact,
-                  int max_blocks, cudaStream_t st)
+                  const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
+                  const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ, bool pdl,
+                  bool compact, int max_blocks, cudaStream_t st)
 {
     const int block = 128;
     if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;   // the 8x4 direction tile needs D % 8 == 0
+    const int ystep = march_avg_ystep(lv.D, map);
+    if (!ystep || compact) avg_out = nullptr;
     size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
     if (map == MAP_PROBE_TILE) n = (size_t)((lv.sw + 7) / 8) * ((lv.sh + 3) / 4) * lv.D * lv.D * 32;
     const int UD = up ? up->D : 0;
@@ -748,8 +956,8 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && fused && !top) ? 1 : 0;   // only a kernel that waits on its predecessor may start early
 #define RC_LAUNCH_MARCH(F, M, T)                                                                                              \
-    (compact ? cudaLaunchKernelEx(&cfg, k_march_compact<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_texels, link_idx, link_w) \
-             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirs, texels, up_texels, link_idx, link_w))
+    (compact ? cudaLaunchKernelEx(&cfg, k_march_compact<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_avg, link_idx, link_w) \
+             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirs, texels, up_avg, link_idx, link_w, entry, avg_out, ystep))
     const bool f = fused && !top;
     const int t = f ? 0 : topi;
     if (occ >= 16) { if (f) RC_LAUNCH_MARCH(true, 16, t); else RC_LAUNCH_MARCH(false, 16, t); }
@@ -759,8 +967,36 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
 #undef RC_LAUNCH_MARCH
 }
 
+void launch_march_all(const DScene& s, const DLights& L, const DLevelSet& ls, const int* levels, int n, const int* map,
+                      const size_t* dir_offset, int entry_levels, int top_level, float3 sky, const float4* origin,
+                      const float* dirs, uint2* cascade, const int4* entry, int occ, cudaStream_t st)
+{
+    MarchPlan plan{};
+    plan.n = n;
+    unsigned blocks = 0;
+    for (int k = 0; k < n; k++) {
+        const DLevel& lv = ls.lv[levels[k]];
+        int m = map[levels[k]];
+        if (m == MAP_DIR_TILE && (lv.D & 7)) m = MAP_LINEAR;
+        size_t cnt = (size_t)lv.sw * lv.sh * lv.D * lv.D;
+        if (m == MAP_PROBE_TILE) cnt = (size_t)((lv.sw + 7) / 8) * ((lv.sh + 3) / 4) * lv.D * lv.D * 32;
+        plan.level[k] = levels[k];
+        plan.map[k] = m;
+        plan.top[k] = levels[k] == top_level ? 1 : 0;
+        plan.use_entry[k] = levels[k] < entry_levels ? 1 : 0;
+        plan.dir_offset[k] = (unsigned)dir_offset[levels[k]];
+        plan.block_offset[k] = blocks;
+        blocks += (unsigned)((cnt + 127) / 128);
+    }
+    plan.block_offset[n] = blocks;
+    if (!blocks) return;
+    if (occ >= 12) k_march_all<12><<<blocks, 128, 0, st>>>(s, L, ls, plan, sky, origin, dirs, cascade, entry);
+    else if (occ >= 10) k_march_all<10><<<blocks, 128, 0, st>>>(s, L, ls, plan, sky, origin, dirs, cascade, entry);
+    else k_march_all<8><<<blocks, 128, 0, st>>>(s, L, ls, plan, sky, origin, dirs, cascade, entry);
+}
+
 void launch_march_persist(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
-                          const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
+                          const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
                           const uint4* link_idx, const float4* link_w, bool fused, int map, int thresh, int grid_blocks,
                           unsigned int* counter, bool pdl, cudaStream_t st)
 {
@@ -780,9 +1016,9 @@ void launch_march_persist(const DScene& s, const DLights& L, const DLevel& lv, c
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     if (fused && !top)
-        cudaLaunchKernelEx(&cfg, k_march_persist<true>, s, L, lv, UD, 0, sky, map, n, thresh, counter, origin, dirs, texels, up_texels, link_idx, link_w);
+        cudaLaunchKernelEx(&cfg, k_march_persist<true>, s, L, lv, UD, 0, sky, map, n, thresh, counter, origin, dirs, texels, up_avg, link_idx, link_w);
     else
-        cudaLaunchKernelEx(&cfg, k_march_persist<false>, s, L, lv, UD, topi, sky, map, n, thresh, counter, origin, dirs, texels, up_texels, link_idx, link_w);
+        cudaLaunchKernelEx(&cfg, k_march_persist<false>, s, L, lv, UD, topi, sky, map, n, thresh, counter, origin, dirs, texels, up_avg, link_idx, link_w);
 }
 
 int march_persist_blocks_per_sm()
@@ -793,17 +1029,23 @@ int march_persist_blocks_per_sm()
     return a < b ? a : b;
 }
 
-void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, cudaStream_t st)
+void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, float4* avg_out, cudaStream_t st)
 {
     const size_t n2 = (size_t)lv.sw * lv.sh * (((size_t)lv.D * lv.D) >> 1);
-    k_fill_top<<<blocks_for(n2), kBlock, 0, st>>>(lv, sky, origin, reinterpret_cast<uint4*>(texels));
+    k_fill_top<<<blocks_for(n2), kBlock, 0, st>>>(lv, sky, origin, reinterpret_cast<uint4*>(texels), avg_out);
 }
 
-void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const uint2* up_texels,
+void launch_child_avg(const DLevel& lv, const uint2* texels, float4* avg_out, cudaStream_t st)
+{
+    const size_t n = (size_t)lv.sw * lv.sh * (((size_t)lv.D * lv.D) >> 2);
+    if (n) k_child_avg<<<blocks_for(n), kBlock, 0, st>>>(lv, texels, avg_out);
+}
+
+void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st)
 {
     const size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
-    k_merge<<<blocks_for(n), kBlock, 0, st>>>(lv, up.D, sky, origin, texels, up_texels, link_idx, link_w);
+    k_merge<<<blocks_for(n), kBlock, 0, st>>>(lv, up.D, sky, origin, texels, up_avg, link_idx, link_w);
 }
 
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,

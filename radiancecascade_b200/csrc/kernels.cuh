@@ -10,6 +10,16 @@ struct GBufferOut {
 
 struct TileRect { int x0, y0, w, h; };
 
+// k_entry work decomposition: level l is covered by groups of g[l] x g[l] probes, one thread each
+// k_march_all work decomposition: launch slot k marches level level[k] with blocks [block_offset[k], block_offset[k+1])
+struct MarchPlan {
+    unsigned block_offset[RC_MAX_LEVELS + 1];
+    unsigned dir_offset[RC_MAX_LEVELS];
+    int level[RC_MAX_LEVELS], map[RC_MAX_LEVELS], top[RC_MAX_LEVELS], use_entry[RC_MAX_LEVELS];
+    int n;
+};
+struct EntryPlan { unsigned group_offset[RC_MAX_LEVELS + 1]; int g[RC_MAX_LEVELS]; int n; };
+
 void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, cudaStream_t st);
 // deferred fs_main: albedo / direct colour from the stored visibility (on demand)
 void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
@@ -17,24 +27,38 @@ void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRe
 // all levels' probes in one launch; anchors inside the tile reuse the G-buffer hit
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, cudaStream_t st);
-// per lower probe (levels 0..N-2, `total` probes): the 4 upper probe slots (sub-grid linear) and
-// normalised weights (w.x < 0: no valid upper probe)
-void launch_link(const DLevelSet& ls, unsigned total, const float4* origin, const float4* normal, uint4* link_idx,
-                 float4* link_w, cudaStream_t st);
-// march level lv; fused != 0 also merges with the (already merged) upper level
+// One launch, two independent jobs that only read the probe origins:
+//  link:  per lower probe (levels 0..N-2, `link_total` probes) the 4 upper probe slots (sub-grid linear) and
+//         normalised weights (w.x < 0: no valid upper probe)
+//  entry: per probe of levels 0..entry_levels-1 the entry frontier of the BVH for the ball B(origin, t1) —
+//         2 x int4 links per probe, valid first, padded with 0x80000000 (rc_device.cuh trace(..., entry))
+void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total, int entry_levels, const float4* origin,
+                       const float4* normal, uint4* link_idx, float4* link_w, int4* entry, cudaStream_t st);
+// march level lv; fused != 0 also merges with the (already merged) upper level, read through its child averages
+// `up_avg` (float4 per upper probe and lower direction: 0.25*(((c0+c1)+c2)+c3), S8); entry: this level's
+// frontiers or null; avg_out: where to leave this level's own child averages when the kernel finalises the
+// level — only honoured when march_avg_ystep(D, map) != 0, otherwise call launch_child_avg afterwards
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
-                  const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
-                  const uint4* link_idx, const float4* link_w, bool fused, int map, int occ, bool pdl, bool compact,
-                  int max_blocks, cudaStream_t st);
+                  const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
+                  const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ,
+                  bool pdl, bool compact, int max_blocks, cudaStream_t st);
+int march_avg_ystep(int D, int map);
+// child averages of a finalised level from its texels (paths whose march kernel does not write them itself)
+void launch_child_avg(const DLevel& lv, const uint2* texels, float4* avg_out, cudaStream_t st);
+// every listed level's rays in one launch, unmerged (the caller runs launch_merge top-down afterwards);
+// levels[k] in launch order, map[level], dir_offset[level] in floats into dirs, origin / cascade / entry: whole-frame bases
+void launch_march_all(const DScene& s, const DLights& L, const DLevelSet& ls, const int* levels, int n, const int* map,
+                      const size_t* dir_offset, int entry_levels, int top_level, float3 sky, const float4* origin,
+                      const float* dirs, uint2* cascade, const int4* entry, int occ, cudaStream_t st);
 // persistent variant: resident grid, dynamic ray fetch with lane replacement, PDL-chained across levels
 void launch_march_persist(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
-                          const float4* origin, const float* dirs, uint2* texels, const uint2* up_texels,
+                          const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
                           const uint4* link_idx, const float4* link_w, bool fused, int map, int thresh, int grid_blocks,
                           unsigned int* counter, bool pdl, cudaStream_t st);
 int march_persist_blocks_per_sm();
 // top level whose interval lies entirely outside the scene bounds: fill with (sky, 1) instead of marching
-void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, cudaStream_t st);
-void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const uint2* up_texels,
+void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, float4* avg_out, cudaStream_t st);
+void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st);
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
                    const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, cudaStream_t st);

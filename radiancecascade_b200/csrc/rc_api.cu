@@ -99,6 +99,10 @@ struct rc_ctx {
     DevBuf<float4> d_origin, d_normal;   // all probes
     DevBuf<uint4> d_link_idx;
     DevBuf<float4> d_link_w;
+    DevBuf<int4> d_entry;                // 2 x int4 per probe: BVH entry frontier (k_entry)
+    DevBuf<float4> d_avg;                // levels >= 1: child averages per (probe, lower direction) for the merge (S8)
+    std::vector<size_t> avg_offset;      // float4s before level i in d_avg (level 0 has none)
+    float4* avg_of(uint32_t level) { return level >= 1 && level < N ? d_avg.p + avg_offset[level] : nullptr; }
     DevBuf<float> d_dirs;
     DevBuf<float> d_depth;
     DevBuf<uint32_t> d_prim, d_nrm;
@@ -123,6 +127,7 @@ struct rc_ctx {
     cudaEvent_t ev[8]{};
     cudaEvent_t ev_level[RC_MAX_LEVELS + 1]{};   // ev_level[i] recorded after level i's kernels
     bool ev_recorded = false;
+    bool frame_batched = false;          // the last frame went through render_levels_batched
     uint32_t launches = 0;
     cudaStream_t last_stream = nullptr;
     int march_map[RC_MAX_LEVELS];   // thread->texel mapping per level (kernels.cu MAP_*)
@@ -134,6 +139,36 @@ struct rc_ctx {
     int fill_top = 1;        // fill a top level that cannot hit anything instead of marching it (exact)
     int march_waves = 0;     // > 0: march grid capped at SMs * occ * waves blocks (grid-stride loop); 0: one thread per ray
     int sm_count = 148;
+    // levels 0..march_entry-1 start their traversal at the per-probe entry frontier (0 = at the root); -1 = automatic:
+    // the levels whose interval ends within a tenth of the scene diagonal (0..2 at the defaults), on frames of at
+    // least 3 M texels per level — building the frontiers is one latency-bound wave of ~17 us, which a 1080p frame
+    // does not win back (teapot: march -14 us) while a 4K frame does (living_room: march -150 us)
+    int march_entry = -1;
+    // 1: march all levels in one launch, then merge top-down with k_merge; 0 (default): one fused march+merge kernel
+    // per level, PDL-chained.  Measured: the single launch saves nothing over the PDL chain and the
+    // separate merges cost more than the fused ones.
+    int march_batch = 0;
+    size_t texels_per_level() const { return levels.empty() ? 0 : (size_t)levels[0].sw * levels[0].sh * levels[0].D * levels[0].D; }
+    bool batched() const
+    {
+        if (march_persist || level_timing) return false;
+        return march_batch > 0;
+    }
+    bool top_fillable() const
+    {
+        // S7 shortcut, exact: a ray that starts on a surface (inside the scene's box grown by the probe offset) is
+        // farther than the box diagonal from every triangle once t > diag + 2*offset -> the whole level misses
+        const DLevel& L = levels[N - 1];
+        return fill_top && L.t0 > host.diag * 1.001f + 2.0f * offset && (((size_t)L.texel_offset) & 1) == 0;
+    }
+    int entry_levels() const
+    {
+        if (march_entry >= 0) return march_entry < (int)N ? march_entry : (int)N;
+        if (texels_per_level() < 3000000u) return 0;
+        int n = 0;
+        while (n < (int)N && levels[n].t1 <= 0.1f * host.diag) n++;
+        return n;
+    }
 
     bool fail(rc_status, const std::string& m) { error = m; return false; }
 };
@@ -285,6 +320,14 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
     CU_OK(c, c->d_normal.alloc(probes));
     CU_OK(c, c->d_link_idx.alloc(probes));
     CU_OK(c, c->d_link_w.alloc(probes));
+    CU_OK(c, c->d_entry.alloc(2 * probes));
+    c->avg_offset.assign(N, 0);
+    size_t avgs = 0;
+    for (uint32_t i = 1; i < N; i++) {
+        c->avg_offset[i] = avgs;
+        avgs += (size_t)c->levels[i].sw * c->levels[i].sh * ((size_t)c->levels[i].D * c->levels[i].D / 4);
+    }
+    CU_OK(c, c->d_avg.alloc(avgs ? avgs : 1));
     CU_OK(c, c->d_dirs.upload(all_dirs));
     CU_OK(c, c->d_depth.alloc(npx));
     CU_OK(c, c->d_prim.alloc(npx));
@@ -483,7 +526,7 @@ void destroy_ctx(rc_ctx* c)
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tri_geom.release(); c->d_tri_eg.release(); c->d_tris.release(); c->d_tri_model.release();
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
-    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release();
+    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release();
     c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -494,7 +537,7 @@ void destroy_ctx(rc_ctx* c)
     delete c;
 }
 
-enum { EV_START = 0, EV_GBUF, EV_PROBES, EV_LEVELS, EV_GATHER, EV_MARCH0 /* .. + 2*level */ };
+enum { EV_START = 0, EV_GBUF, EV_PROBES, EV_LEVELS, EV_GATHER, EV_MARCH_ALL /* batched path: after k_march_all, before the merges */ };
 
 }  // namespace
 
@@ -552,6 +595,8 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_MARCH_WAVES")) c->march_waves = atoi(e);
         if (const char* e = getenv("RC_MARCH_THRESH")) c->march_thresh = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
         if (const char* e = getenv("RC_MARCH_PDL")) c->march_pdl = atoi(e);
+        if (const char* e = getenv("RC_MARCH_ENTRY")) c->march_entry = atoi(e) < -1 ? -1 : atoi(e);
+        if (const char* e = getenv("RC_MARCH_BATCH")) c->march_batch = atoi(e) > 0 ? 1 : 0;
         cudaDeviceProp prop;
         int bps = march_persist_blocks_per_sm();
         if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
@@ -603,6 +648,7 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     if (c->march_persist) CU_OK(c, cudaMemsetAsync(c->d_counters.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
     c->composite_valid = false;
     c->direct_valid = false;
+    c->frame_batched = false;
     c->cam_rendered = c->cam;
     c->lights_rendered = c->lights;
     CU_OK(c, cudaEventRecord(c->ev[EV_START], st));
@@ -617,9 +663,12 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     const unsigned n_probes = top.probe_offset + (unsigned)(top.sw * top.sh);
     launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p, st);
     c->launches++;
-    if (c->N > 1) {
-        launch_link(ls, top.probe_offset, c->d_origin.p, c->d_normal.p, c->d_link_idx.p, c->d_link_w.p, st);
-        c->launches++;
+    {
+        const int ne = c->march_persist ? 0 : c->entry_levels();
+        if (c->N > 1 || ne > 0) {
+            launch_link_entry(c->scene, ls, top.probe_offset, ne, c->d_origin.p, c->d_normal.p, c->d_link_idx.p, c->d_link_w.p, c->d_entry.p, st);
+            c->launches++;
+        }
     }
     CU_OK(c, cudaEventRecord(c->ev[EV_PROBES], st));
     CU_OK(c, cudaGetLastError());
@@ -636,27 +685,37 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     const DLevel* U = top ? nullptr : &c->levels[level + 1];
     const float3 sky = make_float3(c->cfg.sky[0], c->cfg.sky[1], c->cfg.sky[2]);
     uint2* tex = c->d_cascade.p + L.texel_offset;
-    const uint2* up = top ? nullptr : c->d_cascade.p + U->texel_offset;
-    // S7 shortcut, exact: a ray that starts on a surface (inside the scene's box grown by the probe offset) is
-    // farther than the box diagonal from every triangle once t > diag + 2*offset -> the whole level misses
-    if (top && c->fill_top && L.t0 > c->host.diag * 1.001f + 2.0f * c->offset && (((size_t)L.texel_offset) & 1) == 0) {
-        launch_fill_top(L, sky, c->d_origin.p + L.probe_offset, tex, st);
+    const float4* up = top ? nullptr : c->avg_of(level + 1);   // the merge reads level i+1 through its child averages
+    float4* my_avg = c->avg_of(level);                          // ... and level i-1 will read this level's
+    if (top && c->top_fillable()) {
+        launch_fill_top(L, sky, c->d_origin.p + L.probe_offset, tex, my_avg, st);
         c->launches++;
         if (c->level_timing) CU_OK(c, cudaEventRecord(c->ev_level[level], st));
         CU_OK(c, cudaGetLastError());
         return RC_OK;
     }
+    const bool compact = ((c->march_compact >> level) & 1) != 0;
+    int eff_map = c->march_map[level];
+    if (eff_map == 1 && (L.D & 7)) eff_map = 0;   // as launch_march: the 8x4 direction tile needs D % 8 == 0
+    // the march kernel leaves the child averages itself when it finalises the level and the 2x2 children share a warp
+    const bool avg_in_kernel = my_avg && (fused || top) && !c->march_persist && !compact && march_avg_ystep(L.D, eff_map) != 0;
     if (c->march_persist)
         launch_march_persist(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
                              c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_thresh,
                              c->march_grid, c->d_counters.p + level, c->march_pdl && fused && !top, st);
     else
         launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
-                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, ((c->march_compact >> level) & 1) != 0,
+                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset,
+                     (int)level < c->entry_levels() ? c->d_entry.p + 2 * (size_t)L.probe_offset : nullptr,
+                     avg_in_kernel ? my_avg : nullptr, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, compact,
                      c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0, st);
     c->launches++;
     if (!fused && !top) {
         launch_merge(L, *U, sky, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
+        c->launches++;
+    }
+    if (my_avg && !avg_in_kernel) {
+        launch_child_avg(L, tex, my_avg, st);
         c->launches++;
     }
     // per-level events sit between the level kernels and would defeat their PDL overlap: opt-in only
@@ -677,6 +736,8 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "march_compact" && value >= 0) c->march_compact = value;
     else if (k == "march_waves" && value >= 0) c->march_waves = value;
     else if (k == "fill_top") c->fill_top = value != 0;
+    else if (k == "march_entry" && value >= -1) c->march_entry = value;
+    else if (k == "march_batch" && value >= 0 && value <= 1) c->march_batch = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
     else if (k.rfind("march_map", 0) == 0 && k.size() == 10 && k[9] >= '0' && k[9] <= '9' && value >= 0 && value <= 2)
@@ -705,10 +766,57 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
     return RC_OK;
 }
 
+// small frames: every level's march in one launch, then the merges top-down (rc_ctx::march_batch)
+static rc_status render_levels_batched(rc_ctx* c, void* stream)
+{
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const float3 sky = make_float3(c->cfg.sky[0], c->cfg.sky[1], c->cfg.sky[2]);
+    DLevelSet ls;
+    ls.n = (int)c->N;
+    for (uint32_t i = 0; i < c->N; i++) ls.lv[i] = c->levels[i];
+    int order[RC_MAX_LEVELS], n = 0;
+    int first = (int)c->N - 1;
+    if (c->top_fillable()) {
+        const DLevel& T = c->levels[c->N - 1];
+        launch_fill_top(T, sky, c->d_origin.p + T.probe_offset, c->d_cascade.p + T.texel_offset, c->avg_of(c->N - 1), st);
+        c->launches++;
+        first--;
+    }
+    for (int i = first; i >= 0; i--) order[n++] = i;
+    if (n) {
+        launch_march_all(c->scene, c->lights, ls, order, n, c->march_map, c->dir_offset.data(), c->entry_levels(), (int)c->N - 1, sky,
+                         c->d_origin.p, c->d_dirs.p, c->d_cascade.p, c->d_entry.p, c->march_occ, st);
+        c->launches++;
+    }
+    CU_OK(c, cudaEventRecord(c->ev[EV_MARCH_ALL], st));
+    if (first == (int)c->N - 1 && c->N > 1) {   // a marched top level is final as it is
+        launch_child_avg(c->levels[c->N - 1], c->d_cascade.p + c->levels[c->N - 1].texel_offset, c->avg_of(c->N - 1), st);
+        c->launches++;
+    }
+    for (int i = (int)c->N - 2; i >= 0; i--) {
+        const DLevel &L = c->levels[i], &U = c->levels[i + 1];
+        launch_merge(L, U, sky, c->d_origin.p + L.probe_offset, c->d_cascade.p + L.texel_offset, c->avg_of(i + 1),
+                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
+        c->launches++;
+        if (i >= 1) {
+            launch_child_avg(L, c->d_cascade.p + L.texel_offset, c->avg_of(i), st);
+            c->launches++;
+        }
+    }
+    CU_OK(c, cudaGetLastError());
+    return RC_OK;
+}
+
 rc_status rc_render(rc_ctx* c, void* stream)
 {
     rc_status s = rc_render_begin(c, stream);
     if (s != RC_OK) return s;
+    c->frame_batched = c->batched();
+    if (c->frame_batched) {
+        s = render_levels_batched(c, stream);
+        if (s != RC_OK) return s;
+        return rc_render_end(c, stream);
+    }
     for (int i = (int)c->N - 1; i >= 0; i--) {
         s = rc_render_level(c, (uint32_t)i, stream);
         if (s != RC_OK) return s;
@@ -818,8 +926,13 @@ rc_status rc_stage_times(rc_ctx* c, float* ms, uint32_t n)
     float t[RC_STAGE_COUNT] = {0};
     cudaEventElapsedTime(&t[RC_STAGE_GBUFFER], c->ev[EV_START], c->ev[EV_GBUF]);
     cudaEventElapsedTime(&t[RC_STAGE_PROBES], c->ev[EV_GBUF], c->ev[EV_PROBES]);
-    cudaEventElapsedTime(&t[RC_STAGE_MARCH], c->ev[EV_PROBES], c->ev[EV_LEVELS]);   // march (+ merge)
-    t[RC_STAGE_MERGE] = 0.f;
+    if (c->frame_batched) {
+        cudaEventElapsedTime(&t[RC_STAGE_MARCH], c->ev[EV_PROBES], c->ev[EV_MARCH_ALL]);   // (top fill +) k_march_all
+        cudaEventElapsedTime(&t[RC_STAGE_MERGE], c->ev[EV_MARCH_ALL], c->ev[EV_LEVELS]);   // k_merge x (N-1)
+    } else {
+        cudaEventElapsedTime(&t[RC_STAGE_MARCH], c->ev[EV_PROBES], c->ev[EV_LEVELS]);      // march fused with merge
+        t[RC_STAGE_MERGE] = 0.f;
+    }
     cudaEventElapsedTime(&t[RC_STAGE_GATHER], c->ev[EV_LEVELS], c->ev[EV_GATHER]);
     cudaEventElapsedTime(&t[RC_STAGE_FRAME], c->ev[EV_START], c->ev[EV_GATHER]);
     for (uint32_t i = 0; i < n && i < RC_STAGE_COUNT; i++) ms[i] = t[i];

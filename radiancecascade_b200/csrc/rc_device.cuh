@@ -106,7 +106,15 @@ __device__ __forceinline__ void tri_test(const float4* __restrict__ g, float3 o,
 
 // While-while traversal of the 2-wide BVH with a per-thread stack.  h.t doubles as the
 // current far bound (initialised to tmax); on return h.prim == ~0u means miss.
-__device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float tmin, float tmax)
+//
+// `entry` (optional): the probe's entry frontier (k_entry) — up to RC_ENTRY_SLOTS node / leaf links, valid ones
+// first, padded with kDoneLink — a set of subtrees that together hold every triangle within reach of the
+// probe's interval.  The traversal then starts with those links on its stack instead of at the root, skipping
+// the upper levels of the tree that every ray of the probe would walk through identically.
+constexpr int RC_ENTRY_SLOTS = 8;
+constexpr int kDoneLinkC = (int)0x80000000;
+
+__device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float tmin, float tmax, const int4* __restrict__ entry = nullptr)
 {
     Hit h; h.t = tmax; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
     const float3 inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
@@ -115,10 +123,21 @@ __device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float 
     // done); the warp reconverges at the end of the node loop and tests triangles together.  The
     // earlier "one node, then drain leaves" shape ran 57% of the kernel's warp-instructions — the
     // triangle tests — with 1.5-3 active lanes (profiles/r1_a_*).
-    constexpr int kDoneLink = (int)0x80000000;   // never a real leaf code (first < 2^28)
+    constexpr int kDoneLink = kDoneLinkC;   // never a real leaf code (first < 2^28)
     int stack[48];
     int sp = 0;
     int cur = 0;
+    if (entry) {
+        const int4 ea = __ldg(entry), eb = __ldg(entry + 1);
+        if (eb.w != kDoneLink) stack[sp++] = eb.w;
+        if (eb.z != kDoneLink) stack[sp++] = eb.z;
+        if (eb.y != kDoneLink) stack[sp++] = eb.y;
+        if (eb.x != kDoneLink) stack[sp++] = eb.x;
+        if (ea.w != kDoneLink) stack[sp++] = ea.w;
+        if (ea.z != kDoneLink) stack[sp++] = ea.z;
+        if (ea.y != kDoneLink) stack[sp++] = ea.y;
+        cur = ea.x;
+    }
     while (cur != kDoneLink) {
         while (cur >= 0) {
             const float4* n = s.nodes + 4 * (size_t)cur;

@@ -233,6 +233,42 @@ def test_march_variants_agree(persist):
             assert np.array_equal(r.read_cascade(i).view(np.uint16), ref_c[i]), (persist, mp, i)
 
 
+@pytest.mark.parametrize("name,W,H", SMALL + [("living_room", 480, 270)])
+def test_entry_frontier_equals_root_traversal(name, W, H):
+    """Starting each probe's rays at its BVH entry frontier (k_entry) instead of at the root changes no texel:
+    closest hits are min (t, id) over all triangles (S5) and the frontier covers every leaf within reach."""
+    st, _, _ = frame_setup(name, W, H)
+    out = []
+    for entry in (0, 10, 3):
+        r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name))
+        r.set_tuning("march_entry", entry)
+        r.update(st)
+        r.render()
+        out.append([r.read_cascade(i).view(np.uint16) for i in range(6)] + [r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)])
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,W,H", [("living_room", 160, 90), ("teapot", 192, 108), ("cube", 128, 128)])
+def test_batched_march_equals_per_level_path(name, W, H):
+    """All levels marched in one launch + k_merge top-down == one fused march+merge kernel per level, bit for bit."""
+    st, _, _ = frame_setup(name, W, H)
+    out = []
+    for batch, entry in ((0, 0), (1, 0), (1, 3)):
+        r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name))
+        r.set_tuning("march_batch", batch)
+        r.set_tuning("march_entry", entry)
+        r.update(st)
+        r.render()
+        out.append([r.read_cascade(i).view(np.uint16) for i in range(6)] + [r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)])
+        ms = r.stage_times()
+        assert (ms["merge"] > 0) == bool(batch)
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert np.array_equal(a, b)
+
+
 def test_resize_matches_fresh_context():
     st, _, _ = frame_setup("cube", 96, 64)
     a = render_product("cube", 96, 64, st)
