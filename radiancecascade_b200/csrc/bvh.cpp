@@ -6,6 +6,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <queue>
 
 namespace rc {
 namespace {
@@ -24,6 +25,97 @@ struct Box {
 };
 
 struct Prim { Box box; float c[3]; uint32_t id; };
+
+// Bounding box of triangle (a, b, c) clipped to `cell` (Sutherland-Hodgman against the six planes, in double).
+// Returns false when the clipped polygon is empty.  The result is grown by a relative 1e-6 of the cell (the
+// caller's pad is added on top in write_node), so the union of the fragments' boxes always covers the triangle.
+bool clipped_bounds(const float* a, const float* b, const float* c, const Box& cell, Box& out)
+{
+    double poly[16][3], tmp[16][3];
+    int n = 3;
+    for (int k = 0; k < 3; k++) { poly[0][k] = a[k]; poly[1][k] = b[k]; poly[2][k] = c[k]; }
+    for (int axis = 0; axis < 3 && n; axis++)
+        for (int side = 0; side < 2 && n; side++) {
+            const double plane = side ? cell.hi[axis] : cell.lo[axis];
+            const double sgn = side ? -1.0 : 1.0;   // inside: sgn * (x - plane) >= 0
+            int m = 0;
+            for (int i = 0; i < n; i++) {
+                const double* p = poly[i];
+                const double* q = poly[(i + 1) % n];
+                const double dp = sgn * (p[axis] - plane), dq = sgn * (q[axis] - plane);
+                if (dp >= 0.0) { for (int k = 0; k < 3; k++) tmp[m][k] = p[k]; m++; }
+                if ((dp >= 0.0) != (dq >= 0.0)) {
+                    const double t = dp / (dp - dq);
+                    for (int k = 0; k < 3; k++) tmp[m][k] = p[k] + t * (q[k] - p[k]);
+                    tmp[m][axis] = plane;
+                    m++;
+                }
+            }
+            n = m > 15 ? 15 : m;
+            memcpy(poly, tmp, sizeof(double) * 3 * (size_t)n);
+        }
+    if (n == 0) return false;
+    out.reset();
+    for (int i = 0; i < n; i++) {
+        float p[3] = {(float)poly[i][0], (float)poly[i][1], (float)poly[i][2]};
+        out.grow(p);
+    }
+    for (int k = 0; k < 3; k++) {
+        const float eps = 1e-6f * std::max(std::fabs(cell.hi[k] - cell.lo[k]), std::max(std::fabs(cell.lo[k]), std::fabs(cell.hi[k])));
+        out.lo[k] = std::max(out.lo[k] - eps, cell.lo[k] - eps);
+        out.hi[k] = std::min(out.hi[k] + eps, cell.hi[k] + eps);
+    }
+    return true;
+}
+
+// Triangle pre-splitting (early split clipping): the largest boxes are halved along their longest axis, each
+// half keeping the clipped triangle's bounds, until `budget` extra references exist.  Walls and floors that
+// span the whole scene otherwise put a scene-sized box around every node they fall into.  A triangle may then
+// sit in several leaves; closest hits are min (t, id) over all tests (S5), so results do not change.
+void presplit(std::vector<Prim>& prims, const float* v0, const float* e1, const float* e2, size_t budget, float min_area)
+{
+    auto cmp = [&](uint32_t x, uint32_t y) { return prims[x].box.area() < prims[y].box.area(); };
+    std::priority_queue<uint32_t, std::vector<uint32_t>, decltype(cmp)> heap(cmp);
+    for (uint32_t i = 0; i < prims.size(); i++) heap.push(i);
+    size_t added = 0;
+    while (!heap.empty() && added < budget) {
+        const uint32_t i = heap.top();
+        heap.pop();
+        const Box bx = prims[i].box;
+        if (!(bx.area() > min_area)) break;
+        int axis = 0;
+        for (int k = 1; k < 3; k++) if (bx.hi[k] - bx.lo[k] > bx.hi[axis] - bx.lo[axis]) axis = k;
+        const float mid = 0.5f * (bx.lo[axis] + bx.hi[axis]);
+        if (!(mid > bx.lo[axis] && mid < bx.hi[axis])) continue;   // cannot be halved any further
+        const uint32_t t = prims[i].id;
+        const float a[3] = {v0[3 * t], v0[3 * t + 1], v0[3 * t + 2]};
+        const float b[3] = {a[0] + e1[3 * t], a[1] + e1[3 * t + 1], a[2] + e1[3 * t + 2]};
+        const float c[3] = {a[0] + e2[3 * t], a[1] + e2[3 * t + 1], a[2] + e2[3 * t + 2]};
+        Box lc = bx, rc_ = bx, lb, rb;
+        lc.hi[axis] = mid;
+        rc_.lo[axis] = mid;
+        const bool hl = clipped_bounds(a, b, c, lc, lb), hr = clipped_bounds(a, b, c, rc_, rb);
+        if (!hl && !hr) continue;            // numerically empty: keep the fragment as it is
+        auto set = [&](Prim& p, const Box& nb) {
+            p.box = nb;
+            for (int k = 0; k < 3; k++) p.c[k] = 0.5f * (nb.lo[k] + nb.hi[k]);
+        };
+        if (hl && hr) {
+            Prim q = prims[i];
+            set(prims[i], lb);
+            set(q, rb);
+            prims.push_back(q);
+            added++;
+            heap.push(i);
+            heap.push((uint32_t)prims.size() - 1);
+        } else {
+            const Box& nb = hl ? lb : rb;
+            const bool shrunk = nb.area() < bx.area();
+            set(prims[i], nb);
+            if (shrunk) heap.push(i);       // tighter than before: may still be worth splitting
+        }
+    }
+}
 
 struct Builder {
     std::vector<Prim> prims;
@@ -105,8 +197,13 @@ struct Builder {
     int32_t make_leaf(uint32_t first, uint32_t count)
     {
         uint32_t at = (uint32_t)out->leaf_tris.size();
-        for (uint32_t i = 0; i < count; i++) out->leaf_tris.push_back(prims[first + i].id);
-        return ~(int32_t)((at << 3) | count);
+        uint32_t n = 0;
+        for (uint32_t i = 0; i < count; i++) {   // two fragments of one pre-split triangle may share a leaf
+            bool dup = false;
+            for (uint32_t j = 0; j < n; j++) dup = dup || out->leaf_tris[at + j] == prims[first + i].id;
+            if (!dup) { out->leaf_tris.push_back(prims[first + i].id); n++; }
+        }
+        return ~(int32_t)((at << 3) | n);
     }
 
     void write_node(int32_t idx, const Box& a, const Box& b, int32_t c0, int32_t c1)
@@ -127,7 +224,7 @@ struct Builder {
 }  // namespace
 
 void build_bvh(const float* v0, const float* e1, const float* e2, const uint8_t* skip, uint32_t n_tris,
-               float pad, Bvh& out, int max_leaf, float node_cost)
+               float pad, Bvh& out, int max_leaf, float node_cost, float split_budget)
 {
     out = Bvh();
     Builder b;
@@ -152,6 +249,12 @@ void build_bvh(const float* v0, const float* e1, const float* e2, const uint8_t*
         if (!finite) continue;
         for (int k = 0; k < 3; k++) p.c[k] = 0.5f * (p.box.lo[k] + p.box.hi[k]);
         b.prims.push_back(p);
+    }
+    if (split_budget > 0.f && !b.prims.empty()) {
+        Box scene;
+        scene.reset();
+        for (const Prim& p : b.prims) scene.grow(p.box);
+        presplit(b.prims, v0, e1, e2, (size_t)(split_budget * (float)b.prims.size()), 1e-5f * scene.area());
     }
     // Root is always an inner node (index 0) so traversal starts uniformly.
     out.nodes.emplace_back();

@@ -21,7 +21,9 @@ struct Bvh {
 };
 
 // v0/e1/e2: per-triangle geometry (3 floats each); skip[t] != 0 excludes a triangle (S5).
+// split_budget > 0: pre-split the largest triangles' boxes, adding up to split_budget * n_tris references
+// (a triangle can then appear in several leaves: leaf_tris.size() >= number of triangles).
 void build_bvh(const float* v0, const float* e1, const float* e2, const uint8_t* skip, uint32_t n_tris,
-               float pad, Bvh& out, int max_leaf = 4, float node_cost = 0.f);
+               float pad, Bvh& out, int max_leaf = 4, float node_cost = 0.f, float split_budget = 0.f);
 
 }  // namespace rc

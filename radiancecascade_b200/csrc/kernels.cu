@@ -46,8 +46,39 @@ __device__ __forceinline__ bool pixel_footprint(const DScene& s, const DCamera& 
     return plane_bary(v0, e1, e2, cam.eye, dx, fp[0], fp[1]) && plane_bary(v0, e1, e2, cam.eye, dy, fp[2], fp[3]);
 }
 
-__global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out)
+// S1: the two level-0 probes (clamped) and bilinear weights of pixel coordinate `coord` along one axis
+__device__ __forceinline__ void gather_axis(int coord, int P, int gmax, int& i0, int& i1, float& w0, float& w1)
 {
+    const int s = coord - P / 2;
+    int base, rem;
+    if ((P & (P - 1)) == 0) {           // power-of-two spacing: arithmetic shift == floor division
+        const int lp = 31 - __clz(P);
+        base = s >> lp;
+        rem = s & (P - 1);
+    } else {
+        base = (s >= 0) ? s / P : -((-s + P - 1) / P);
+        rem = s - base * P;
+    }
+    const float f = (float)rem / (float)P;
+    i0 = min(max(base, 0), gmax - 1);
+    i1 = min(max(base + 1, 0), gmax - 1);
+    w0 = 1.0f - f; w1 = f;
+}
+
+// Direction culling, level 0 (`pixmask` != null).  The gather (S9) weights texel (probe, d) by
+// cs_d = max(dot(n, w_d), 0) of the pixels that interpolate the probe: a level-0 direction that is at or below
+// the horizon of EVERY such pixel is multiplied by zero and need not be traced.  Each covered pixel evaluates
+// the very expression the gather will evaluate (decoded normal, same dot product) and stores its mask of
+// directions with cs_d > 0 (D0^2 <= 16 bits); k_probes ORs the masks of the pixels each level-0 probe serves
+// and k_need carries the result up the cascade.
+__global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out,
+                                                    int DD0, const float* __restrict__ dirs0, uint16_t* __restrict__ pixmask)
+{
+    __shared__ float s_dirs[3 * 16];
+    if (pixmask) {
+        if (threadIdx.x < 3 * DD0) s_dirs[threadIdx.x] = dirs0[threadIdx.x];
+        __syncthreads();
+    }
     // a block covers 32x8 pixels; each warp an 8x4 pixel tile (compact frustum -> coherent traversal; four
     // 32-byte row segments per store)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -59,6 +90,7 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLigh
     const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
     if (h.prim == 0xffffffffu) {
         out.depth[o] = -1.0f; out.prim[o] = 0xffffffffu; out.normal[o] = 0u; out.bary[o] = make_float2(0.f, 0.f);
+        if (pixmask) pixmask[o] = 0;
         return;
     }
     const float3 P = vfma(h.t, d, cam.eye);
@@ -67,10 +99,25 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLigh
     const float* fpp = nullptr;
     if ((s.mats[s.tri_model[h.prim]].ebit & 2u) && (L.flags & 1u) && pixel_footprint(s, cam, h.prim, tile.x0 + tx, tile.y0 + ty, fp)) fpp = fp;
     const Shade sh = shade_hit<true>(s, L, h.prim, h.u, h.v, P, vneg(d), fpp);
+    const uint32_t enc = oct_encode(sh.n);
     out.depth[o] = h.t;
     out.prim[o] = h.prim;
-    out.normal[o] = oct_encode(sh.n);
+    out.normal[o] = enc;
     out.bary[o] = make_float2(h.u, h.v);
+    if (pixmask) {
+        // S9: n = decoded stored normal, cs_d = max(dot(n, w_d), 0) > 0  <=>  dot(n, w_d) > 0
+        const float3 n = oct_decode(enc);
+        uint32_t m = 0u;
+        if (DD0 == 16) {
+#pragma unroll
+            for (int di = 0; di < 16; di++)
+                if (vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])) > 0.0f) m |= 1u << di;
+        } else {
+            for (int di = 0; di < DD0; di++)
+                if (vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])) > 0.0f) m |= 1u << di;
+        }
+        pixmask[o] = (uint16_t)m;
+    }
 }
 
 // fs_main for every covered pixel from the stored visibility (on demand; not part of the per-frame GI path)
@@ -108,13 +155,25 @@ __device__ __forceinline__ int level_of(const DLevelSet& ls, unsigned i)
 
 __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, TileRect tile, float offset,
                                                    const float* __restrict__ depth, const uint32_t* __restrict__ prim,
-                                                   float4* __restrict__ origin, float4* __restrict__ normal)
+                                                   float4* __restrict__ origin, float4* __restrict__ normal,
+                                                   const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0)
 {
     const unsigned gi = blockIdx.x * kBlock + threadIdx.x;
     if (gi >= total) return;
-    const DLevel& lv = ls.lv[level_of(ls, gi)];
+    const int level = level_of(ls, gi);
+    const DLevel& lv = ls.lv[level];
     const int i = (int)(gi - lv.probe_offset);
     const int px = lv.px0 + i % lv.sw, py = lv.py0 + i / lv.sw;
+    if (pixmask && level == 0) {
+        // direction culling: the pixels whose gather (S1/S9) can touch this probe are x in [(px-1)P + P/2, (px+1)P + P/2)
+        // (clamped indices at the frame border stay inside that range), likewise y; only the tile's pixels exist here
+        const int xa = max((px - 1) * lv.P + lv.P / 2, tile.x0), xb = min((px + 1) * lv.P + lv.P / 2, tile.x0 + tile.w);
+        const int ya = max((py - 1) * lv.P + lv.P / 2, tile.y0), yb = min((py + 1) * lv.P + lv.P / 2, tile.y0 + tile.h);
+        uint32_t m = 0u;
+        for (int y = ya; y < yb; y++)
+            for (int x = xa; x < xb; x++) m |= pixmask[(size_t)(y - tile.y0) * tile.w + (x - tile.x0)];
+        need0[i] = m;
+    }
     const int ax = min(px * lv.P + lv.P / 2, cam.W - 1), ay = min(py * lv.P + lv.P / 2, cam.H - 1);
     const float3 d = primary_dir(cam, ax, ay);
     float t;
@@ -279,6 +338,129 @@ __global__ void __launch_bounds__(kBlock) k_link_entry(DScene s, DLevelSet ls, E
     else entry_one(s, ls, plan, (blockIdx.x - link_blocks) * kBlock + threadIdx.x, origin, entry);
 }
 
+// ------------------------------------------------------------------ direction culling: request masks and ray lists
+// Request mask R_i of a probe of level i, one bit per REQUEST, row-major at resolution Dr_i:
+//   level 0:   a request is a texel;  Dr_0 = D_0;      bit set by k_gbuffer (a pixel weights it with cs_d > 0)
+//   level i>0: a request is a 2x2 quad of texels = one direction of level i-1;  Dr_i = D_{i-1}
+// A lower texel that misses takes its far field from the quad below its own direction in each of its (up to
+// four) upper probes (S8), so  R_1[k] |= R_0[p]  and  R_{i+1}[k] |= expand2x(R_i[p])  for every lower probe p
+// and every upper probe k that p links to with non-zero weight (k_link's own tables: exactly the set far_field
+// reads).  Texels outside the masks can only ever be multiplied by zero on the way to the irradiance.
+// One launch per level i, bottom-up, one thread per (probe, mask word): (a) append the word's requests to the
+// level's ray list (warp-aggregated append; entry = probe * Dr^2 + bit), (b) push the mask up to level i+1.
+// 16 bits -> 32 bits, every bit doubled: bit i -> bits 2i, 2i+1
+__device__ __forceinline__ uint32_t dup_spread16(uint32_t x)
+{
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x | (x << 1);
+}
+
+__global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_upper, int up_words, const float4* __restrict__ origin,
+                                                 const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
+                                                 const uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
+                                                 uint32_t* __restrict__ list, unsigned int* __restrict__ count)
+{
+    const int bits = Dr * Dr, words = (bits + 31) >> 5;
+    const size_t total = (size_t)lv.sw * lv.sh * words;
+    const size_t gi = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    uint32_t r = 0u, probe = 0u;
+    int w = 0;
+    if (gi < total) {
+        probe = (uint32_t)(gi / words);
+        w = (int)(gi - (size_t)probe * words);
+        if (__ldg(origin + probe).w != 0.0f) r = need[gi];
+        if (w == words - 1 && (bits & 31)) r &= (1u << (bits & 31)) - 1u;
+    }
+    // (a) ray list: block-aggregated append (one atomicAdd per block; all blocks hit the same counter)
+    __shared__ unsigned s_warp[kBlock / 32], s_base;
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const int n = __popc(r);
+    int pre = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if ((int)lane >= o) pre += t; }
+    if (lane == 31) s_warp[wid] = (unsigned)pre;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int k = 0; k < kBlock / 32; k++) { const unsigned t = s_warp[k]; s_warp[k] = tot; tot += t; }
+        s_base = tot ? atomicAdd(count, tot) : 0u;
+    }
+    __syncthreads();
+    unsigned base = s_base + s_warp[wid] + (unsigned)(pre - n);
+    for (uint32_t m = r; m; m &= m - 1u) list[base++] = probe * (uint32_t)bits + (uint32_t)(32 * w + __ffs((int)m) - 1);
+    // (b) the upper level's requests
+    if (!has_upper || !r) return;
+    const float4 lw = __ldg(link_w + probe);
+    if (lw.x < 0.0f) return;                       // no valid upper probe: the far field is the sky (S8)
+    uint32_t tw_idx[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, tw_val[4] = {0u, 0u, 0u, 0u};
+    if (has_upper == 1) {                          // level 0 -> 1: same resolution, no expansion
+        tw_idx[0] = (uint32_t)w; tw_val[0] = r;
+    } else if ((Dr & (Dr - 1)) == 0 && Dr >= 2) {  // expand2x by bit spreading (power-of-two Dr: every default level)
+        if (Dr >= 32) {        // the word is 32 requests of row y: rows 2y and 2y+1 of the target get the same two words
+            const int wpr = Dr >> 5, y = w / wpr, xw = w - y * wpr;
+            const uint32_t a = dup_spread16(r & 0xffffu), b = dup_spread16(r >> 16);
+            const uint32_t row0 = (uint32_t)((2 * y) * (2 * wpr) + 2 * xw), row1 = row0 + (uint32_t)(2 * wpr);
+            tw_idx[0] = row0; tw_val[0] = a; tw_idx[1] = row0 + 1; tw_val[1] = b;
+            tw_idx[2] = row1; tw_val[2] = a; tw_idx[3] = row1 + 1; tw_val[3] = b;
+        } else if (Dr == 16) { // two rows of 16 -> four target rows of 32
+            const uint32_t a = dup_spread16(r & 0xffffu), b = dup_spread16(r >> 16);
+            tw_idx[0] = 4u * w; tw_val[0] = a; tw_idx[1] = 4u * w + 1; tw_val[1] = a;
+            tw_idx[2] = 4u * w + 2; tw_val[2] = b; tw_idx[3] = 4u * w + 3; tw_val[3] = b;
+        } else if (Dr == 8) {  // four rows of 8 -> eight target rows of 16, two per word
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t t = dup_spread16((r >> (8 * q)) & 0xffu);
+                tw_idx[q] = 4u * w + q; tw_val[q] = t | (t << 16);
+            }
+        } else if (Dr == 4) {  // four rows of 4 -> eight target rows of 8, four per word
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint32_t t0 = dup_spread16((r >> (8 * q)) & 0xfu), t1 = dup_spread16((r >> (8 * q + 4)) & 0xfu);
+                tw_idx[q] = (uint32_t)q; tw_val[q] = t0 | (t0 << 8) | (t1 << 16) | (t1 << 24);
+            }
+        } else {               // Dr == 2: two rows of 2 -> four target rows of 4 in one word
+            const uint32_t t0 = dup_spread16(r & 3u), t1 = dup_spread16((r >> 2) & 3u);
+            tw_idx[0] = 0u; tw_val[0] = t0 | (t0 << 4) | (t1 << 8) | (t1 << 12);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (!tw_val[q]) tw_idx[q] = 0xffffffffu;
+    } else {                                       // expand2x: request (x, y) -> requests (2x..2x+1, 2y..2y+1) at 2*Dr
+        const int D2 = 2 * Dr;
+        for (uint32_t m = r; m; m &= m - 1u) {
+            const int sbit = 32 * w + __ffs((int)m) - 1, x = sbit % Dr, y = sbit / Dr;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t tbit = (uint32_t)((2 * y + j) * D2 + 2 * x);   // even: bits tbit, tbit+1 share a word
+                const uint32_t ti = tbit >> 5, tv = 3u << (tbit & 31u);
+                int slot = -1;
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (slot < 0 && (tw_idx[q] == ti || tw_idx[q] == 0xffffffffu)) slot = q;
+                if (slot < 0) {   // more than four target words (non-power-of-two Dr): flush one
+                    const uint4 li = __ldg(link_idx + probe);
+                    const uint32_t up[4] = {li.x, li.y, li.z, li.w};
+                    const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
+                    for (int k = 0; k < 4; k++) if (wk[k] > 0.0f) atomicOr(need_up + (size_t)up[k] * up_words + tw_idx[0], tw_val[0]);
+                    slot = 0; tw_idx[0] = 0xffffffffu; tw_val[0] = 0u;
+                }
+                tw_idx[slot] = ti; tw_val[slot] |= tv;
+            }
+        }
+    }
+    const uint4 li = __ldg(link_idx + probe);
+    const uint32_t up[4] = {li.x, li.y, li.z, li.w};
+    const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (!(wk[k] > 0.0f)) continue;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (tw_idx[q] != 0xffffffffu) atomicOr(need_up + (size_t)up[k] * up_words + tw_idx[q], tw_val[q]);
+    }
+}
+
 // far-field radiance of lower texel (dx, dy) from the merged upper level (S8).
 // `up_avg` holds, per upper probe and LOWER direction, a_k = 0.25*(((c0 + c1) + c2) + c3) of the four child texels
 // (float16 values summed in float32, exactly the S8 expression) — written once by the kernel that finalised
@@ -416,17 +598,40 @@ __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel
                                                   const float4* __restrict__ origin, const float* __restrict__ dirs,
                                                   uint2* __restrict__ texels, const float4* __restrict__ up_avg,
                                                   const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
-                                                  const int4* __restrict__ entry, float4* __restrict__ avg_out, int ystep)
+                                                  const int4* __restrict__ entry, float4* __restrict__ avg_out, int ystep,
+                                                  const uint32_t* __restrict__ list, const unsigned int* __restrict__ count, int quad)
 {
     cudaTriggerProgrammaticLaunchCompletion();   // the next level's kernel may begin once every block got here
     const size_t DD = (size_t)lv.D * lv.D;
+    // culled mode (list != null): thread j marches the j-th requested texel of the level's ray list (k_need) —
+    // for levels >= 1 the list holds 2x2 quads, four consecutive lanes each, so the child average is two shuffles
+    if (list) total = (size_t)__ldg(count) * (quad ? 4u : 1u);
     // grid-stride over whole warps (the child-average epilogue shuffles with a full mask): with a full-size grid
     // this is one iteration; with a resident grid (rc_set_tuning "march_waves") each warp walks packets g, g + G, ...
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const unsigned lane = threadIdx.x & 31u;
     for (size_t g0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); g0 < total; g0 += stride) {
         uint32_t probe = 0, d = 0;
-        const bool in_range = decode_texel(lv, map, g0 + lane, probe, d);
+        bool in_range;
+        if (list) {
+            const size_t j = g0 + lane;
+            in_range = j < total;
+            if (in_range) {
+                const int ld = 31 - __clz(lv.D);   // culled mode requires power-of-two D (rc_api)
+                const uint32_t e = __ldg(list + (quad ? j >> 2 : j));
+                if (quad) {
+                    const uint32_t q = e & (uint32_t)((DD >> 2) - 1);
+                    const uint32_t x = q & (uint32_t)((lv.D >> 1) - 1), y = q >> (ld - 1);
+                    probe = e >> (2 * ld - 2);
+                    d = ((2u * y + (((uint32_t)j >> 1) & 1u)) << ld) + 2u * x + ((uint32_t)j & 1u);
+                } else {
+                    probe = e >> (2 * ld);
+                    d = e & (uint32_t)(DD - 1);
+                }
+            }
+        } else {
+            in_range = decode_texel(lv, map, g0 + lane, probe, d);
+        }
         uint2 t = pack_half4(0.f, 0.f, 0.f, 1.f);   // invalid probe (S7)
         if (in_range) {
             const float4 og = __ldg(origin + probe);
@@ -722,24 +927,6 @@ __global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, float3 sky,
 }
 
 // ------------------------------------------------------------------ gather (S9)
-__device__ __forceinline__ void gather_axis(int coord, int P, int gmax, int& i0, int& i1, float& w0, float& w1)
-{
-    const int s = coord - P / 2;
-    int base, rem;
-    if ((P & (P - 1)) == 0) {           // power-of-two spacing: arithmetic shift == floor division
-        const int lp = 31 - __clz(P);
-        base = s >> lp;
-        rem = s & (P - 1);
-    } else {
-        base = (s >= 0) ? s / P : -((-s + P - 1) / P);
-        rem = s - base * P;
-    }
-    const float f = (float)rem / (float)P;
-    i0 = min(max(base, 0), gmax - 1);
-    i1 = min(max(base + 1, 0), gmax - 1);
-    w0 = 1.0f - f; w1 = f;
-}
-
 // Shared-memory staged gather.  A block owns 32x8 pixels; the <= (32/P0+2) x (8/P0+2) level-0 probes its
 // pixels interpolate between are copied once, coalesced (one 128-byte line per probe at D0 = 4), into
 // shared memory with a 16-byte pad per probe (so that the 8-9 probes a warp touches fall into different
@@ -885,10 +1072,11 @@ inline unsigned blocks_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlo
 
 }  // namespace
 
-void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, cudaStream_t st)
+void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, int DD0,
+                    const float* dirs0, uint16_t* pixmask, cudaStream_t st)
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
-    k_gbuffer<<<grid, kBlock, 0, st>>>(s, cam, L, tile, out);
+    k_gbuffer<<<grid, kBlock, 0, st>>>(s, cam, L, tile, out, DD0, dirs0, DD0 <= 16 ? pixmask : nullptr);
 }
 
 void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
@@ -899,9 +1087,10 @@ void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRe
 }
 
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
-                   const float* depth, const uint32_t* prim, float4* origin, float4* normal, cudaStream_t st)
+                   const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
+                   uint32_t* need0, cudaStream_t st)
 {
-    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal);
+    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal, pixmask, need0);
 }
 
 // lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do
@@ -934,11 +1123,12 @@ void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ, bool pdl,
-                  bool compact, int max_blocks, cudaStream_t st)
+                  bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, cudaStream_t st)
 {
     const int block = 128;
     if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;   // the 8x4 direction tile needs D % 8 == 0
-    const int ystep = march_avg_ystep(lv.D, map);
+    int ystep = march_avg_ystep(lv.D, map);
+    if (list) { map = MAP_LINEAR; ystep = quad ? 2 : 0; compact = false; max_blocks = 0; }
     if (!ystep || compact) avg_out = nullptr;
     size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
     if (map == MAP_PROBE_TILE) n = (size_t)((lv.sw + 7) / 8) * ((lv.sh + 3) / 4) * lv.D * lv.D * 32;
@@ -957,7 +1147,7 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     cfg.numAttrs = (pdl && fused && !top) ? 1 : 0;   // only a kernel that waits on its predecessor may start early
 #define RC_LAUNCH_MARCH(F, M, T)                                                                                              \
     (compact ? cudaLaunchKernelEx(&cfg, k_march_compact<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_avg, link_idx, link_w) \
-             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirs, texels, up_avg, link_idx, link_w, entry, avg_out, ystep))
+             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirs, texels, up_avg, link_idx, link_w, entry, avg_out, ystep, list, count, quad))
     const bool f = fused && !top;
     const int t = f ? 0 : topi;
     if (occ >= 16) { if (f) RC_LAUNCH_MARCH(true, 16, t); else RC_LAUNCH_MARCH(false, 16, t); }
@@ -965,6 +1155,13 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     else if (occ >= 10) { if (f) RC_LAUNCH_MARCH(true, 10, t); else RC_LAUNCH_MARCH(false, 10, t); }
     else { if (f) RC_LAUNCH_MARCH(true, 8, t); else RC_LAUNCH_MARCH(false, 8, t); }
 #undef RC_LAUNCH_MARCH
+}
+
+void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
+                 const float4* link_w, const uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, cudaStream_t st)
+{
+    const size_t total = (size_t)lv.sw * lv.sh * ((Dr * Dr + 31) / 32);
+    if (total) k_need<<<blocks_for(total), kBlock, 0, st>>>(lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count);
 }
 
 void launch_march_all(const DScene& s, const DLights& L, const DLevelSet& ls, const int* levels, int n, const int* map,

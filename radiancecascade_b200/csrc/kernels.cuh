@@ -20,13 +20,23 @@ struct MarchPlan {
 };
 struct EntryPlan { unsigned group_offset[RC_MAX_LEVELS + 1]; int g[RC_MAX_LEVELS]; int n; };
 
-void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, cudaStream_t st);
+// pixmask != null (direction culling, DD0 = D0^2 <= 16): also stores per pixel the mask of level-0 directions
+// the gather will weight with cs_d > 0
+void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, int DD0,
+                    const float* dirs0, uint16_t* pixmask, cudaStream_t st);
+// direction culling, level lv (bottom-up): appends the requests of `need` (bits at resolution Dr, probes of lv) to
+// `list` / `count` and pushes them to the upper level's masks `need_up` (has_upper: 0 none, 1 same resolution
+// [level 0 -> 1], 2 expanded 2x; up_words = mask words per upper probe) through k_link's tables
+void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
+                 const float4* link_w, const uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, cudaStream_t st);
 // deferred fs_main: albedo / direct colour from the stored visibility (on demand)
 void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
                    const float2* bary, uint2* albedo, uint2* direct, cudaStream_t st);
-// all levels' probes in one launch; anchors inside the tile reuse the G-buffer hit
+// all levels' probes in one launch; anchors inside the tile reuse the G-buffer hit; with pixmask (direction
+// culling) every level-0 probe also gets need0[probe] = OR of the masks of the pixels it serves
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
-                   const float* depth, const uint32_t* prim, float4* origin, float4* normal, cudaStream_t st);
+                   const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
+                   uint32_t* need0, cudaStream_t st);
 // One launch, two independent jobs that only read the probe origins:
 //  link:  per lower probe (levels 0..N-2, `link_total` probes) the 4 upper probe slots (sub-grid linear) and
 //         normalised weights (w.x < 0: no valid upper probe)
@@ -37,11 +47,13 @@ void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total
 // march level lv; fused != 0 also merges with the (already merged) upper level, read through its child averages
 // `up_avg` (float4 per upper probe and lower direction: 0.25*(((c0+c1)+c2)+c3), S8); entry: this level's
 // frontiers or null; avg_out: where to leave this level's own child averages when the kernel finalises the
-// level — only honoured when march_avg_ystep(D, map) != 0, otherwise call launch_child_avg afterwards
+// level — only honoured when march_avg_ystep(D, map) != 0, otherwise call launch_child_avg afterwards.
+// list / count (direction culling): march only the requested texels (quad = 0, level 0) or 2x2 quads (quad = 1)
+// listed by launch_need; avg_out is then always honoured
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ,
-                  bool pdl, bool compact, int max_blocks, cudaStream_t st);
+                  bool pdl, bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, cudaStream_t st);
 int march_avg_ystep(int D, int map);
 // child averages of a finalised level from its texels (paths whose march kernel does not write them itself)
 void launch_child_avg(const DLevel& lv, const uint2* texels, float4* avg_out, cudaStream_t st);

@@ -48,6 +48,12 @@ struct DevBuf {
         if (e != cudaSuccess || v.empty()) return e;
         return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     }
+    cudaError_t alloc_zero(size_t count)
+    {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || !count) return e;
+        return cudaMemset(p, 0, count * sizeof(T));
+    }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
@@ -103,6 +109,20 @@ struct rc_ctx {
     DevBuf<float4> d_avg;                // levels >= 1: child averages per (probe, lower direction) for the merge (S8)
     std::vector<size_t> avg_offset;      // float4s before level i in d_avg (level 0 has none)
     float4* avg_of(uint32_t level) { return level >= 1 && level < N ? d_avg.p + avg_offset[level] : nullptr; }
+    // direction culling (kernels.cu k_need): per level request masks, ray lists and list lengths
+    DevBuf<uint32_t> d_need, d_list;
+    DevBuf<uint16_t> d_pixmask;                     // per pixel: level-0 directions with cs_d > 0 (k_gbuffer)
+    DevBuf<unsigned int> d_ray_count;
+    std::vector<size_t> need_offset, list_offset;   // words / entries before level i
+    std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
+    int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
+    bool frame_culled = false;                      // the frame being recorded uses the ray lists
+    bool cull_possible() const
+    {
+        const uint32_t D0 = (uint32_t)levels[0].D;
+        return cull && !(cfg.flags & RC_CFG_SEPARATE_MERGE) && !march_persist && !march_compact && !march_batch &&
+               D0 * D0 <= 16 && (D0 & (D0 - 1)) == 0;
+    }
     DevBuf<float> d_dirs;
     DevBuf<float> d_depth;
     DevBuf<uint32_t> d_prim, d_nrm;
@@ -315,7 +335,7 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
         I.t_begin = L.t0; I.t_end = L.t1;
     }
     const size_t npx = (size_t)t.w * t.h;
-    CU_OK(c, c->d_cascade.alloc(texels));
+    CU_OK(c, c->d_cascade.alloc_zero(texels));
     CU_OK(c, c->d_origin.alloc(probes));
     CU_OK(c, c->d_normal.alloc(probes));
     CU_OK(c, c->d_link_idx.alloc(probes));
@@ -327,12 +347,27 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
         c->avg_offset[i] = avgs;
         avgs += (size_t)c->levels[i].sw * c->levels[i].sh * ((size_t)c->levels[i].D * c->levels[i].D / 4);
     }
-    CU_OK(c, c->d_avg.alloc(avgs ? avgs : 1));
+    // zero-initialised: culled texels / averages are only ever multiplied by zero weights, so they must stay finite
+    CU_OK(c, c->d_avg.alloc_zero(avgs ? avgs : 1));
+    c->need_offset.assign(N + 1, 0);
+    c->list_offset.assign(N + 1, 0);
+    c->need_res.assign(N, 0);
+    for (uint32_t i = 0; i < N; i++) {
+        const int Dr = i == 0 ? c->levels[0].D : c->levels[i - 1].D;
+        const size_t np = (size_t)c->levels[i].sw * c->levels[i].sh;
+        c->need_res[i] = Dr;
+        c->need_offset[i + 1] = c->need_offset[i] + np * (size_t)((Dr * Dr + 31) / 32);
+        c->list_offset[i + 1] = c->list_offset[i] + np * (size_t)(Dr * Dr);
+    }
+    CU_OK(c, c->d_need.alloc_zero(c->need_offset[N]));
+    CU_OK(c, c->d_list.alloc(c->list_offset[N]));
+    CU_OK(c, c->d_ray_count.alloc_zero(RC_MAX_LEVELS));
     CU_OK(c, c->d_dirs.upload(all_dirs));
     CU_OK(c, c->d_depth.alloc(npx));
     CU_OK(c, c->d_prim.alloc(npx));
     CU_OK(c, c->d_nrm.alloc(npx));
     CU_OK(c, c->d_bary.alloc(npx));
+    CU_OK(c, c->d_pixmask.alloc(npx));
     CU_OK(c, c->d_albedo.alloc(npx));
     CU_OK(c, c->d_direct.alloc(npx));
     CU_OK(c, c->d_irr.alloc(npx));
@@ -449,7 +484,9 @@ rc_status load_scene(rc_ctx* c)
     float node_cost = 0.f;
     if (const char* e = getenv("RC_BVH_LEAF")) max_leaf = atoi(e);
     if (const char* e = getenv("RC_BVH_NODE_COST")) node_cost = (float)atof(e);
-    build_bvh(h.v0.data(), h.e1.data(), h.e2.data(), h.skip.data(), nt, 1e-4f * diag, bvh, max_leaf, node_cost);
+    float split_budget = 0.f;
+    if (const char* e = getenv("RC_BVH_SPLIT")) split_budget = (float)atof(e);
+    build_bvh(h.v0.data(), h.e1.data(), h.e2.data(), h.skip.data(), nt, 1e-4f * diag, bvh, max_leaf, node_cost, split_budget);
     if (bvh.max_depth > 44) { c->error = "BVH deeper than the traversal stack"; return RC_ERR_SCENE_LOAD; }
     h.info.bvh_nodes = (uint32_t)bvh.nodes.size();
 
@@ -526,7 +563,7 @@ void destroy_ctx(rc_ctx* c)
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tri_geom.release(); c->d_tri_eg.release(); c->d_tris.release(); c->d_tri_model.release();
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
-    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release();
+    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release(); c->d_need.release(); c->d_list.release(); c->d_pixmask.release(); c->d_ray_count.release();
     c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -597,6 +634,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_MARCH_PDL")) c->march_pdl = atoi(e);
         if (const char* e = getenv("RC_MARCH_ENTRY")) c->march_entry = atoi(e) < -1 ? -1 : atoi(e);
         if (const char* e = getenv("RC_MARCH_BATCH")) c->march_batch = atoi(e) > 0 ? 1 : 0;
+        if (const char* e = getenv("RC_CULL")) c->cull = atoi(e) != 0;
         cudaDeviceProp prop;
         int bps = march_persist_blocks_per_sm();
         if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
@@ -652,8 +690,14 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     c->cam_rendered = c->cam;
     c->lights_rendered = c->lights;
     CU_OK(c, cudaEventRecord(c->ev[EV_START], st));
+    c->frame_culled = c->cull_possible();
+    if (c->frame_culled) {
+        CU_OK(c, cudaMemsetAsync(c->d_need.p, 0, c->d_need.n * sizeof(uint32_t), st));
+        CU_OK(c, cudaMemsetAsync(c->d_ray_count.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
+    }
     GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p};
-    launch_gbuffer(c->scene, c->cam, c->lights, c->tile, gb, st);
+    launch_gbuffer(c->scene, c->cam, c->lights, c->tile, gb, c->levels[0].D * c->levels[0].D, c->d_dirs.p,
+                   c->frame_culled ? c->d_pixmask.p : nullptr, st);
     c->launches++;
     CU_OK(c, cudaEventRecord(c->ev[EV_GBUF], st));
     DLevelSet ls;
@@ -661,12 +705,27 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     for (uint32_t i = 0; i < c->N; i++) ls.lv[i] = c->levels[i];
     const DLevel& top = c->levels[c->N - 1];
     const unsigned n_probes = top.probe_offset + (unsigned)(top.sw * top.sh);
-    launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p, st);
+    launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p,
+                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, st);
     c->launches++;
     {
         const int ne = c->march_persist ? 0 : c->entry_levels();
         if (c->N > 1 || ne > 0) {
             launch_link_entry(c->scene, ls, top.probe_offset, ne, c->d_origin.p, c->d_normal.p, c->d_link_idx.p, c->d_link_w.p, c->d_entry.p, st);
+            c->launches++;
+        }
+    }
+    if (c->frame_culled) {
+        // request masks bottom-up + one ray list per level; a top level that is filled needs neither
+        const uint32_t n_lists = c->top_fillable() ? c->N - 1 : c->N;
+        for (uint32_t i = 0; i < n_lists; i++) {
+            const DLevel& L = c->levels[i];
+            const int has_upper = i + 1 < n_lists ? (i == 0 ? 1 : 2) : 0;
+            const int up_res = i + 1 < c->N ? c->need_res[i + 1] : 0;
+            launch_need(L, c->need_res[i], has_upper, (up_res * up_res + 31) / 32, c->d_origin.p + L.probe_offset,
+                        c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, c->d_need.p + c->need_offset[i],
+                        has_upper ? c->d_need.p + c->need_offset[i + 1] : nullptr, c->d_list.p + c->list_offset[i],
+                        c->d_ray_count.p + i, st);
             c->launches++;
         }
     }
@@ -698,7 +757,8 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     int eff_map = c->march_map[level];
     if (eff_map == 1 && (L.D & 7)) eff_map = 0;   // as launch_march: the 8x4 direction tile needs D % 8 == 0
     // the march kernel leaves the child averages itself when it finalises the level and the 2x2 children share a warp
-    const bool avg_in_kernel = my_avg && (fused || top) && !c->march_persist && !compact && march_avg_ystep(L.D, eff_map) != 0;
+    const bool culled = c->frame_culled && !c->march_persist && !compact && fused;
+    const bool avg_in_kernel = my_avg && (fused || top) && !c->march_persist && !compact && (culled || march_avg_ystep(L.D, eff_map) != 0);
     if (c->march_persist)
         launch_march_persist(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
                              c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_thresh,
@@ -708,7 +768,8 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
                      c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset,
                      (int)level < c->entry_levels() ? c->d_entry.p + 2 * (size_t)L.probe_offset : nullptr,
                      avg_in_kernel ? my_avg : nullptr, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, compact,
-                     c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0, st);
+                     c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0,
+                     culled ? c->d_list.p + c->list_offset[level] : nullptr, c->d_ray_count.p + level, level >= 1 ? 1 : 0, st);
     c->launches++;
     if (!fused && !top) {
         launch_merge(L, *U, sky, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
@@ -738,6 +799,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "fill_top") c->fill_top = value != 0;
     else if (k == "march_entry" && value >= -1) c->march_entry = value;
     else if (k == "march_batch" && value >= 0 && value <= 1) c->march_batch = value;
+    else if (k == "cull" && value >= 0 && value <= 1) c->cull = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
     else if (k.rfind("march_map", 0) == 0 && k.size() == 10 && k[9] >= '0' && k[9] <= '9' && value >= 0 && value <= 2)

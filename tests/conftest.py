@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "culled: runs with the product's default direction culling (see tests/test_gpu_parity.py)")
 
 
 def _have_gpu() -> bool:

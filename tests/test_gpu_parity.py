@@ -13,6 +13,15 @@ from common import frame_setup, half_to_f32, oracle_scene, psnr, render_product
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _full_cascades(request, monkeypatch):
+    """The product culls texels that can only be multiplied by zero on the way to the irradiance (k_need); their
+    cascade texels are then unspecified.  The tests in this file compare whole cascades with the oracle, so they
+    run with every texel marched (RC_CULL=0, read at rc_create) unless marked `culled`."""
+    if "culled" not in request.keywords:
+        monkeypatch.setenv("RC_CULL", "0")
+
 SMALL = [("cube", 128, 128), ("test_room", 160, 96), ("teapot", 192, 108), ("sonic", 96, 128), ("living_room", 160, 90)]
 
 
@@ -267,6 +276,60 @@ def test_batched_march_equals_per_level_path(name, W, H):
     for o in out[1:]:
         for a, b in zip(out[0], o):
             assert np.array_equal(a, b)
+
+
+CULL_CASES = SMALL + [("living_room", 480, 270), ("teapot", 384, 216)]
+
+
+@pytest.mark.culled
+@pytest.mark.parametrize("name,W,H", CULL_CASES)
+def test_direction_culling_leaves_irradiance_bit_identical(name, W, H):
+    """Default path (direction culling on) against every-texel marching: same irradiance bit for bit; every texel
+    that was marched equals the unculled one, the others were never written (zero-initialised memory)."""
+    st, _, _ = frame_setup(name, W, H)
+    res = []
+    for cull in (0, 1):
+        r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name))
+        r.set_tuning("cull", cull)
+        r.update(st)
+        r.render()
+        res.append(([r.read_cascade(i).view(np.uint16).reshape(-1, 4) for i in range(6)],
+                    r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16), r.launch_count()))
+    (c0, e0, _), (c1, e1, _) = res
+    assert np.array_equal(e0, e1)
+    traced = total = 0
+    for a, b in zip(c0, c1):
+        same = np.all(a == b, axis=1)
+        assert np.all(b[~same] == 0), "a culled texel must be untouched"
+        traced += int(same.sum()); total += len(same)
+    assert traced < total        # something was culled (lower-hemisphere directions at the very least)
+
+
+@pytest.mark.culled
+@pytest.mark.parametrize("name,W,H,P0,D0,N", [("cube", 96, 96, 2, 2, 4), ("test_room", 120, 72, 8, 4, 3), ("teapot", 100, 60, 4, 2, 5),
+                                              ("living_room", 128, 72, 3, 4, 5), ("sonic", 64, 96, 4, 4, 1)])
+def test_direction_culling_non_default_parameters(name, W, H, P0, D0, N):
+    st, _, _ = frame_setup(name, W, H)
+    e = []
+    for cull in (0, 1):
+        r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name), rc.CascadeConfig(probe_spacing0=P0, dir_res0=D0, num_levels=N))
+        r.set_tuning("cull", cull)
+        r.update(st)
+        r.render()
+        e.append(r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16))
+    assert np.array_equal(e[0], e[1])
+
+
+@pytest.mark.culled
+def test_direction_culling_tile_equals_full_frame_crop():
+    name, W, H = "living_room", 256, 144
+    st, _, _ = frame_setup(name, W, H)
+    full = render_product(name, W, H, st).read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)
+    x0, y0, w, h = 64, 32, 128, 80
+    r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name), rc.CascadeConfig(tile=(x0, y0, w, h)))
+    r.update(st)
+    r.render()
+    assert np.array_equal(r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16), full[y0:y0 + h, x0:x0 + w])
 
 
 def test_resize_matches_fresh_context():
