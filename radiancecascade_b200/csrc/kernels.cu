@@ -156,13 +156,21 @@ __device__ __forceinline__ int level_of(const DLevelSet& ls, unsigned i)
 __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, TileRect tile, float offset,
                                                    const float* __restrict__ depth, const uint32_t* __restrict__ prim,
                                                    float4* __restrict__ origin, float4* __restrict__ normal,
-                                                   const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0)
+                                                   const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0,
+                                                   NeedPlan np, unsigned int* __restrict__ ray_count)
 {
     const unsigned gi = blockIdx.x * kBlock + threadIdx.x;
     if (gi >= total) return;
     const int level = level_of(ls, gi);
     const DLevel& lv = ls.lv[level];
     const int i = (int)(gi - lv.probe_offset);
+    if (pixmask) {   // direction culling: start the frame with empty request masks (levels >= 1) and empty ray lists
+        if (gi < RC_MAX_LEVELS) ray_count[gi] = 0u;
+        if (level >= 1) {
+            uint32_t* nw = need0 + np.offset[level] + (size_t)i * np.words[level];
+            for (int k = 0; k < np.words[level]; k++) nw[k] = 0u;
+        }
+    }
     const int px = lv.px0 + i % lv.sw, py = lv.py0 + i / lv.sw;
     if (pixmask && level == 0) {
         // direction culling: the pixels whose gather (S1/S9) can touch this probe are x in [(px-1)P + P/2, (px+1)P + P/2)
@@ -467,16 +475,23 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
 // level i+1 (k_march's warp-shuffle epilogue / k_fill_top / k_child_avg).  Each upper texel is needed by 16 lower
 // probes; averaging at the producer replaces 8 x 16-byte loads, 32 half2 conversions and 16 adds per lower texel
 // by 4 x 16-byte loads here.
-__device__ __forceinline__ float4 far_field(const float4* __restrict__ up_avg, int D, uint4 li, float4 lw, int dx, int dy, float3 sky)
+// up_const: the upper level is a top level that cannot hit anything (k_fill_top's case): every texel of a valid
+// upper probe is (sky, 1) rounded to float16, of an invalid one (0,0,0,1), and so are their child averages —
+// `up_avg` then points at the upper probes' ORIGINS (w = valid) and nothing needs to be filled or stored.
+__device__ __forceinline__ float4 far_field(const float4* __restrict__ up_avg, int D, uint4 li, float4 lw, int dx, int dy, float3 sky,
+                                            bool up_const = false)
 {
     if (lw.x < 0.0f) return make_float4(sky.x, sky.y, sky.z, 0.f);   // S8: no valid upper probe -> the sky
     float4 far = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t idx[4] = {li.x, li.y, li.z, li.w};
     const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
     const size_t DD = (size_t)D * D, off = (size_t)dy * D + dx;
+    const float4 skyh = unpack_half4(pack_half4(sky.x, sky.y, sky.z, 1.0f));
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const float4 a = __ldg(up_avg + idx[k] * DD + off);
+        float4 a;
+        if (up_const) a = __ldg(up_avg + idx[k]).w != 0.0f ? skyh : make_float4(0.f, 0.f, 0.f, 1.f);
+        else a = __ldg(up_avg + idx[k] * DD + off);
         far.x = fmaf(wk[k], a.x, far.x);
         far.y = fmaf(wk[k], a.y, far.y);
         far.z = fmaf(wk[k], a.z, far.z);
@@ -580,7 +595,7 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
             int dx, dy;
             if ((lv.D & (lv.D - 1)) == 0) { dx = (int)(d & (uint32_t)(lv.D - 1)); dy = (int)(d >> (31 - __clz(lv.D))); }
             else { dx = (int)(d % (uint32_t)lv.D); dy = (int)(d / (uint32_t)lv.D); }
-            const float4 far = far_field(up_avg, lv.D, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky);
+            const float4 far = far_field(up_avg, lv.D, __ldg(link_idx + probe), __ldg(link_w + probe), dx, dy, sky, UD < 0);
             c = make_float4(fmaf(raw.w, far.x, raw.x), fmaf(raw.w, far.y, raw.y), fmaf(raw.w, far.z, raw.z), raw.w * far.w);
             c.x = fminf(c.x, 65504.0f); c.y = fminf(c.y, 65504.0f); c.z = fminf(c.z, 65504.0f);
         } else {
@@ -938,9 +953,13 @@ template <int DDT>
 __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileRect tile, const float4* __restrict__ origin0,
                                                    const uint2* __restrict__ texels0, const float* __restrict__ dirs0,
                                                    const float* __restrict__ depth, const uint32_t* __restrict__ normal,
-                                                   uint2* __restrict__ out, int max_probes)
+                                                   uint2* __restrict__ out, int max_probes,
+                                                   const unsigned int* __restrict__ counts_in, unsigned int* __restrict__ counts_out)
 {
     extern __shared__ uint4 s_mem[];
+    // last kernel of the frame: publish the ray-list lengths to (mapped, pinned) host memory — posted writes,
+    // nothing waits for them; the host sizes the next frames' march grids from whatever has arrived
+    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) counts_out[threadIdx.x] = counts_in[threadIdx.x];
     const int DD = DDT ? DDT : l0.D * l0.D, H2 = DD >> 1, stride = H2 + 1;
     uint4* s_tex = s_mem;                                                   // [max_probes][stride]
     float4* s_org = reinterpret_cast<float4*>(s_mem + (size_t)max_probes * stride);   // [max_probes]
@@ -999,6 +1018,10 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
         const float cb = fmaxf(vdot(n, f3(s_dirs[3 * di + 3], s_dirs[3 * di + 4], s_dirs[3 * di + 5])), 0.0f);
         csum = csum + ca;
         csum = csum + cb;
+        // both cosines zero (about half of the directions: the lower hemisphere): fma(0, texel, acc) == acc for the
+        // finite, non-negative texels a cascade holds, so the pair is skipped — lanes of a warp are neighbouring
+        // pixels with similar normals, the branch is mostly uniform
+        if (!(ca > 0.0f || cb > 0.0f)) continue;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint4 r = s_tex[lk[k] * stride + (di >> 1)];
@@ -1088,9 +1111,9 @@ void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRe
 
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
-                   uint32_t* need0, cudaStream_t st)
+                   uint32_t* need0, const NeedPlan& np, unsigned int* ray_count, cudaStream_t st)
 {
-    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal, pixmask, need0);
+    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal, pixmask, need0, np, ray_count);
 }
 
 // lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do
@@ -1123,16 +1146,16 @@ void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ, bool pdl,
-                  bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, cudaStream_t st)
+                  bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const, cudaStream_t st)
 {
     const int block = 128;
     if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;   // the 8x4 direction tile needs D % 8 == 0
     int ystep = march_avg_ystep(lv.D, map);
-    if (list) { map = MAP_LINEAR; ystep = quad ? 2 : 0; compact = false; max_blocks = 0; }
+    if (list) { map = MAP_LINEAR; ystep = quad ? 2 : 0; compact = false; }   // max_blocks: the caller's estimate of the list length
     if (!ystep || compact) avg_out = nullptr;
     size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
     if (map == MAP_PROBE_TILE) n = (size_t)((lv.sw + 7) / 8) * ((lv.sh + 3) / 4) * lv.D * lv.D * 32;
-    const int UD = up ? up->D : 0;
+    const int UD = up_const ? -1 : (up ? up->D : 0);   // -1: up_avg holds the top probes' origins (far_field up_const)
     const int topi = top ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     size_t blocks = (n + block - 1) / block;
@@ -1246,14 +1269,15 @@ void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* 
 }
 
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
-                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, cudaStream_t st)
+                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, const unsigned int* counts_in,
+                   unsigned int* counts_out, cudaStream_t st)
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
     const int DD = l0.D * l0.D;
     const int max_probes = ((32 + l0.P - 1) / l0.P + 2) * ((8 + l0.P - 1) / l0.P + 2);
     const size_t smem = (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
     if (DD == 16) {
-        k_gather<16><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes);
+        k_gather<16><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out);
         return;
     }
     static size_t configured = 0;
@@ -1261,7 +1285,7 @@ void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const fl
         cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    k_gather<0><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes);
+    k_gather<0><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out);
 }
 
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,

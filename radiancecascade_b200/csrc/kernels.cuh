@@ -18,6 +18,8 @@ struct MarchPlan {
     int level[RC_MAX_LEVELS], map[RC_MAX_LEVELS], top[RC_MAX_LEVELS], use_entry[RC_MAX_LEVELS];
     int n;
 };
+// request-mask layout (direction culling): level l's words start at offset[l] (in 32-bit words), words[l] per probe
+struct NeedPlan { unsigned offset[RC_MAX_LEVELS]; int words[RC_MAX_LEVELS]; };
 struct EntryPlan { unsigned group_offset[RC_MAX_LEVELS + 1]; int g[RC_MAX_LEVELS]; int n; };
 
 // pixmask != null (direction culling, DD0 = D0^2 <= 16): also stores per pixel the mask of level-0 directions
@@ -33,10 +35,11 @@ void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const fl
 void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
                    const float2* bary, uint2* albedo, uint2* direct, cudaStream_t st);
 // all levels' probes in one launch; anchors inside the tile reuse the G-buffer hit; with pixmask (direction
-// culling) every level-0 probe also gets need0[probe] = OR of the masks of the pixels it serves
+// culling) every level-0 probe also gets need0[probe] = OR of the masks of the pixels it serves, and the request
+// masks of the upper levels (need0 + np.offset[l]) and the ray-list lengths are zeroed for the frame
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
-                   uint32_t* need0, cudaStream_t st);
+                   uint32_t* need0, const NeedPlan& np, unsigned int* ray_count, cudaStream_t st);
 // One launch, two independent jobs that only read the probe origins:
 //  link:  per lower probe (levels 0..N-2, `link_total` probes) the 4 upper probe slots (sub-grid linear) and
 //         normalised weights (w.x < 0: no valid upper probe)
@@ -49,11 +52,13 @@ void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total
 // frontiers or null; avg_out: where to leave this level's own child averages when the kernel finalises the
 // level — only honoured when march_avg_ystep(D, map) != 0, otherwise call launch_child_avg afterwards.
 // list / count (direction culling): march only the requested texels (quad = 0, level 0) or 2x2 quads (quad = 1)
-// listed by launch_need; avg_out is then always honoured
+// listed by launch_need; avg_out is then always honoured.  up_const: the upper level is an unmaterialised top
+// level that cannot hit anything — up_avg then holds the top probes' origins (far_field)
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ,
-                  bool pdl, bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, cudaStream_t st);
+                  bool pdl, bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const,
+                  cudaStream_t st);
 int march_avg_ystep(int D, int map);
 // child averages of a finalised level from its texels (paths whose march kernel does not write them itself)
 void launch_child_avg(const DLevel& lv, const uint2* texels, float4* avg_out, cudaStream_t st);
@@ -73,7 +78,8 @@ void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* 
 void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st);
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
-                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, cudaStream_t st);
+                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, const unsigned int* counts_in,
+                   unsigned int* counts_out, cudaStream_t st);
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
                       uchar4* composite, uchar4* direct_srgb, cudaStream_t st);
 void launch_trace_rays(const DScene& s, const float* rays, uint32_t n, float* hits, cudaStream_t st);

@@ -113,9 +113,20 @@ struct rc_ctx {
     DevBuf<uint32_t> d_need, d_list;
     DevBuf<uint16_t> d_pixmask;                     // per pixel: level-0 directions with cs_d > 0 (k_gbuffer)
     DevBuf<unsigned int> d_ray_count;
+    // List lengths are only known on the device.  The frame's last kernel (k_gather) writes them to mapped pinned
+    // host memory (posted writes, no copy, no sync); the next frames size their march grids from the latest values that have arrived
+    // (x1.25 + slack).  The kernels loop over the list with a grid stride, so any grid size is correct — a
+    // stale or missing estimate only costs empty blocks (too large) or a second loop trip (too small).
+    unsigned int* h_ray_count = nullptr;            // pinned, RC_MAX_LEVELS entries; 0xffffffff = nothing arrived yet
     std::vector<size_t> need_offset, list_offset;   // words / entries before level i
     std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
     int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
+    // rc_render records the frame's ~18 launches into a CUDA graph (stream capture) and submits it with ONE
+    // cudaGraphLaunch; every frame is re-captured and the executable graph updated in place
+    // (cudaGraphExecUpdate: camera, lights, grid sizes and the output slot are node parameters).
+    int use_graph = 1;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool capturing = false;
     bool frame_culled = false;                      // the frame being recorded uses the ray lists
     bool cull_possible() const
     {
@@ -362,6 +373,8 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
     CU_OK(c, c->d_need.alloc_zero(c->need_offset[N]));
     CU_OK(c, c->d_list.alloc(c->list_offset[N]));
     CU_OK(c, c->d_ray_count.alloc_zero(RC_MAX_LEVELS));
+    if (!c->h_ray_count) CU_OK(c, cudaHostAlloc((void**)&c->h_ray_count, RC_MAX_LEVELS * sizeof(unsigned int), cudaHostAllocMapped));
+    for (uint32_t i = 0; i < RC_MAX_LEVELS; i++) c->h_ray_count[i] = 0xffffffffu;
     CU_OK(c, c->d_dirs.upload(all_dirs));
     CU_OK(c, c->d_depth.alloc(npx));
     CU_OK(c, c->d_prim.alloc(npx));
@@ -563,7 +576,9 @@ void destroy_ctx(rc_ctx* c)
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tri_geom.release(); c->d_tri_eg.release(); c->d_tris.release(); c->d_tri_model.release();
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
-    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release(); c->d_need.release(); c->d_list.release(); c->d_pixmask.release(); c->d_ray_count.release();
+    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release(); c->d_need.release(); c->d_list.release(); c->d_pixmask.release();
+    if (c->h_ray_count) cudaFreeHost(c->h_ray_count);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec); c->d_ray_count.release();
     c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -635,6 +650,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_MARCH_ENTRY")) c->march_entry = atoi(e) < -1 ? -1 : atoi(e);
         if (const char* e = getenv("RC_MARCH_BATCH")) c->march_batch = atoi(e) > 0 ? 1 : 0;
         if (const char* e = getenv("RC_CULL")) c->cull = atoi(e) != 0;
+        if (const char* e = getenv("RC_GRAPH")) c->use_graph = atoi(e) != 0;
         cudaDeviceProp prop;
         int bps = march_persist_blocks_per_sm();
         if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
@@ -675,6 +691,13 @@ rc_status rc_resize(rc_ctx* c, uint32_t width, uint32_t height)
     return setup_frame(c, width, height);
 }
 
+// stage-timing events: inside a stream capture they must become EXTERNAL event-record nodes, otherwise the host
+// cannot synchronise on / time them (cudaErrorInvalidValue)
+static cudaError_t record_event(rc_ctx* c, cudaEvent_t ev, cudaStream_t st)
+{
+    return cudaEventRecordWithFlags(ev, st, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
 rc_status rc_render_begin(rc_ctx* c, void* stream)
 {
     if (!c) return RC_ERR_INVALID_ARG;
@@ -689,24 +712,25 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     c->frame_batched = false;
     c->cam_rendered = c->cam;
     c->lights_rendered = c->lights;
-    CU_OK(c, cudaEventRecord(c->ev[EV_START], st));
+    CU_OK(c, record_event(c, c->ev[EV_START], st));
     c->frame_culled = c->cull_possible();
-    if (c->frame_culled) {
-        CU_OK(c, cudaMemsetAsync(c->d_need.p, 0, c->d_need.n * sizeof(uint32_t), st));
-        CU_OK(c, cudaMemsetAsync(c->d_ray_count.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
-    }
     GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p};
     launch_gbuffer(c->scene, c->cam, c->lights, c->tile, gb, c->levels[0].D * c->levels[0].D, c->d_dirs.p,
                    c->frame_culled ? c->d_pixmask.p : nullptr, st);
     c->launches++;
-    CU_OK(c, cudaEventRecord(c->ev[EV_GBUF], st));
+    CU_OK(c, record_event(c, c->ev[EV_GBUF], st));
     DLevelSet ls;
     ls.n = (int)c->N;
     for (uint32_t i = 0; i < c->N; i++) ls.lv[i] = c->levels[i];
     const DLevel& top = c->levels[c->N - 1];
     const unsigned n_probes = top.probe_offset + (unsigned)(top.sw * top.sh);
+    NeedPlan np{};
+    for (uint32_t i = 0; i < c->N; i++) {
+        np.offset[i] = (unsigned)c->need_offset[i];
+        np.words[i] = (c->need_res[i] * c->need_res[i] + 31) / 32;
+    }
     launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p,
-                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, st);
+                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, np, c->d_ray_count.p, st);
     c->launches++;
     {
         const int ne = c->march_persist ? 0 : c->entry_levels();
@@ -729,7 +753,7 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
             c->launches++;
         }
     }
-    CU_OK(c, cudaEventRecord(c->ev[EV_PROBES], st));
+    CU_OK(c, record_event(c, c->ev[EV_PROBES], st));
     CU_OK(c, cudaGetLastError());
     return RC_OK;
 }
@@ -746,6 +770,15 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     uint2* tex = c->d_cascade.p + L.texel_offset;
     const float4* up = top ? nullptr : c->avg_of(level + 1);   // the merge reads level i+1 through its child averages
     float4* my_avg = c->avg_of(level);                          // ... and level i-1 will read this level's
+    // culled frames never materialise a top level that cannot hit anything: level N-2 evaluates its far field
+    // from the top probes' validity alone (far_field's up_const)
+    const bool const_top = c->frame_culled && c->top_fillable();
+    if (top && const_top) {
+        if (c->level_timing) CU_OK(c, cudaEventRecord(c->ev_level[level], st));
+        return RC_OK;
+    }
+    const bool up_const = const_top && level + 2 == c->N;
+    if (up_const) up = c->d_origin.p + U->probe_offset;
     if (top && c->top_fillable()) {
         launch_fill_top(L, sky, c->d_origin.p + L.probe_offset, tex, my_avg, st);
         c->launches++;
@@ -758,6 +791,14 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     if (eff_map == 1 && (L.D & 7)) eff_map = 0;   // as launch_march: the 8x4 direction tile needs D % 8 == 0
     // the march kernel leaves the child averages itself when it finalises the level and the 2x2 children share a warp
     const bool culled = c->frame_culled && !c->march_persist && !compact && fused;
+    int list_blocks = 0;   // 0 = the upper bound (every texel)
+    if (culled && c->h_ray_count) {
+        const unsigned int prev = *(volatile unsigned int*)(c->h_ray_count + level);   // entries of the last list that arrived
+        if (prev != 0xffffffffu) {
+            const double threads = (double)prev * (level >= 1 ? 4.0 : 1.0) * 1.25;
+            list_blocks = (int)std::min(threads / 128.0 + 64.0, 2.0e9);
+        }
+    }
     const bool avg_in_kernel = my_avg && (fused || top) && !c->march_persist && !compact && (culled || march_avg_ystep(L.D, eff_map) != 0);
     if (c->march_persist)
         launch_march_persist(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
@@ -768,8 +809,8 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
                      c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset,
                      (int)level < c->entry_levels() ? c->d_entry.p + 2 * (size_t)L.probe_offset : nullptr,
                      avg_in_kernel ? my_avg : nullptr, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, compact,
-                     c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0,
-                     culled ? c->d_list.p + c->list_offset[level] : nullptr, c->d_ray_count.p + level, level >= 1 ? 1 : 0, st);
+                     culled ? list_blocks : (c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0),
+                     culled ? c->d_list.p + c->list_offset[level] : nullptr, c->d_ray_count.p + level, level >= 1 ? 1 : 0, up_const, st);
     c->launches++;
     if (!fused && !top) {
         launch_merge(L, *U, sky, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
@@ -800,6 +841,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "march_entry" && value >= -1) c->march_entry = value;
     else if (k == "march_batch" && value >= 0 && value <= 1) c->march_batch = value;
     else if (k == "cull" && value >= 0 && value <= 1) c->cull = value;
+    else if (k == "graph" && value >= 0 && value <= 1) c->use_graph = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
     else if (k.rfind("march_map", 0) == 0 && k.size() == 10 && k[9] >= '0' && k[9] <= '9' && value >= 0 && value <= 2)
@@ -808,21 +850,31 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     return RC_OK;
 }
 
-rc_status rc_render_end(rc_ctx* c, void* stream)
+// the irradiance is double-buffered for rc_read_target_async: flip, and wait for a read-back still using the new slot
+static rc_status next_output_slot(rc_ctx* c, cudaStream_t st)
 {
-    if (!c) return RC_ERR_INVALID_ARG;
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    CU_OK(c, cudaEventRecord(c->ev[EV_LEVELS], st));
     c->irr_slot ^= 1;
     if (c->copy_pending[c->irr_slot]) {   // an asynchronous read-back of this buffer may still be in flight
         CU_OK(c, cudaStreamWaitEvent(st, c->ev_copy_done[c->irr_slot], 0));
         c->copy_pending[c->irr_slot] = false;
     }
+    return RC_OK;
+}
+
+rc_status rc_render_end(rc_ctx* c, void* stream)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CU_OK(c, record_event(c, c->ev[EV_LEVELS], st));
+    if (!c->capturing) {                  // (a captured frame did this before the capture began)
+        rc_status s = next_output_slot(c, st);
+        if (s != RC_OK) return s;
+    }
     const DLevel& L0 = c->levels[0];
     launch_gather(c->cam, L0, c->tile, c->d_origin.p + L0.probe_offset, c->d_cascade.p + L0.texel_offset, c->d_dirs.p,
-                  c->d_depth.p, c->d_nrm.p, c->irr(), st);
+                  c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, st);
     c->launches++;
-    CU_OK(c, cudaEventRecord(c->ev[EV_GATHER], st));
+    CU_OK(c, record_event(c, c->ev[EV_GATHER], st));
     CU_OK(c, cudaGetLastError());
     c->ev_recorded = true;
     return RC_OK;
@@ -850,7 +902,7 @@ static rc_status render_levels_batched(rc_ctx* c, void* stream)
                          c->d_origin.p, c->d_dirs.p, c->d_cascade.p, c->d_entry.p, c->march_occ, st);
         c->launches++;
     }
-    CU_OK(c, cudaEventRecord(c->ev[EV_MARCH_ALL], st));
+    CU_OK(c, record_event(c, c->ev[EV_MARCH_ALL], st));
     if (first == (int)c->N - 1 && c->N > 1) {   // a marched top level is final as it is
         launch_child_avg(c->levels[c->N - 1], c->d_cascade.p + c->levels[c->N - 1].texel_offset, c->avg_of(c->N - 1), st);
         c->launches++;
@@ -869,7 +921,57 @@ static rc_status render_levels_batched(rc_ctx* c, void* stream)
     return RC_OK;
 }
 
+static rc_status render_enqueue(rc_ctx* c, void* stream);
+
 rc_status rc_render(rc_ctx* c, void* stream)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    if (!c->use_graph || c->level_timing || !c->have_camera) return render_enqueue(c, stream);
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    rc_status s = next_output_slot(c, st);     // waits on an event from outside the capture: must precede it
+    if (s != RC_OK) return s;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        c->use_graph = 0;
+        c->irr_slot ^= 1;                      // render_enqueue flips again
+        return render_enqueue(c, stream);
+    }
+    c->capturing = true;
+    s = render_enqueue(c, stream);
+    c->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (s != RC_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (s != RC_OK) return s;
+        c->use_graph = 0;                      // this driver / stream cannot capture the frame: plain launches from now on
+        c->irr_slot ^= 1;
+        return render_enqueue(c, stream);
+    }
+    if (c->graph_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(c->graph_exec, graph, &info) != cudaSuccess) {   // topology changed (tuning, resize, ...)
+            cudaGetLastError();
+            cudaGraphExecDestroy(c->graph_exec);
+            c->graph_exec = nullptr;
+        }
+    }
+    if (!c->graph_exec && cudaGraphInstantiate(&c->graph_exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphDestroy(graph);
+        c->graph_exec = nullptr;
+        c->use_graph = 0;
+        c->irr_slot ^= 1;
+        return render_enqueue(c, stream);
+    }
+    cudaGraphDestroy(graph);
+    CU_OK(c, cudaGraphLaunch(c->graph_exec, st));
+    return RC_OK;
+}
+
+static rc_status render_enqueue(rc_ctx* c, void* stream)
 {
     rc_status s = rc_render_begin(c, stream);
     if (s != RC_OK) return s;
@@ -984,6 +1086,8 @@ rc_status rc_stage_times(rc_ctx* c, float* ms, uint32_t n)
     if (!c || !ms) return RC_ERR_INVALID_ARG;
     if (!c->ev_recorded) { c->error = "rc_stage_times before rc_render"; return RC_ERR_STATE; }
     cudaSetDevice(c->device);
+    // (events recorded by graph nodes only change state when the graph runs: wait for the stream, not the event)
+    CU_OK(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
     CU_OK(c, cudaEventSynchronize(c->ev[EV_GATHER]));
     float t[RC_STAGE_COUNT] = {0};
     cudaEventElapsedTime(&t[RC_STAGE_GBUFFER], c->ev[EV_START], c->ev[EV_GBUF]);

@@ -28,7 +28,7 @@ N = 40
 side = torch.cuda.Stream()
 junk = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
 junk_host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-for mode in ("pipelined", "render_only_nosync", "nosync_plus_unrelated_d2h", "nosync_plus_unrelated_h2d"):
+for mode in ("pipelined", "render_only_nosync", "pipelined_nowait"):
     T = dict(set=0.0, render=0.0, read=0.0, wait=0.0)
     for i in range(3):
         set_frame(i); r.render(sh)
@@ -41,10 +41,10 @@ for mode in ("pipelined", "render_only_nosync", "nosync_plus_unrelated_d2h", "no
         t1 = time.perf_counter()
         if mode != "copy_only": r.render(sh)
         t2 = time.perf_counter()
-        if mode in ("pipelined", "copy_only"):
+        if mode in ("pipelined", "copy_only", "pipelined_nowait"):
             tk = r.read_irradiance_async(hosts[i & 1].data_ptr(), nbytes)
             t3 = time.perf_counter()
-            if prev is not None: r.read_wait(prev)
+            if prev is not None and mode != "pipelined_nowait": r.read_wait(prev)
             prev = tk
         elif mode == "render_only_sync_each":
             t3 = time.perf_counter(); stream.synchronize()
@@ -63,4 +63,4 @@ for mode in ("pipelined", "render_only_nosync", "nosync_plus_unrelated_d2h", "no
     if prev is not None: r.read_wait(prev)
     torch.cuda.synchronize()
     tot = (time.perf_counter() - t_start) * 1e3 / N
-    print(mode, "ms/frame %.4f" % tot, {k: round(v * 1e3 / N, 4) for k, v in T.items()}, "device frame", r.stage_times()["frame"])
+    print(mode, "ms/frame %.4f" % tot, {k: round(v * 1e3 / N, 4) for k, v in T.items()}, "device stages", {k: round(v, 4) for k, v in r.stage_times().items()})
