@@ -165,10 +165,17 @@ rc_status rc_level_times(rc_ctx* ctx, float* ms, uint32_t n);
 /* Runtime tuning knobs (A/B measurement; defaults are the measured best): "level_timing" 0/1,
  * "march_persist" 0/1 (persistent ray-replacement march vs one ray per thread), "march_thresh"
  * 1..32 (refill when fewer lanes are busy), "march_pdl" 0/1, "march_block" 64..512, "march_grid",
- * "march_map<level>" 0 linear / 1 direction tile / 2 probe tile. */
+ * "march_map<level>" 0 linear / 1 direction tile / 2 probe tile, "march_entry" -1 auto / n levels that start their
+ * traversal at per-probe BVH entry frontiers, "march_batch" 0/1 (all levels in one launch + separate merges),
+ * "cull" 0/1 (direction culling), "graph" 0/1 (submit the frame as one CUDA graph). */
 rc_status rc_set_tuning(rc_ctx* ctx, const char* key, int value);
 /* Number of kernels rc_render launches per frame. */
 rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
+/* Direction culling (default on; rc_set_tuning "cull" 0 marches every texel): rays[level] = texels of the level
+ * that the last frame actually marched — the texels some pixel's irradiance depends on with a non-zero weight;
+ * every other texel of the cascade is left unspecified.  UINT32_MAX where the level was not culled (every texel
+ * marched), 0 for a top level that is constant and never materialised.  Waits for the frame to finish. */
+rc_status rc_rays_marched(rc_ctx* ctx, uint32_t* rays, uint32_t n);
 
 rc_status rc_get_levels(rc_ctx* ctx, rc_level_info* out, uint32_t max_levels, uint32_t* num_levels);
 rc_status rc_get_scene_info(rc_ctx* ctx, rc_scene_info* out);

@@ -81,6 +81,7 @@ SYMBOLS = {
     "rc_level_times": (C.c_int32, [_P, C.POINTER(C.c_float), C.c_uint32]),
     "rc_set_tuning": (C.c_int32, [_P, C.c_char_p, C.c_int]),
     "rc_launch_count": (C.c_int32, [_P, C.POINTER(C.c_uint32)]),
+    "rc_rays_marched": (C.c_int32, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "rc_get_levels": (C.c_int32, [_P, C.POINTER(rc_level_info), C.c_uint32, C.POINTER(C.c_uint32)]),
     "rc_get_scene_info": (C.c_int32, [_P, C.POINTER(rc_scene_info)]),
     "rc_get_tile": (C.c_int32, [_P, C.POINTER(C.c_uint32)]),

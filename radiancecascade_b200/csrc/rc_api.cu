@@ -170,28 +170,12 @@ struct rc_ctx {
     int fill_top = 1;        // fill a top level that cannot hit anything instead of marching it (exact)
     int march_waves = 0;     // > 0: march grid capped at SMs * occ * waves blocks (grid-stride loop); 0: one thread per ray
     int sm_count = 148;
-    // levels 0..march_entry-1 start their traversal at the per-probe entry frontier (0 = at the root); -1 = automatic:
-    // the levels whose interval ends within a tenth of the scene diagonal (0..2 at the defaults), on frames of at
-    // least 3 M texels per level — building the frontiers is one latency-bound wave of ~17 us, which a 1080p frame
-    // does not win back (teapot: march -14 us) while a 4K frame does (living_room: march -150 us)
-    int march_entry = -1;
-    // 1: march all levels in one launch, then merge top-down with k_merge; 0 (default): one fused march+merge kernel
-    // per level, PDL-chained.  Measured: the single launch saves nothing over the PDL chain and the
-    // separate merges cost more than the fused ones.
-    int march_batch = 0;
-    size_t texels_per_level() const { return levels.empty() ? 0 : (size_t)levels[0].sw * levels[0].sh * levels[0].D * levels[0].D; }
-    bool batched() const
-    {
-        if (march_persist || level_timing) return false;
-        return march_batch > 0;
-    }
-    bool top_fillable() const
-    {
-        // S7 shortcut, exact: a ray that starts on a surface (inside the scene's box grown by the probe offset) is
-        // farther than the box diagonal from every triangle once t > diag + 2*offset -> the whole level misses
-        const DLevel& L = levels[N - 1];
-        return fill_top && L.t0 > host.diag * 1.001f + 2.0f * offset && (((size_t)L.texel_offset) & 1) == 0;
-    }
+    // levels 0..march_entry-1 start their traversal at the per-probe BVH entry frontier (k_link_entry); 0 = at the root.
+    // Measured: with every texel marched the frontiers save 0.15 ms of a 4K living_room frame (L0 -24 %,
+    // L1 -22 %, L2 -9 %); with direction culling half of those rays are gone and building the frontiers (35 us) costs
+    // what they save, so the default is off.  -1 = the levels whose interval ends within a tenth of the scene
+    // diagonal, on frames of at least 3 M texels per level.
+    int march_entry = 0;
     int entry_levels() const
     {
         if (march_entry >= 0) return march_entry < (int)N ? march_entry : (int)N;
@@ -1124,6 +1108,23 @@ rc_status rc_launch_count(rc_ctx* c, uint32_t* launches)
 {
     if (!c || !launches) return RC_ERR_INVALID_ARG;
     *launches = c->launches;
+    return RC_OK;
+}
+
+rc_status rc_rays_marched(rc_ctx* c, uint32_t* rays, uint32_t n)
+{
+    if (!c || !rays) return RC_ERR_INVALID_ARG;
+    if (!c->ev_recorded) { c->error = "rc_rays_marched before rc_render"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    CU_OK(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t v = 0xffffffffu;
+        if (i < c->N && c->frame_culled) {
+            if (i + 1 == c->N && c->top_fillable()) v = 0;
+            else v = c->h_ray_count[i] * (i >= 1 ? 4u : 1u);   // lists above level 0 hold 2x2 quads
+        }
+        rays[i] = v;
+    }
     return RC_OK;
 }
 

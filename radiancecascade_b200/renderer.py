@@ -281,6 +281,13 @@ class DefaultRenderer:
     def set_tuning(self, key: str, value: int) -> None:
         self._check(self._lib.rc_set_tuning(self._h, key.encode(), int(value)))
 
+    def rays_marched(self) -> List[Optional[int]]:
+        """Texels each level of the last frame actually marched (None: the level was not culled)."""
+        n = len(self.levels())
+        v = (C.c_uint32 * n)()
+        self._check(self._lib.rc_rays_marched(self._h, v, n))
+        return [None if int(x) == 0xFFFFFFFF else int(x) for x in v]
+
     def launch_count(self) -> int:
         n = C.c_uint32()
         self._check(self._lib.rc_launch_count(self._h, C.byref(n)))
