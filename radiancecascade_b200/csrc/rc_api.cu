@@ -176,6 +176,23 @@ struct rc_ctx {
     // what they save, so the default is off.  -1 = the levels whose interval ends within a tenth of the scene
     // diagonal, on frames of at least 3 M texels per level.
     int march_entry = 0;
+    // 1: march all levels in one launch, then merge top-down with k_merge; 0 (default): one fused march+merge kernel
+    // per level, PDL-chained.  Measured: the single launch saves nothing over the PDL chain and the
+    // separate merges cost more than the fused ones.
+    int march_batch = 0;
+    size_t texels_per_level() const { return levels.empty() ? 0 : (size_t)levels[0].sw * levels[0].sh * levels[0].D * levels[0].D; }
+    bool batched() const
+    {
+        if (march_persist || level_timing) return false;
+        return march_batch > 0;
+    }
+    bool top_fillable() const
+    {
+        // S7 shortcut, exact: a ray that starts on a surface (inside the scene's box grown by the probe offset) is
+        // farther than the box diagonal from every triangle once t > diag + 2*offset -> the whole level misses
+        const DLevel& L = levels[N - 1];
+        return fill_top && L.t0 > host.diag * 1.001f + 2.0f * offset && (((size_t)L.texel_offset) & 1) == 0;
+    }
     int entry_levels() const
     {
         if (march_entry >= 0) return march_entry < (int)N ? march_entry : (int)N;
