@@ -156,21 +156,14 @@ __device__ __forceinline__ int level_of(const DLevelSet& ls, unsigned i)
 __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, TileRect tile, float offset,
                                                    const float* __restrict__ depth, const uint32_t* __restrict__ prim,
                                                    float4* __restrict__ origin, float4* __restrict__ normal,
-                                                   const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0,
-                                                   NeedPlan np, unsigned int* __restrict__ ray_count)
+                                                   const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0)
 {
     const unsigned gi = blockIdx.x * kBlock + threadIdx.x;
     if (gi >= total) return;
     const int level = level_of(ls, gi);
     const DLevel& lv = ls.lv[level];
     const int i = (int)(gi - lv.probe_offset);
-    if (pixmask) {   // direction culling: start the frame with empty request masks (levels >= 1) and empty ray lists
-        if (gi < RC_MAX_LEVELS) ray_count[gi] = 0u;
-        if (level >= 1) {
-            uint32_t* nw = need0 + np.offset[level] + (size_t)i * np.words[level];
-            for (int k = 0; k < np.words[level]; k++) nw[k] = 0u;
-        }
-    }
+
     const int px = lv.px0 + i % lv.sw, py = lv.py0 + i / lv.sw;
     if (pixmask && level == 0) {
         // direction culling: the pixels whose gather (S1/S9) can touch this probe are x in [(px-1)P + P/2, (px+1)P + P/2)
@@ -178,9 +171,15 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
         const int xa = max((px - 1) * lv.P + lv.P / 2, tile.x0), xb = min((px + 1) * lv.P + lv.P / 2, tile.x0 + tile.w);
         const int ya = max((py - 1) * lv.P + lv.P / 2, tile.y0), yb = min((py + 1) * lv.P + lv.P / 2, tile.y0 + tile.h);
         uint32_t m = 0u;
-        for (int y = ya; y < yb; y++)
-            for (int x = xa; x < xb; x++) m |= pixmask[(size_t)(y - tile.y0) * tile.w + (x - tile.x0)];
-        need0[i] = m;
+        for (int y = ya; y < yb; y++) {
+            const uint16_t* row = pixmask + (size_t)(y - tile.y0) * tile.w + (xa - tile.x0);
+            int x = 0;
+            const int n = xb - xa;
+            if ((reinterpret_cast<uintptr_t>(row) & 3u) == 0)   // two pixels per load
+                for (; x + 1 < n; x += 2) m |= *reinterpret_cast<const uint32_t*>(row + x);
+            for (; x < n; x++) m |= row[x];
+        }
+        need0[i] = (m | (m >> 16)) & 0xffffu;
     }
     const int ax = min(px * lv.P + lv.P / 2, cam.W - 1), ay = min(py * lv.P + lv.P / 2, cam.H - 1);
     const float3 d = primary_dir(cam, ax, ay);
@@ -368,19 +367,28 @@ __device__ __forceinline__ uint32_t dup_spread16(uint32_t x)
 
 __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_upper, int up_words, const float4* __restrict__ origin,
                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
-                                                 const uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
-                                                 uint32_t* __restrict__ list, unsigned int* __restrict__ count)
+                                                 uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
+                                                 uint32_t* __restrict__ list, unsigned int* __restrict__ count, int clear)
 {
     const int bits = Dr * Dr, words = (bits + 31) >> 5;
     const size_t total = (size_t)lv.sw * lv.sh * words;
     const size_t gi = (size_t)blockIdx.x * kBlock + threadIdx.x;
     uint32_t r = 0u, probe = 0u;
     int w = 0;
+    float4 lw = make_float4(-1.f, 0.f, 0.f, 0.f);
+    uint4 li = make_uint4(0u, 0u, 0u, 0u);
     if (gi < total) {
         probe = (uint32_t)(gi / words);
         w = (int)(gi - (size_t)probe * words);
-        if (__ldg(origin + probe).w != 0.0f) r = need[gi];
+        // independent loads first: the kernel is one short latency-bound wave
+        const float valid = __ldg(origin + probe).w;
+        r = need[gi];
+        if (has_upper) { lw = __ldg(link_w + probe); li = __ldg(link_idx + probe); }
+        if (valid == 0.0f) r = 0u;
         if (w == words - 1 && (bits & 31)) r &= (1u << (bits & 31)) - 1u;
+        // consume and clear: the masks of levels >= 1 are accumulated by atomicOr, so they must be empty when the next
+        // frame starts (level 0 is overwritten by k_probes).  A stale bit could only ever add a ray, never lose one.
+        if (clear) need[gi] = 0u;
     }
     // (a) ray list: block-aggregated append (one atomicAdd per block; all blocks hit the same counter)
     __shared__ unsigned s_warp[kBlock / 32], s_base;
@@ -401,7 +409,6 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
     for (uint32_t m = r; m; m &= m - 1u) list[base++] = probe * (uint32_t)bits + (uint32_t)(32 * w + __ffs((int)m) - 1);
     // (b) the upper level's requests
     if (!has_upper || !r) return;
-    const float4 lw = __ldg(link_w + probe);
     if (lw.x < 0.0f) return;                       // no valid upper probe: the far field is the sky (S8)
     uint32_t tw_idx[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, tw_val[4] = {0u, 0u, 0u, 0u};
     if (has_upper == 1) {                          // level 0 -> 1: same resolution, no expansion
@@ -447,7 +454,6 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
 #pragma unroll
                 for (int q = 0; q < 4; q++) if (slot < 0 && (tw_idx[q] == ti || tw_idx[q] == 0xffffffffu)) slot = q;
                 if (slot < 0) {   // more than four target words (non-power-of-two Dr): flush one
-                    const uint4 li = __ldg(link_idx + probe);
                     const uint32_t up[4] = {li.x, li.y, li.z, li.w};
                     const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
                     for (int k = 0; k < 4; k++) if (wk[k] > 0.0f) atomicOr(need_up + (size_t)up[k] * up_words + tw_idx[0], tw_val[0]);
@@ -457,7 +463,6 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
             }
         }
     }
-    const uint4 li = __ldg(link_idx + probe);
     const uint32_t up[4] = {li.x, li.y, li.z, li.w};
     const float wk[4] = {lw.x, lw.y, lw.z, lw.w};
 #pragma unroll
@@ -954,12 +959,15 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
                                                    const uint2* __restrict__ texels0, const float* __restrict__ dirs0,
                                                    const float* __restrict__ depth, const uint32_t* __restrict__ normal,
                                                    uint2* __restrict__ out, int max_probes,
-                                                   const unsigned int* __restrict__ counts_in, unsigned int* __restrict__ counts_out)
+                                                   unsigned int* __restrict__ counts_in, unsigned int* __restrict__ counts_out)
 {
     extern __shared__ uint4 s_mem[];
     // last kernel of the frame: publish the ray-list lengths to (mapped, pinned) host memory — posted writes,
     // nothing waits for them; the host sizes the next frames' march grids from whatever has arrived
-    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) counts_out[threadIdx.x] = counts_in[threadIdx.x];
+    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) {
+        counts_out[threadIdx.x] = counts_in[threadIdx.x];
+        counts_in[threadIdx.x] = 0u;   // the next frame's lists start empty
+    }
     const int DD = DDT ? DDT : l0.D * l0.D, H2 = DD >> 1, stride = H2 + 1;
     uint4* s_tex = s_mem;                                                   // [max_probes][stride]
     float4* s_org = reinterpret_cast<float4*>(s_mem + (size_t)max_probes * stride);   // [max_probes]
@@ -1111,9 +1119,9 @@ void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRe
 
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
-                   uint32_t* need0, const NeedPlan& np, unsigned int* ray_count, cudaStream_t st)
+                   uint32_t* need0, cudaStream_t st)
 {
-    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal, pixmask, need0, np, ray_count);
+    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal, pixmask, need0);
 }
 
 // lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do
@@ -1181,10 +1189,10 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
 }
 
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
-                 const float4* link_w, const uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, cudaStream_t st)
+                 const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, cudaStream_t st)
 {
     const size_t total = (size_t)lv.sw * lv.sh * ((Dr * Dr + 31) / 32);
-    if (total) k_need<<<blocks_for(total), kBlock, 0, st>>>(lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count);
+    if (total) k_need<<<blocks_for(total), kBlock, 0, st>>>(lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count, clear ? 1 : 0);
 }
 
 void launch_march_all(const DScene& s, const DLights& L, const DLevelSet& ls, const int* levels, int n, const int* map,
@@ -1269,7 +1277,7 @@ void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* 
 }
 
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
-                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, const unsigned int* counts_in,
+                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
                    unsigned int* counts_out, cudaStream_t st)
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);

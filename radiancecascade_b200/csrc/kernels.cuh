@@ -18,8 +18,6 @@ struct MarchPlan {
     int level[RC_MAX_LEVELS], map[RC_MAX_LEVELS], top[RC_MAX_LEVELS], use_entry[RC_MAX_LEVELS];
     int n;
 };
-// request-mask layout (direction culling): level l's words start at offset[l] (in 32-bit words), words[l] per probe
-struct NeedPlan { unsigned offset[RC_MAX_LEVELS]; int words[RC_MAX_LEVELS]; };
 struct EntryPlan { unsigned group_offset[RC_MAX_LEVELS + 1]; int g[RC_MAX_LEVELS]; int n; };
 
 // pixmask != null (direction culling, DD0 = D0^2 <= 16): also stores per pixel the mask of level-0 directions
@@ -28,18 +26,18 @@ void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileR
                     const float* dirs0, uint16_t* pixmask, cudaStream_t st);
 // direction culling, level lv (bottom-up): appends the requests of `need` (bits at resolution Dr, probes of lv) to
 // `list` / `count` and pushes them to the upper level's masks `need_up` (has_upper: 0 none, 1 same resolution
-// [level 0 -> 1], 2 expanded 2x; up_words = mask words per upper probe) through k_link's tables
+// [level 0 -> 1], 2 expanded 2x; up_words = mask words per upper probe) through k_link's tables; clear: zero the
+// consumed words (levels >= 1, whose masks are accumulated with atomicOr and must be empty for the next frame)
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
-                 const float4* link_w, const uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, cudaStream_t st);
+                 const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, cudaStream_t st);
 // deferred fs_main: albedo / direct colour from the stored visibility (on demand)
 void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
                    const float2* bary, uint2* albedo, uint2* direct, cudaStream_t st);
 // all levels' probes in one launch; anchors inside the tile reuse the G-buffer hit; with pixmask (direction
-// culling) every level-0 probe also gets need0[probe] = OR of the masks of the pixels it serves, and the request
-// masks of the upper levels (need0 + np.offset[l]) and the ray-list lengths are zeroed for the frame
+// culling) every level-0 probe also gets need0[probe] = OR of the masks of the pixels it serves
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
-                   uint32_t* need0, const NeedPlan& np, unsigned int* ray_count, cudaStream_t st);
+                   uint32_t* need0, cudaStream_t st);
 // One launch, two independent jobs that only read the probe origins:
 //  link:  per lower probe (levels 0..N-2, `link_total` probes) the 4 upper probe slots (sub-grid linear) and
 //         normalised weights (w.x < 0: no valid upper probe)
@@ -78,7 +76,7 @@ void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* 
 void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st);
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
-                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, const unsigned int* counts_in,
+                   const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
                    unsigned int* counts_out, cudaStream_t st);
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
                       uchar4* composite, uchar4* direct_srgb, cudaStream_t st);

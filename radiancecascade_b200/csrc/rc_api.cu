@@ -128,6 +128,7 @@ struct rc_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     bool capturing = false;
     bool frame_culled = false;                      // the frame being recorded uses the ray lists
+    bool frame_open = false;                        // rc_render_begin without its rc_render_end (which resets the list lengths)
     bool cull_possible() const
     {
         const uint32_t D0 = (uint32_t)levels[0].D;
@@ -715,6 +716,9 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     c->lights_rendered = c->lights;
     CU_OK(c, record_event(c, c->ev[EV_START], st));
     c->frame_culled = c->cull_possible();
+    if (c->frame_open && c->frame_culled)           // the last frame never reached its gather: its list lengths are still set
+        CU_OK(c, cudaMemsetAsync(c->d_ray_count.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
+    c->frame_open = true;
     GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p};
     launch_gbuffer(c->scene, c->cam, c->lights, c->tile, gb, c->levels[0].D * c->levels[0].D, c->d_dirs.p,
                    c->frame_culled ? c->d_pixmask.p : nullptr, st);
@@ -725,13 +729,8 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     for (uint32_t i = 0; i < c->N; i++) ls.lv[i] = c->levels[i];
     const DLevel& top = c->levels[c->N - 1];
     const unsigned n_probes = top.probe_offset + (unsigned)(top.sw * top.sh);
-    NeedPlan np{};
-    for (uint32_t i = 0; i < c->N; i++) {
-        np.offset[i] = (unsigned)c->need_offset[i];
-        np.words[i] = (c->need_res[i] * c->need_res[i] + 31) / 32;
-    }
     launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p,
-                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, np, c->d_ray_count.p, st);
+                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, st);
     c->launches++;
     {
         const int ne = c->march_persist ? 0 : c->entry_levels();
@@ -750,7 +749,7 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
             launch_need(L, c->need_res[i], has_upper, (up_res * up_res + 31) / 32, c->d_origin.p + L.probe_offset,
                         c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, c->d_need.p + c->need_offset[i],
                         has_upper ? c->d_need.p + c->need_offset[i + 1] : nullptr, c->d_list.p + c->list_offset[i],
-                        c->d_ray_count.p + i, st);
+                        c->d_ray_count.p + i, i >= 1, st);
             c->launches++;
         }
     }
@@ -877,6 +876,7 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
     c->launches++;
     CU_OK(c, record_event(c, c->ev[EV_GATHER], st));
     CU_OK(c, cudaGetLastError());
+    c->frame_open = false;
     c->ev_recorded = true;
     return RC_OK;
 }
