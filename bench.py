@@ -398,6 +398,9 @@ def run_tiled(args):
     rays_local = rays_per_frame(r.levels())
     stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peer = args.exchange == "peer"
+    if peer:
+        tr.attach_peers()
 
     def step(i):
         uc, pts = frame_inputs(rc, info, W, H, i, lk)      # every rank renders the SAME view
@@ -409,7 +412,10 @@ def run_tiled(args):
             e0.record(stream)
             tr.render(state, stream.cuda_stream)
             e1.record(stream)
-            full = rd.all_gather_tiles(rd.irradiance_tensor(r), tr.tiles, W, H)
+            if peer:      # tiles were stored into every rank's frame by the gather kernel itself: only wait for the flags
+                full = tr.gather_peer(stream.cuda_stream)
+            else:
+                full = rd.all_gather_tiles(rd.irradiance_tensor(r), tr.tiles, W, H)
             e2.record(stream)
         return e0, e1, e2, full
 
@@ -431,7 +437,9 @@ def run_tiled(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "render_ms_per_step": float(tmax[1]) / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic orbit camera",
             "config": {"workload": f"{name} {W}x{H} tiled over {world} GPU(s)", "tiles": tr.tiles,
-                       "halo": "recomputed locally", "collective": "NCCL all_gather_into_tensor of RGBA16F tiles",
+                       "halo": "recomputed locally",
+                       "collective": "none: k_gather stores each tile into all ranks' frames over NVLink peer memory" if peer
+                       else "NCCL all_gather_into_tensor of RGBA16F tiles",
                        "redundant_rays": float(tsum[2]) / full_rays - 1.0, "l2": "flushed between timed steps"}}))
     dist.destroy_process_group()
     return 0
@@ -447,6 +455,8 @@ def main():
     ap.add_argument("--separate-merge", action="store_true")
     ap.add_argument("--mode", default="batch", choices=["batch", "tiled"], help="N>1: independent views per rank (default) or one tiled frame")
     ap.add_argument("--grid", default=None, help="tiled mode: NXxNY tile grid (default: horizontal strips)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="tiled mode: peer-memory stores fused into the gather kernel (default) or an NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=1,
                     help="CPU arm renders at 1/div of the resolution per axis (1 = the full workload: a 1080p frame is ~0.3 s on 16 cores)")

@@ -177,6 +177,22 @@ rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
  * marched), 0 for a top level that is constant and never materialised.  Waits for the frame to finish. */
 rc_status rc_rays_marched(rc_ctx* ctx, uint32_t* rays, uint32_t n);
 
+/* ---- Tiled multi-GPU: final-image exchange through NVLink peer memory (one context per GPU, one process each,
+ * all on one node).  Replaces the all-gather of the finished tiles: k_gather stores every pixel of this rank's tile
+ * straight into EVERY rank's full-frame buffer as it is produced, then publishes a per-rank "delivered frame n"
+ * flag; rc_peer_wait enqueues the acquire of all ranks' flags.  Two buffer slots alternate, and a rank announces
+ * that it is done with frame n when it starts frame n+1 in stream order — so consume the assembled frame on the
+ * stream you render on, before the next rc_render.
+ *   rc_peer_export  allocates this rank's buffers and returns their 64-byte CUDA IPC handle
+ *   rc_peer_attach  handles = world x 64 bytes, rank-ordered (exchange them with any host-side all-gather)
+ *   rc_peer_wait    enqueue: wait until every rank's tile of the last rendered frame has arrived here
+ *   rc_peer_frame   device pointer of the assembled W x H RGBA16F frame; timeouts (optional) = waits that gave up
+ *                   after ~2 s instead of hanging the GPU (0 in a healthy run) */
+rc_status rc_peer_export(rc_ctx* ctx, void* handle, size_t handle_bytes);
+rc_status rc_peer_attach(rc_ctx* ctx, const void* handles, uint32_t world, uint32_t rank);
+rc_status rc_peer_wait(rc_ctx* ctx, void* stream);
+rc_status rc_peer_frame(rc_ctx* ctx, void** device_ptr, size_t* bytes, uint32_t* timeouts);
+
 rc_status rc_get_levels(rc_ctx* ctx, rc_level_info* out, uint32_t max_levels, uint32_t* num_levels);
 rc_status rc_get_scene_info(rc_ctx* ctx, rc_scene_info* out);
 /* The tile this context renders: x0, y0, w, h in full-frame pixels. */

@@ -959,7 +959,8 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
                                                    const uint2* __restrict__ texels0, const float* __restrict__ dirs0,
                                                    const float* __restrict__ depth, const uint32_t* __restrict__ normal,
                                                    uint2* __restrict__ out, int max_probes,
-                                                   unsigned int* __restrict__ counts_in, unsigned int* __restrict__ counts_out)
+                                                   unsigned int* __restrict__ counts_in, unsigned int* __restrict__ counts_out,
+                                                   PeerOut peer)
 {
     extern __shared__ uint4 s_mem[];
     // last kernel of the frame: publish the ray-list lengths to (mapped, pinned) host memory — posted writes,
@@ -997,57 +998,114 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
 
     const int tx = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ty = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (tx >= tile.w || ty >= tile.h) return;
-    const size_t o = (size_t)ty * tile.w + tx;
-    const float dep = depth[o];
-    if (dep < 0.0f) { out[o] = make_uint2(0u, 0u); return; }
-    const int x = tile.x0 + tx, y = tile.y0 + ty;
-    const float3 d = primary_dir(cam, x, y);
-    const float3 hp = vfma(dep, d, cam.eye);
-    const float3 n = oct_decode(normal[o]);
-    int x0, x1, y0, y1;
-    float wx0, wx1, wy0, wy1;
-    gather_axis(x, l0.P, l0.gw, x0, x1, wx0, wx1);
-    gather_axis(y, l0.P, l0.gh, y0, y1, wy0, wy1);
-    const int lk[4] = {(y0 - rmin) * ncols + (x0 - cmin), (y0 - rmin) * ncols + (x1 - cmin),
-                       (y1 - rmin) * ncols + (x0 - cmin), (y1 - rmin) * ncols + (x1 - cmin)};
-    float w[4];
-    w[0] = (wx0 * wy0) * plane_weight(n, hp, s_org[lk[0]]);
-    w[1] = (wx1 * wy0) * plane_weight(n, hp, s_org[lk[1]]);
-    w[2] = (wx0 * wy1) * plane_weight(n, hp, s_org[lk[2]]);
-    w[3] = (wx1 * wy1) * plane_weight(n, hp, s_org[lk[3]]);
-    const float S = ((w[0] + w[1]) + w[2]) + w[3];
-    // S9: one cosine per direction, shared by the four probes; normalised quadrature q = pi / sum(cos)
-    float3 acc[4] = {f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f)};
-    float csum = 0.0f;
-#pragma unroll
-    for (int di = 0; di < DD; di += 2) {
-        const float ca = fmaxf(vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])), 0.0f);
-        const float cb = fmaxf(vdot(n, f3(s_dirs[3 * di + 3], s_dirs[3 * di + 4], s_dirs[3 * di + 5])), 0.0f);
-        csum = csum + ca;
-        csum = csum + cb;
-        // both cosines zero (about half of the directions: the lower hemisphere): fma(0, texel, acc) == acc for the
-        // finite, non-negative texels a cascade holds, so the pair is skipped — lanes of a warp are neighbouring
-        // pixels with similar normals, the branch is mostly uniform
-        if (!(ca > 0.0f || cb > 0.0f)) continue;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint4 r = s_tex[lk[k] * stride + (di >> 1)];
-            const float4 a = unpack_half4(make_uint2(r.x, r.y)), b = unpack_half4(make_uint2(r.z, r.w));
-            acc[k] = f3(fmaf(ca, a.x, acc[k].x), fmaf(ca, a.y, acc[k].y), fmaf(ca, a.z, acc[k].z));
-            acc[k] = f3(fmaf(cb, b.x, acc[k].x), fmaf(cb, b.y, acc[k].y), fmaf(cb, b.z, acc[k].z));
+    const bool inside = tx < tile.w && ty < tile.h;
+    uint2 v = make_uint2(0u, 0u);            // pixels without geometry: (0,0,0,0)
+    const size_t o = inside ? (size_t)ty * tile.w + tx : 0;
+    const float dep = inside ? depth[o] : -1.0f;
+    if (dep >= 0.0f) {
+        const int x = tile.x0 + tx, y = tile.y0 + ty;
+        const float3 d = primary_dir(cam, x, y);
+        const float3 hp = vfma(dep, d, cam.eye);
+        const float3 n = oct_decode(normal[o]);
+        int x0, x1, y0, y1;
+        float wx0, wx1, wy0, wy1;
+        gather_axis(x, l0.P, l0.gw, x0, x1, wx0, wx1);
+        gather_axis(y, l0.P, l0.gh, y0, y1, wy0, wy1);
+        const int lk[4] = {(y0 - rmin) * ncols + (x0 - cmin), (y0 - rmin) * ncols + (x1 - cmin),
+                           (y1 - rmin) * ncols + (x0 - cmin), (y1 - rmin) * ncols + (x1 - cmin)};
+        float w[4];
+        w[0] = (wx0 * wy0) * plane_weight(n, hp, s_org[lk[0]]);
+        w[1] = (wx1 * wy0) * plane_weight(n, hp, s_org[lk[1]]);
+        w[2] = (wx0 * wy1) * plane_weight(n, hp, s_org[lk[2]]);
+        w[3] = (wx1 * wy1) * plane_weight(n, hp, s_org[lk[3]]);
+        const float S = ((w[0] + w[1]) + w[2]) + w[3];
+        // S9: one cosine per direction, shared by the four probes; normalised quadrature q = pi / sum(cos)
+        float3 acc[4] = {f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f)};
+        float csum = 0.0f;
+    #pragma unroll
+        for (int di = 0; di < DD; di += 2) {
+            const float ca = fmaxf(vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])), 0.0f);
+            const float cb = fmaxf(vdot(n, f3(s_dirs[3 * di + 3], s_dirs[3 * di + 4], s_dirs[3 * di + 5])), 0.0f);
+            csum = csum + ca;
+            csum = csum + cb;
+            // both cosines zero (about half of the directions: the lower hemisphere): fma(0, texel, acc) == acc for the
+            // finite, non-negative texels a cascade holds, so the pair is skipped — lanes of a warp are neighbouring
+            // pixels with similar normals, the branch is mostly uniform
+            if (!(ca > 0.0f || cb > 0.0f)) continue;
+    #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint4 r = s_tex[lk[k] * stride + (di >> 1)];
+                const float4 a = unpack_half4(make_uint2(r.x, r.y)), b = unpack_half4(make_uint2(r.z, r.w));
+                acc[k] = f3(fmaf(ca, a.x, acc[k].x), fmaf(ca, a.y, acc[k].y), fmaf(ca, a.z, acc[k].z));
+                acc[k] = f3(fmaf(cb, b.x, acc[k].x), fmaf(cb, b.y, acc[k].y), fmaf(cb, b.z, acc[k].z));
+            }
+        }
+        float3 E = f3(0.f, 0.f, 0.f);
+        if (S > 0.0f) {
+            const float q = csum > 0.0f ? RC_PI_F / csum : 0.0f;
+    #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float wd = (w[k] / S) * q;
+                E = f3(fmaf(wd, acc[k].x, E.x), fmaf(wd, acc[k].y, E.y), fmaf(wd, acc[k].z, E.z));
+            }
+        }
+        v = pack_half4(fminf(E.x, 65504.0f), fminf(E.y, 65504.0f), fminf(E.z, 65504.0f), 1.0f);
+    }
+    if (inside) out[o] = v;
+    if (peer.world) {
+        // Fused final-image all-gather: the tile is stored straight into every rank's full-frame
+        // buffer through NVLink peer mappings, as it is produced (plain stores, nothing waits for them here).
+        // k_peer_publish, the next kernel in the stream, raises the "delivered" flags once this grid has retired.
+        if (inside) {
+            const size_t fo = (size_t)(tile.y0 + ty) * peer.W + (tile.x0 + tx);
+            for (int d = 0; d < peer.world; d++) peer.frame[d][fo] = v;
         }
     }
-    float3 E = f3(0.f, 0.f, 0.f);
-    if (S > 0.0f) {
-        const float q = csum > 0.0f ? RC_PI_F / csum : 0.0f;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float wd = (w[k] / S) * q;
-            E = f3(fmaf(wd, acc[k].x, E.x), fmaf(wd, acc[k].y, E.y), fmaf(wd, acc[k].z, E.z));
-        }
+}
+
+// ------------------------------------------------------------------ peer-memory frame exchange (tiled multi-GPU)
+// Control block of a rank (uint32 words, in its IPC-shared allocation): [kPeerArrived + r] = last frame rank r has
+// delivered into THIS rank's frame buffers; [kPeerReleased + r] = last frame rank r has finished consuming (so that
+// its buffer slot may be overwritten); [kPeerError] = number of timed-out waits.  Frames alternate between two
+// buffer slots, so a producer may run at most one frame ahead of the slowest consumer.
+__device__ __forceinline__ bool peer_spin(volatile uint32_t* flag, uint32_t want)
+{
+    const long long t0 = clock64();
+    while ((int)(*flag - want) < 0) {
+        if (clock64() - t0 > 4000000000ll) return false;   // ~2 s: never hang the GPU on a lost peer
+        __nanosleep(200);
     }
-    out[o] = pack_half4(fminf(E.x, 65504.0f), fminf(E.y, 65504.0f), fminf(E.z, 65504.0f), 1.0f);
+    return true;
+}
+
+// before this rank's gather of frame `seq`: tell every rank that this rank is done reading frame seq-1 (stream
+// order guarantees it), then wait until every rank has released frame seq-2, whose slot frame `seq` overwrites
+__global__ void k_peer_begin(PeerOut peer, uint32_t* my_ctrl)
+{
+    const int r = threadIdx.x;
+    if (r >= peer.world) return;
+    __threadfence_system();
+    *((volatile uint32_t*)(peer.ctrl[r] + kPeerReleased + peer.rank)) = peer.seq - 1u;
+    if (peer.seq >= 2u && !peer_spin(my_ctrl + kPeerReleased + r, peer.seq - 2u)) atomicAdd(my_ctrl + kPeerError, 1u);
+}
+
+// after this rank's gather of frame `seq` (a kernel boundary: all of its peer stores have been performed): tell
+// every rank that this rank's tile has been delivered
+__global__ void k_peer_publish(PeerOut peer)
+{
+    const int r = threadIdx.x;
+    if (r >= peer.world) return;
+    __threadfence_system();
+    *((volatile uint32_t*)(peer.ctrl[r] + kPeerArrived + peer.rank)) = peer.seq;
+}
+
+// consumer side: every rank's tile of frame `seq` has landed in this rank's frame buffer
+__global__ void k_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl)
+{
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    if (!peer_spin(my_ctrl + kPeerArrived + r, seq)) atomicAdd(my_ctrl + kPeerError, 1u);
+    __threadfence_system();
 }
 
 // ------------------------------------------------------------------ display composite (outside the hot path)
@@ -1278,14 +1336,14 @@ void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* 
 
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
                    const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
-                   unsigned int* counts_out, cudaStream_t st)
+                   unsigned int* counts_out, const PeerOut& peer, cudaStream_t st)
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
     const int DD = l0.D * l0.D;
     const int max_probes = ((32 + l0.P - 1) / l0.P + 2) * ((8 + l0.P - 1) / l0.P + 2);
     const size_t smem = (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
     if (DD == 16) {
-        k_gather<16><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out);
+        k_gather<16><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out, peer);
         return;
     }
     static size_t configured = 0;
@@ -1293,8 +1351,12 @@ void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const fl
         cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    k_gather<0><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out);
+    k_gather<0><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out, peer);
 }
+
+void launch_peer_begin(const PeerOut& peer, uint32_t* my_ctrl, cudaStream_t st) { k_peer_begin<<<1, 32, 0, st>>>(peer, my_ctrl); }
+void launch_peer_publish(const PeerOut& peer, cudaStream_t st) { k_peer_publish<<<1, 32, 0, st>>>(peer); }
+void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t st) { k_peer_wait<<<1, 32, 0, st>>>(world, seq, my_ctrl); }
 
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
                       uchar4* composite, uchar4* direct_srgb, cudaStream_t st)

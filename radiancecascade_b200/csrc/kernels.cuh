@@ -18,6 +18,16 @@ struct MarchPlan {
     int level[RC_MAX_LEVELS], map[RC_MAX_LEVELS], top[RC_MAX_LEVELS], use_entry[RC_MAX_LEVELS];
     int n;
 };
+// Peer-memory exchange of the finished tiles (tiled multi-GPU): every rank's k_gather stores its tile into all
+// ranks' full-frame buffers over NVLink.  world == 0: disabled.
+constexpr int kMaxPeers = 8;
+enum { kPeerArrived = 0, kPeerReleased = kMaxPeers, kPeerError = 2 * kMaxPeers, kPeerCtrlWords = 2 * kMaxPeers + 8 };
+struct PeerOut {
+    uint2* frame[kMaxPeers];       // rank d's full-frame buffer (this frame's slot), W x H RGBA16F
+    uint32_t* ctrl[kMaxPeers];     // rank d's control block
+    int world, rank, W;
+    uint32_t seq;                  // frame number, from 1
+};
 struct EntryPlan { unsigned group_offset[RC_MAX_LEVELS + 1]; int g[RC_MAX_LEVELS]; int n; };
 
 // pixmask != null (direction culling, DD0 = D0^2 <= 16): also stores per pixel the mask of level-0 directions
@@ -77,7 +87,10 @@ void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* 
                   const uint4* link_idx, const float4* link_w, cudaStream_t st);
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
                    const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
-                   unsigned int* counts_out, cudaStream_t st);
+                   unsigned int* counts_out, const PeerOut& peer, cudaStream_t st);
+void launch_peer_begin(const PeerOut& peer, uint32_t* my_ctrl, cudaStream_t st);
+void launch_peer_publish(const PeerOut& peer, cudaStream_t st);
+void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t st);
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
                       uchar4* composite, uchar4* direct_srgb, cudaStream_t st);
 void launch_trace_rays(const DScene& s, const float* rays, uint32_t n, float* hits, cudaStream_t st);

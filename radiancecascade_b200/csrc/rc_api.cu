@@ -125,6 +125,17 @@ struct rc_ctx {
     // cudaGraphLaunch; every frame is re-captured and the executable graph updated in place
     // (cudaGraphExecUpdate: camera, lights, grid sizes and the output slot are node parameters).
     int use_graph = 1;
+    // tiled multi-GPU: every rank's gather stores its tile into all ranks' full-frame buffers over NVLink peer
+    // mappings (rc_peer_export / rc_peer_attach); two slots per rank + a control block, one cudaMalloc shared by IPC
+    struct Peer {
+        int world = 0, rank = 0;
+        void* local = nullptr;                  // this rank's shared allocation
+        void* base[kMaxPeers] = {};             // every rank's allocation as mapped here (base[rank] == local)
+        size_t slot_bytes = 0;
+        uint32_t seq = 0;                       // frames delivered so far
+        uint2* frame(int r, uint32_t q) const { return (uint2*)((char*)base[r] + (q & 1u) * slot_bytes); }
+        uint32_t* ctrl(int r) const { return (uint32_t*)((char*)base[r] + 2 * slot_bytes); }
+    } peer;
     cudaGraphExec_t graph_exec = nullptr;
     bool capturing = false;
     bool frame_culled = false;                      // the frame being recorded uses the ray lists
@@ -569,6 +580,16 @@ rc_status scene_model_stream(const rc_scene& s, std::string& error, uint32_t mod
     return RC_OK;
 }
 
+void peer_release(rc_ctx* c)
+{
+    rc_ctx::Peer& p = c->peer;
+    for (int r = 0; r < p.world; r++)
+        if (r != p.rank && p.base[r]) cudaIpcCloseMemHandle(p.base[r]);
+    if (p.local) cudaFree(p.local);
+    p = rc_ctx::Peer();
+}
+
+
 void destroy_ctx(rc_ctx* c)
 {
     if (!c) return;
@@ -580,7 +601,8 @@ void destroy_ctx(rc_ctx* c)
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
     c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release(); c->d_need.release(); c->d_list.release(); c->d_pixmask.release();
     if (c->h_ray_count) cudaFreeHost(c->h_ray_count);
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec); c->d_ray_count.release();
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    peer_release(c); c->d_ray_count.release();
     c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -871,9 +893,21 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
         if (s != RC_OK) return s;
     }
     const DLevel& L0 = c->levels[0];
+    PeerOut po{};
+    if (c->peer.world) {
+        c->peer.seq++;
+        po.world = c->peer.world; po.rank = c->peer.rank; po.W = (int)c->W; po.seq = c->peer.seq;
+        for (int r = 0; r < c->peer.world; r++) { po.frame[r] = c->peer.frame(r, c->peer.seq); po.ctrl[r] = c->peer.ctrl(r); }
+        launch_peer_begin(po, c->peer.ctrl(c->peer.rank), st);
+        c->launches++;
+    }
     launch_gather(c->cam, L0, c->tile, c->d_origin.p + L0.probe_offset, c->d_cascade.p + L0.texel_offset, c->d_dirs.p,
-                  c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, st);
+                  c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, po, st);
     c->launches++;
+    if (c->peer.world) {
+        launch_peer_publish(po, st);
+        c->launches++;
+    }
     CU_OK(c, record_event(c, c->ev[EV_GATHER], st));
     CU_OK(c, cudaGetLastError());
     c->frame_open = false;
@@ -1125,6 +1159,67 @@ rc_status rc_launch_count(rc_ctx* c, uint32_t* launches)
 {
     if (!c || !launches) return RC_ERR_INVALID_ARG;
     *launches = c->launches;
+    return RC_OK;
+}
+
+// ---- peer-memory frame exchange (tiled multi-GPU; kernels.cu k_gather / k_peer_*)
+rc_status rc_peer_export(rc_ctx* c, void* handle, size_t handle_bytes)
+{
+    if (!c || !handle) return RC_ERR_INVALID_ARG;
+    if (handle_bytes < sizeof(cudaIpcMemHandle_t)) { c->error = "rc_peer_export: handle buffer smaller than 64 bytes"; return RC_ERR_BUFFER_SIZE; }
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    peer_release(c);
+    rc_ctx::Peer& p = c->peer;
+    p.slot_bytes = (((size_t)c->W * c->H * sizeof(uint2)) + 255) & ~(size_t)255;
+    const size_t bytes = 2 * p.slot_bytes + kPeerCtrlWords * sizeof(uint32_t);
+    CU_OK(c, cudaMalloc(&p.local, bytes));
+    CU_OK(c, cudaMemset(p.local, 0, bytes));
+    cudaIpcMemHandle_t h;
+    CU_OK(c, cudaIpcGetMemHandle(&h, p.local));
+    memcpy(handle, &h, sizeof(h));
+    return RC_OK;
+}
+
+rc_status rc_peer_attach(rc_ctx* c, const void* handles, uint32_t world, uint32_t rank)
+{
+    if (!c || !handles || world < 1 || world > (uint32_t)kMaxPeers || rank >= world) return RC_ERR_INVALID_ARG;
+    if (!c->peer.local) { c->error = "rc_peer_attach before rc_peer_export"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    rc_ctx::Peer& p = c->peer;
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == rank) { p.base[r] = p.local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + r * sizeof(h), sizeof(h));
+        CU_OK(c, cudaIpcOpenMemHandle(&p.base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    p.rank = (int)rank;
+    p.world = (int)world;     // from the next rc_render on, k_gather also stores into every rank's frame buffer
+    p.seq = 0;
+    return RC_OK;
+}
+
+rc_status rc_peer_wait(rc_ctx* c, void* stream)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    if (!c->peer.world || !c->peer.seq) { c->error = "rc_peer_wait: no frame has been rendered with peers attached"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    launch_peer_wait(c->peer.world, c->peer.seq, c->peer.ctrl(c->peer.rank), st);
+    CU_OK(c, cudaGetLastError());
+    return RC_OK;
+}
+
+rc_status rc_peer_frame(rc_ctx* c, void** device_ptr, size_t* bytes, uint32_t* timeouts)
+{
+    if (!c || !device_ptr) return RC_ERR_INVALID_ARG;
+    if (!c->peer.world) { c->error = "rc_peer_frame: peers not attached"; return RC_ERR_STATE; }
+    *device_ptr = c->peer.frame(c->peer.rank, c->peer.seq);
+    if (bytes) *bytes = (size_t)c->W * c->H * sizeof(uint2);
+    if (timeouts) {
+        cudaSetDevice(c->device);
+        CU_OK(c, cudaMemcpy(timeouts, c->peer.ctrl(c->peer.rank) + kPeerError, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
     return RC_OK;
 }
 

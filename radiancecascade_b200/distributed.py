@@ -149,6 +149,27 @@ class TiledRenderer:
         self.renderer.update(state)
         self.renderer.render(stream)
 
+    def attach_peers(self, group=None):
+        """Exchange CUDA IPC handles (host-side all-gather of 64-byte blobs) and map every rank's frame buffers:
+        from the next render on, the gather kernel stores this rank's tile into all ranks' frames over NVLink."""
+        import torch.distributed as dist
+        mine = self.renderer.peer_export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        self.renderer.peer_attach(handles, self.rank)
+        dist.barrier(group=group)       # nobody renders before everybody has mapped everybody
+        self.peers = True
+
+    def gather_peer(self, stream: Optional[int] = None):
+        """Fused path: enqueue the wait for all ranks' tiles of the last frame and return the assembled frame
+        (torch view of this rank's peer buffer, float16 [H][W][4]); consume it on `stream` before the next render."""
+        import torch
+        self.renderer.peer_wait(stream)
+        ptr, nbytes, _ = self.renderer.peer_frame()
+        W, H = self.size
+        assert nbytes == W * H * 8
+        return torch.as_tensor(_DevicePtr(ptr, (H, W, 4), "<f2"), device="cuda")
+
     def gather(self, group=None):
         """NCCL all-gather of the finished tiles; returns the full frame (torch, cuda, float16)."""
         self.renderer.synchronize()

@@ -281,6 +281,25 @@ class DefaultRenderer:
     def set_tuning(self, key: str, value: int) -> None:
         self._check(self._lib.rc_set_tuning(self._h, key.encode(), int(value)))
 
+    # ---- tiled multi-GPU: final-image exchange through NVLink peer memory (include/rc_b200.h rc_peer_*)
+    def peer_export(self) -> bytes:
+        h = C.create_string_buffer(64)
+        self._check(self._lib.rc_peer_export(self._h, h, 64))
+        return h.raw
+
+    def peer_attach(self, handles: List[bytes], rank: int) -> None:
+        blob = C.create_string_buffer(b"".join(handles), 64 * len(handles))
+        self._check(self._lib.rc_peer_attach(self._h, blob, len(handles), rank))
+
+    def peer_wait(self, stream: Optional[int] = None) -> None:
+        self._check(self._lib.rc_peer_wait(self._h, C.c_void_p(stream) if stream else None))
+
+    def peer_frame(self, check: bool = False) -> Tuple[int, int, int]:
+        """(device pointer, bytes, timed-out waits) of the assembled full frame."""
+        p, n, t = C.c_void_p(), C.c_size_t(), C.c_uint32(0)
+        self._check(self._lib.rc_peer_frame(self._h, C.byref(p), C.byref(n), C.byref(t) if check else None))
+        return int(p.value), int(n.value), int(t.value)
+
     def rays_marched(self) -> List[Optional[int]]:
         """Texels each level of the last frame actually marched (None: the level was not culled)."""
         n = len(self.levels())

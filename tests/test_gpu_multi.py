@@ -1,4 +1,5 @@
-"""Tiled multi-GPU frame over NCCL: needs >= 2 CUDA devices."""
+"""Tiled multi-GPU frame, exchanged by an NCCL all-gather and by the peer-memory stores fused into
+the gather kernel: needs >= 2 CUDA devices."""
 import os
 import socket
 
@@ -21,11 +22,24 @@ def _worker(rank, world, port, W, H, q):
     tr = rd.TiledRenderer(rank, world, rank, (W, H), st, rc.scenes.scene_path("teapot"))
     tr.render(st)
     full = tr.gather()
+    ok = True
+    want = None
     if rank == 0:
         ref = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path("teapot"))
         ref.update(st); ref.render()
         want = ref.read_target(_ffi.RC_TARGET_IRRADIANCE)
-        q.put(bool(np.array_equal(full.cpu().numpy().view(np.uint16), want.view(np.uint16))))
+        ok = bool(np.array_equal(full.cpu().numpy().view(np.uint16), want.view(np.uint16)))
+    # the same frame through the peer-memory exchange fused into the gather kernel (no collective): three frames,
+    # so that both buffer slots and the release / arrive handshake are exercised
+    tr.attach_peers()
+    for _ in range(3):
+        tr.render(st)
+        peer_full = tr.gather_peer().clone()
+    torch.cuda.synchronize()
+    _, _, timeouts = tr.renderer.peer_frame(check=True)
+    if rank == 0:
+        ok = ok and timeouts == 0 and bool(np.array_equal(peer_full.cpu().numpy().view(np.uint16), want.view(np.uint16)))
+        q.put(ok)
     dist.barrier()
     dist.destroy_process_group()
 

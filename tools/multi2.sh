@@ -1,0 +1,4 @@
+python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -15
+for ex in nccl peer; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --mode tiled --exchange $ex --steps 20 --warmup 3 2>&1 | tail -2 | cut -c1-700
+done
