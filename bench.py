@@ -320,12 +320,13 @@ def run_product(args):
                 "achieved": march_bytes_per_launch / (avg_march_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": march_bytes_per_launch,
                 "avg_launch_ms": avg_march_launch_ms}
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if wl == "teapot_1080p" and os.path.exists(tpath):      # dram bytes per launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r1_g_traffic.json")
+        if os.path.exists(tpath):      # dram bytes per launch from the committed ncu --set full capture of this workload
             with open(tpath) as fh:
                 tj = json.load(fh)
-            roof["traffic"] = tj["k_march_dram_bytes_per_launch"]
-            roof["traffic_source"] = tj["source"]
+            if wl in tj:
+                roof["traffic"] = tj[wl]["k_march_dram_bytes_per_launch"]
+                roof["traffic_source"] = tj["source"].replace("<workload>", wl)
         roof["frac"] = roof["achieved"] / peak
         gather = {"kernel": "k_gather", "bound": "hbm", "achieved": gather_bytes / (st_mean["gather"] * 1e-3) / 1e9, "peak": peak,
                   "unit": "GB/s", "bytes": gather_bytes}

@@ -64,7 +64,8 @@ static bool decode_png(const std::vector<uint8_t>& f, Image& img, std::string* w
     if (!w || !h || interlace) { if (why) *why = "unsupported PNG (interlaced or empty)"; return false; }
     int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!channels || (depth != 1 && depth != 2 && depth != 4 && depth != 8 && depth != 16)) {
-        if (why) *why = "unsupported PNG colour type"; return false;
+        if (why) *why = "unsupported PNG colour type";
+        return false;
     }
     size_t bpp_bits = (size_t)channels * depth;
     size_t stride = (w * bpp_bits + 7) / 8;
@@ -72,7 +73,8 @@ static bool decode_png(const std::vector<uint8_t>& f, Image& img, std::string* w
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf dlen = (uLongf)raw.size();
     if (uncompress(raw.data(), &dlen, idat.data(), (uLong)idat.size()) != Z_OK || dlen != raw.size()) {
-        if (why) *why = "PNG inflate failed"; return false;
+        if (why) *why = "PNG inflate failed";
+        return false;
     }
     std::vector<uint8_t> cur(stride), prev(stride, 0);
     img.width = w; img.height = h;

@@ -1,19 +1,21 @@
 // kernels.cu — hand-written CUDA kernels of the radiance-cascade GI path for sm_100a.
 //
-//   k_gbuffer   primary visibility + fs_main per pixel            (rc_spec.h S4, src/shader.wgsl:76-100)
-//   k_probes    probe placement per cascade level                 (S6)
-//   k_link_entry per-probe upper-probe slots and bilateral weights (S1, S8) + per-probe BVH entry frontiers
-//   k_march     per-level interval ray march, optionally fused with the merge from level i+1 (S7, S8)
-//   k_merge     stand-alone merge (A/B against the fused path)    (S8)
-//   k_gather    final irradiance gather                           (S9)
+//   k_gbuffer    primary visibility + shading normal per pixel (+ per-pixel direction masks)   (rc_spec.h S4, src/shader.wgsl:76-100)
+//   k_direct     deferred fs_main (albedo / direct colour), on demand                           (src/shader.wgsl:76-100)
+//   k_probes     probe placement for all cascade levels (+ level-0 request masks)              (S6)
+//   k_link_entry per-probe upper-probe slots and bilateral weights (S1, S8) + optional per-probe BVH entry frontiers
+//   k_need       direction culling: request masks pushed up the cascade, one ray list per level
+//   k_march      per-level interval ray march fused with the merge from level i+1 and with the child
+//                averages the level below will read (S7, S8); list-driven in culled frames
+//   k_merge / k_child_avg / k_fill_top / k_march_all / k_march_persist / k_march_compact   A/B variants and the
+//                every-texel path (rc_set_tuning)
+//   k_gather     final irradiance gather (+ peer-memory stores of the tile in tiled multi-GPU mode)   (S9)
+//   k_peer_*     flag handshake of the peer-memory frame exchange
 //
-// Data layout (all in HBM, sized at rc_create): cascade levels are probe-major
-// RGBA16F texels (8 B) so that one warp marches 32 directions of ONE probe
-// (shared origin -> coherent BVH traversal) and stores 256 contiguous bytes;
-// the merge reads, per lower texel, 4 upper probes x 2 rows x 16 B (two adjacent
-// child directions per 128-bit load).  None of these stages is a dense
-// contraction, so tensor cores / TMEM are not used; the BVH + triangles (< 4 MB)
-// live in L2 (126 MB) and are read through the read-only path.
+// Data layout (all in HBM, sized at rc_create): cascade levels are probe-major RGBA16F texels (8 B): one warp
+// marches directions of ONE probe (shared origin -> coherent BVH traversal); the merge reads, per lower texel,
+// 4 upper probes x one 16-byte child average.  None of these stages is a dense contraction, so tensor cores /
+// TMEM are not used; the BVH + triangles (< 4 MB) live in L2 (126 MB) and are read through the read-only path.
 #include "kernels.cuh"
 
 namespace rc {
@@ -22,13 +24,19 @@ namespace {
 
 constexpr int kBlock = 256;
 
-__device__ __forceinline__ uint4 ldg_u4(const uint4* p) { return __ldg(p); }
 // Plain (coherent, L1-allocating) 128-bit load: the merged upper level is written by the previous
 // kernel of the PDL chain while this kernel may already be running, so the non-coherent .nc path is not used for it.
 __device__ __forceinline__ uint4 ld_u4(const void* p)
 {
     uint4 r;
     asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float4 ld_f4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
 
@@ -496,7 +504,7 @@ __device__ __forceinline__ float4 far_field(const float4* __restrict__ up_avg, i
     for (int k = 0; k < 4; k++) {
         float4 a;
         if (up_const) a = __ldg(up_avg + idx[k]).w != 0.0f ? skyh : make_float4(0.f, 0.f, 0.f, 1.f);
-        else a = __ldg(up_avg + idx[k] * DD + off);
+        else a = ld_f4(up_avg + idx[k] * DD + off);   // coherent: written by the PDL predecessor (see ld_u4)
         far.x = fmaf(wk[k], a.x, far.x);
         far.y = fmaf(wk[k], a.y, far.y);
         far.z = fmaf(wk[k], a.z, far.z);
