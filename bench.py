@@ -300,6 +300,18 @@ def run_product(args):
             lv.append(r.level_times())
         lv_mean = [float(np.mean([x[i] for x in lv])) for i in range(len(levels))]
         r.set_tuning("level_timing", 0)
+    # the same frames with direction culling switched off: every texel of every level is marched (the exhaustive
+    # evaluation the CPU arm performs).  Reported next to the headline so that both readings of "ray samples/s" are on
+    # the line: `value` = nominal cascade texels / frame time of the product path, `all_rays.value` = marched == nominal.
+    r.set_tuning("cull", 0)
+    device_loop(3, None)
+    torch.cuda.synchronize()
+    nocull_ms = float(sum(device_loop(args.steps, None))) / args.steps
+    if dist:
+        t = torch.tensor([nocull_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nocull_ms = float(t.item())
+    r.set_tuning("cull", 1)
     e2e_value = world * rays / (e2e_ms / args.steps * 1e-3) / 1e9
     n_lights = 1 + len(state.extra_lights)
 
@@ -334,6 +346,8 @@ def run_product(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "value_marched": world * traced / (ms_per_step * 1e-3) / 1e9,
+            "all_rays": {"value": world * rays / (nocull_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": nocull_ms,
+                         "note": "direction culling off (rc_set_tuning cull 0): every texel of every level marched; irradiance bit-identical"},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic orbit camera over the reference's bundled scene (scenes/%s.zip)" % name,
             "config": {"workload": f"{name} {W}x{H}, {n_lights} light(s), full cascade stack", "levels": len(levels),

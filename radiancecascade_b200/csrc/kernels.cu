@@ -59,15 +59,17 @@ __device__ __forceinline__ void gather_axis(int coord, int P, int gmax, int& i0,
 {
     const int s = coord - P / 2;
     int base, rem;
+    float f;
     if ((P & (P - 1)) == 0) {           // power-of-two spacing: arithmetic shift == floor division
         const int lp = 31 - __clz(P);
         base = s >> lp;
         rem = s & (P - 1);
+        f = (float)rem * __int_as_float((127 - lp) << 23);   // rem * 2^-lp == rem / P exactly: no IEEE division
     } else {
         base = (s >= 0) ? s / P : -((-s + P - 1) / P);
         rem = s - base * P;
+        f = (float)rem / (float)P;
     }
-    const float f = (float)rem / (float)P;
     i0 = min(max(base, 0), gmax - 1);
     i1 = min(max(base + 1, 0), gmax - 1);
     w0 = 1.0f - f; w1 = f;
@@ -623,7 +625,7 @@ __device__ __forceinline__ uint2 finalize_texel(const DScene& s, const DLights& 
 // loads per warp), so occupancy is traded against spills and measured.
 template <bool FUSED, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel lv, int UD, int top, float3 sky, int map, size_t total,
-                                                  const float4* __restrict__ origin, const float* __restrict__ dirs,
+                                                  const float4* __restrict__ origin, const float4* __restrict__ dirq,
                                                   uint2* __restrict__ texels, const float4* __restrict__ up_avg,
                                                   const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
                                                   const int4* __restrict__ entry, float4* __restrict__ avg_out, int ystep,
@@ -664,9 +666,11 @@ __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel
         if (in_range) {
             const float4 og = __ldg(origin + probe);
             if (og.w != 0.0f) {
-                const float3 w = f3(__ldg(dirs + 3 * d), __ldg(dirs + 3 * d + 1), __ldg(dirs + 3 * d + 2));
+                // direction and its slab reciprocals from the level's table (divided once on the host, same IEEE expression)
+                const float4 qa = __ldg(dirq + 2 * (size_t)d), qb = __ldg(dirq + 2 * (size_t)d + 1);
+                const float3 w = xyz(qa);
                 const float3 o = xyz(og);
-                const Hit h = trace(s, o, w, lv.t0, lv.t1, entry ? entry + 2 * (size_t)probe : nullptr);
+                const Hit h = trace_inv(s, o, w, f3(qa.w, qb.x, qb.y), lv.t0, lv.t1, entry ? entry + 2 * (size_t)probe : nullptr);
                 t = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_avg, link_idx, link_w);
             }
             texels[(size_t)probe * DD + d] = t;
@@ -1218,7 +1222,7 @@ void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total
 }
 
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
-                  const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
+                  const float4* origin, const float* dirs, const float4* dirq, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ, bool pdl,
                   bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const, cudaStream_t st)
 {
@@ -1244,7 +1248,7 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     cfg.numAttrs = (pdl && fused && !top) ? 1 : 0;   // only a kernel that waits on its predecessor may start early
 #define RC_LAUNCH_MARCH(F, M, T)                                                                                              \
     (compact ? cudaLaunchKernelEx(&cfg, k_march_compact<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_avg, link_idx, link_w) \
-             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirs, texels, up_avg, link_idx, link_w, entry, avg_out, ystep, list, count, quad))
+             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirq, texels, up_avg, link_idx, link_w, entry, avg_out, ystep, list, count, quad))
     const bool f = fused && !top;
     const int t = f ? 0 : topi;
     if (occ >= 16) { if (f) RC_LAUNCH_MARCH(true, 16, t); else RC_LAUNCH_MARCH(false, 16, t); }

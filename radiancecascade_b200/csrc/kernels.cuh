@@ -62,8 +62,10 @@ void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total
 // list / count (direction culling): march only the requested texels (quad = 0, level 0) or 2x2 quads (quad = 1)
 // listed by launch_need; avg_out is then always honoured.  up_const: the upper level is an unmaterialised top
 // level that cannot hit anything — up_avg then holds the top probes' origins (far_field)
+// dirs: this level's direction table (the compacting variant reads it); dirq: the same directions with their slab
+// reciprocals, 2 x float4 per direction: (w, 1/w.x), (1/w.y, 1/w.z, 0, 0) — what k_march reads
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
-                  const float4* origin, const float* dirs, uint2* texels, const float4* up_avg,
+                  const float4* origin, const float* dirs, const float4* dirq, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ,
                   bool pdl, bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const,
                   cudaStream_t st);

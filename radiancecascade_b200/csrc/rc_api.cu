@@ -147,6 +147,9 @@ struct rc_ctx {
                D0 * D0 <= 16 && (D0 & (D0 - 1)) == 0;
     }
     DevBuf<float> d_dirs;
+    // per direction (w.xyz, 1/w.x), (1/w.y, 1/w.z, 0, 0): the slab-test reciprocals of S5 depend on the direction only,
+    // so they are divided once here (IEEE, the same safe_inv expression) instead of three times per ray in k_march
+    DevBuf<float4> d_dirq;
     DevBuf<float> d_depth;
     DevBuf<uint32_t> d_prim, d_nrm;
     DevBuf<uint2> d_albedo, d_direct, d_irr, d_irr2;   // irradiance is double-buffered for rc_read_target_async
@@ -389,6 +392,16 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
     if (!c->h_ray_count) CU_OK(c, cudaHostAlloc((void**)&c->h_ray_count, RC_MAX_LEVELS * sizeof(unsigned int), cudaHostAllocMapped));
     for (uint32_t i = 0; i < RC_MAX_LEVELS; i++) c->h_ray_count[i] = 0xffffffffu;
     CU_OK(c, c->d_dirs.upload(all_dirs));
+    {
+        std::vector<float4> q(2 * (all_dirs.size() / 3));
+        auto safe_inv = [](float d) { return 1.0f / (std::fabs(d) > 1e-20f ? d : std::copysign(1e-20f, d)); };   // rc_device.cuh safe_inv
+        for (size_t k = 0; k < all_dirs.size() / 3; k++) {
+            const float x = all_dirs[3 * k], y = all_dirs[3 * k + 1], z = all_dirs[3 * k + 2];
+            q[2 * k] = make_float4(x, y, z, safe_inv(x));
+            q[2 * k + 1] = make_float4(safe_inv(y), safe_inv(z), 0.f, 0.f);
+        }
+        CU_OK(c, c->d_dirq.upload(q));
+    }
     CU_OK(c, c->d_depth.alloc(npx));
     CU_OK(c, c->d_prim.alloc(npx));
     CU_OK(c, c->d_nrm.alloc(npx));
@@ -454,6 +467,7 @@ rc_status load_host_scene(const std::string& scene_path, uint32_t flags, rc_scen
             dm.ke[0] = mat->emission.x; dm.ke[1] = mat->emission.y; dm.ke[2] = mat->emission.z;
         }
         dm.ebit = (uint32_t)(dm.tex_c >= 0) | ((uint32_t)(dm.tex_n >= 0) << 1);   // src/renderer.rs:422-423
+        fill_material_constants(dm);
         mats.push_back(dm);
         memcpy(hm.material80, &um, 64);
         memcpy(&hm.material80[16], &dm.ebit, 4);
@@ -603,7 +617,7 @@ void destroy_ctx(rc_ctx* c)
     if (c->h_ray_count) cudaFreeHost(c->h_ray_count);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     peer_release(c); c->d_ray_count.release();
-    c->d_dirs.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
+    c->d_dirs.release(); c->d_dirq.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_frame_done) cudaEventDestroy(c->ev_frame_done);
@@ -827,7 +841,8 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
                              c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_thresh,
                              c->march_grid, c->d_counters.p + level, c->march_pdl && fused && !top, st);
     else
-        launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
+        launch_march(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level],
+                     c->d_dirq.p + 2 * (c->dir_offset[level] / 3), tex, up,
                      c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset,
                      (int)level < c->entry_levels() ? c->d_entry.p + 2 * (size_t)L.probe_offset : nullptr,
                      avg_in_kernel ? my_avg : nullptr, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, compact,

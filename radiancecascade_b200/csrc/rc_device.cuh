@@ -11,12 +11,19 @@
 namespace rc {
 
 // ------------------------------------------------------------------ layout in HBM
-struct DMaterial {          // 80 bytes: UniformMaterial (src/primitives.rs:37-46) + GI extras
+struct DMaterial {          // UniformMaterial (src/primitives.rs:37-46) + GI extras + per-material constants of fs_main
     float ka[4], kd[4], ks[4];
     float ns;
     uint32_t ebit;          // enable_bit (src/renderer.rs:422-423)
     int32_t tex_c, tex_n;   // texture ids or -1 (Texture::empty)
     float ke[4];
+    // terms of fs_main that depend on the material only, evaluated once on the host with the very expressions
+    // shade_hit used to evaluate per hit (f32, no contraction): ambient Ka*0.05*Ka.w (:82-83), the "unlit" selector
+    // (:99-100) and whether the specular chain can contribute at all
+    float amb[3];
+    float unlit;            // 1.0 or 0.0
+    uint32_t spec;          // (Ks present and non-zero) or Ns < 0 / NaN
+    uint32_t pad[3];
 };
 
 struct DTexture { uint64_t offset; uint32_t w, h; };
@@ -50,6 +57,18 @@ struct DLevel {
 };
 
 struct DLevelSet { DLevel lv[RC_MAX_LEVELS]; int n; };
+
+// Host side of the per-material constants (called once per material at scene load; plain f32, no contraction —
+// the expressions are the ones fs_main spells out, src/shader.wgsl:82-83, 97-100).
+inline void fill_material_constants(DMaterial& m)
+{
+    for (int k = 0; k < 3; k++) m.amb[k] = m.ka[k] * 0.05f * m.ka[3];
+    const float pred = ((m.ka[0] - 1e-5f) + (m.kd[0] - 1e-5f) + (m.ks[0] - 1e-5f))
+                     + ((m.ka[1] - 1e-5f) + (m.kd[1] - 1e-5f) + (m.ks[1] - 1e-5f))
+                     + ((m.ka[2] - 1e-5f) + (m.kd[2] - 1e-5f) + (m.ks[2] - 1e-5f));                   // :99
+    m.unlit = pred <= 0.0f ? 1.0f : 0.0f;
+    m.spec = ((m.ks[3] != 0.0f && (m.ks[0] != 0.0f || m.ks[1] != 0.0f || m.ks[2] != 0.0f)) || !(m.ns >= 0.0f)) ? 1u : 0u;
+}
 
 // ------------------------------------------------------------------ spec arithmetic
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
@@ -114,10 +133,12 @@ __device__ __forceinline__ void tri_test(const float4* __restrict__ g, float3 o,
 constexpr int RC_ENTRY_SLOTS = 8;
 constexpr int kDoneLinkC = (int)0x80000000;
 
-__device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float tmin, float tmax, const int4* __restrict__ entry = nullptr)
+// trace_inv: `inv` = (safe_inv(d.x), safe_inv(d.y), safe_inv(d.z)) supplied by the caller (k_march reads it from the
+// level's direction table); trace computes it.
+__device__ __forceinline__ Hit trace_inv(const DScene& s, float3 o, float3 d, float3 inv, float tmin, float tmax,
+                                         const int4* __restrict__ entry = nullptr)
 {
     Hit h; h.t = tmax; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
-    const float3 inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     const float3 noi = f3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
     // True while-while (Aila & Laine): every lane descends inner nodes until it holds a leaf (or is
     // done); the warp reconverges at the end of the node loop and tests triangles together.  The
@@ -173,6 +194,11 @@ __device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float 
     }
     if (h.prim == 0xffffffffu) h.t = -1.0f;
     return h;
+}
+
+__device__ __forceinline__ Hit trace(const DScene& s, float3 o, float3 d, float tmin, float tmax, const int4* __restrict__ entry = nullptr)
+{
+    return trace_inv(s, o, d, f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z)), tmin, tmax, entry);
 }
 
 // ------------------------------------------------------------------ shading (S7; src/shader.wgsl:76-100)
@@ -292,7 +318,7 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
     }
     float3 albedo = f3(0.f, 0.f, 0.f);
     if (!NORMAL_ONLY) albedo = b0 ? sample_tex(s, m.tex_c, tu, tv, true, duv) : f3(RC_ATTR(3), RC_ATTR(4), RC_ATTR(5));   // :80
-    float3 Lc = f3(m.ka[0] * 0.05f * m.ka[3], m.ka[1] * 0.05f * m.ka[3], m.ka[2] * 0.05f * m.ka[3]);  // :82-83
+    float3 Lc = f3(m.amb[0], m.amb[1], m.amb[2]);                     // :82-83, Ka * 0.05 * Ka.w (fill_material_constants)
     const float3 Nv = f3(RC_ATTR(6), RC_ATTR(7), RC_ATTR(8));
     float3 raw;
     if (b1) {
@@ -309,7 +335,7 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
     if (NORMAL_ONLY) { Shade r; r.rad = r.albedo = r.direct = f3(0.f, 0.f, 0.f); r.n = N; return r; }
     // specular chain (normalize, powf) only when Ks can contribute: Ks present and non-zero, or Ns < 0
     // (pow(0, Ns<0) = inf must still poison the result exactly as the plain formula does)
-    const bool spec = (m.ks[3] != 0.0f && (m.ks[0] != 0.0f || m.ks[1] != 0.0f || m.ks[2] != 0.0f)) || !(m.ns >= 0.0f);
+    const bool spec = m.spec != 0u;
     for (int li = 0; li < L.n; li++) {
         const float3 lp = f3(L.pos[li][0], L.pos[li][1], L.pos[li][2]);
         const float3 Ld = vnormalize(vsub(lp, P));                   // :91
@@ -323,10 +349,7 @@ __device__ __forceinline__ Shade shade_hit(const DScene& s, const DLights& L, ui
             Lc = f3(fmaf(m.ks[0], ks, Lc.x), fmaf(m.ks[1], ks, Lc.y), fmaf(m.ks[2], ks, Lc.z));
         }
     }
-    const float pred = ((m.ka[0] - 1e-5f) + (m.kd[0] - 1e-5f) + (m.ks[0] - 1e-5f))
-                     + ((m.ka[1] - 1e-5f) + (m.kd[1] - 1e-5f) + (m.ks[1] - 1e-5f))
-                     + ((m.ka[2] - 1e-5f) + (m.kd[2] - 1e-5f) + (m.ks[2] - 1e-5f));                   // :99
-    const float unlit = pred <= 0.0f ? 1.0f : 0.0f;
+    const float unlit = m.unlit;                                     // :99-100 (fill_material_constants)
     Shade r;
     r.direct = f3((Lc.x + unlit) * albedo.x, (Lc.y + unlit) * albedo.y, (Lc.z + unlit) * albedo.z);   // :100
     r.rad = f3(clamp_rad(m.ke[0] + r.direct.x), clamp_rad(m.ke[1] + r.direct.y), clamp_rad(m.ke[2] + r.direct.z));
