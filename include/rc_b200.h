@@ -167,7 +167,9 @@ rc_status rc_level_times(rc_ctx* ctx, float* ms, uint32_t n);
  * 1..32 (refill when fewer lanes are busy), "march_pdl" 0/1, "march_block" 64..512, "march_grid",
  * "march_map<level>" 0 linear / 1 direction tile / 2 probe tile, "march_entry" -1 auto / n levels that start their
  * traversal at per-probe BVH entry frontiers, "march_batch" 0/1 (all levels in one launch + separate merges),
- * "cull" 0/1 (direction culling), "graph" 0/1 (submit the frame as one CUDA graph). */
+ * "cull" 0/1 (direction culling), "graph" 0/1 (submit the frame as one CUDA graph), "gather_tiles" 0 auto / 1 the
+ * one-tile-per-block gather / n tiles per block with prefetch, "list_dir_major" bit i: level i's ray list is ordered
+ * direction-major, "need_pdl" 0/1 (programmatic dependent launch along the k_need chain). */
 rc_status rc_set_tuning(rc_ctx* ctx, const char* key, int value);
 /* Number of kernels rc_render launches per frame. */
 rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);

@@ -378,8 +378,14 @@ __device__ __forceinline__ uint32_t dup_spread16(uint32_t x)
 __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_upper, int up_words, const float4* __restrict__ origin,
                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
                                                  uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
-                                                 uint32_t* __restrict__ list, unsigned int* __restrict__ count, int clear)
+                                                 uint32_t* __restrict__ list, unsigned int* __restrict__ count, int clear, int trigger, int dir_major)
 {
+    // The per-level launches form a chain of short, latency-bound waves.  Launched with programmatic stream
+    // serialization (launch_need pdl) level i+1 is set up while level i still runs: it may read what kernels before
+    // level i produced (origins, link tables) at once and waits for level i — whose atomicOr's fill its masks — only
+    // before it reads them.  `trigger` is set only when the NEXT launch in the stream is such a k_need: the march kernel
+    // that follows the last level reads the list length at its very top and must not start early.
+    if (trigger) cudaTriggerProgrammaticLaunchCompletion();
     const int bits = Dr * Dr, words = (bits + 31) >> 5;
     const size_t total = (size_t)lv.sw * lv.sh * words;
     const size_t gi = (size_t)blockIdx.x * kBlock + threadIdx.x;
@@ -392,8 +398,9 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
         w = (int)(gi - (size_t)probe * words);
         // independent loads first: the kernel is one short latency-bound wave
         const float valid = __ldg(origin + probe).w;
-        r = need[gi];
         if (has_upper) { lw = __ldg(link_w + probe); li = __ldg(link_idx + probe); }
+        cudaGridDependencySynchronize();
+        r = need[gi];
         if (valid == 0.0f) r = 0u;
         if (w == words - 1 && (bits & 31)) r &= (1u << (bits & 31)) - 1u;
         // consume and clear: the masks of levels >= 1 are accumulated by atomicOr, so they must be empty when the next
@@ -415,8 +422,27 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
         s_base = tot ? atomicAdd(count, tot) : 0u;
     }
     __syncthreads();
-    unsigned base = s_base + s_warp[wid] + (unsigned)(pre - n);
-    for (uint32_t m = r; m; m &= m - 1u) list[base++] = probe * (uint32_t)bits + (uint32_t)(32 * w + __ffs((int)m) - 1);
+    if (dir_major) {
+        // Direction-major order inside the warp's share of the list: the warp's threads are 32 / words neighbouring
+        // probes of a row; their requests are appended request by request (same direction across the probes) instead
+        // of probe by probe.  A warp of k_march then marches (nearly) parallel rays from adjacent origins — same
+        // nodes, same hit / miss outcome — instead of one probe's whole fan.  The list is a set: its order cannot
+        // change any texel.
+        unsigned wbase = s_base + s_warp[wid];
+        const unsigned lt = (1u << lane) - 1u;
+        for (int ww = 0; ww < words; ww++) {
+            for (uint32_t any = __reduce_or_sync(0xffffffffu, w == ww ? r : 0u); any; any &= any - 1u) {
+                const int d = __ffs((int)any) - 1;
+                const bool on = w == ww && ((r >> d) & 1u);
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) list[wbase + (unsigned)__popc(m & lt)] = probe * (uint32_t)bits + (uint32_t)(32 * ww + d);
+                wbase += (unsigned)__popc(m);
+            }
+        }
+    } else {
+        unsigned base = s_base + s_warp[wid] + (unsigned)(pre - n);
+        for (uint32_t m = r; m; m &= m - 1u) list[base++] = probe * (uint32_t)bits + (uint32_t)(32 * w + __ffs((int)m) - 1);
+    }
     // (b) the upper level's requests
     if (!has_upper || !r) return;
     if (lw.x < 0.0f) return;                       // no valid upper probe: the far field is the sky (S8)
@@ -959,6 +985,70 @@ __global__ void __launch_bounds__(kBlock) k_merge(DLevel lv, int UD, float3 sky,
 }
 
 // ------------------------------------------------------------------ gather (S9)
+// S9 for one pixel of the tile from the staged level-0 probes (s_tex / s_org hold probe rows rmin.., columns cmin..,
+// `ncols` per row, `stride` uint4 per probe).  Shared by k_gather and k_gather_pipe: the same statements, so the two
+// kernels are bit-identical.
+template <int DDT>
+__device__ __forceinline__ uint2 gather_pixel(const DCamera& cam, const DLevel& l0, const TileRect& tile, int tx, int ty, bool inside, size_t o,
+                                              const float* __restrict__ depth, const uint32_t* __restrict__ normal,
+                                              const uint4* s_tex, const float4* s_org, const float* s_dirs, int cmin, int rmin, int ncols)
+{
+    const int DD = DDT ? DDT : l0.D * l0.D, H2 = DD >> 1, stride = H2 + 1;
+    uint2 v = make_uint2(0u, 0u);            // pixels without geometry: (0,0,0,0)
+    const float dep = inside ? depth[o] : -1.0f;
+    if (dep >= 0.0f) {
+        const int x = tile.x0 + tx, y = tile.y0 + ty;
+        const float3 d = primary_dir(cam, x, y);
+        const float3 hp = vfma(dep, d, cam.eye);
+        const float3 n = oct_decode(normal[o]);
+        int x0, x1, y0, y1;
+        float wx0, wx1, wy0, wy1;
+        gather_axis(x, l0.P, l0.gw, x0, x1, wx0, wx1);
+        gather_axis(y, l0.P, l0.gh, y0, y1, wy0, wy1);
+        const int lk[4] = {(y0 - rmin) * ncols + (x0 - cmin), (y0 - rmin) * ncols + (x1 - cmin),
+                           (y1 - rmin) * ncols + (x0 - cmin), (y1 - rmin) * ncols + (x1 - cmin)};
+        float w[4];
+        w[0] = (wx0 * wy0) * plane_weight(n, hp, s_org[lk[0]]);
+        w[1] = (wx1 * wy0) * plane_weight(n, hp, s_org[lk[1]]);
+        w[2] = (wx0 * wy1) * plane_weight(n, hp, s_org[lk[2]]);
+        w[3] = (wx1 * wy1) * plane_weight(n, hp, s_org[lk[3]]);
+        const float S = ((w[0] + w[1]) + w[2]) + w[3];
+        // S9: one cosine per direction, shared by the four probes; normalised quadrature q = pi / sum(cos)
+        float3 acc[4] = {f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f)};
+        float csum = 0.0f;
+    #pragma unroll
+        for (int di = 0; di < DD; di += 2) {
+            const float ca = fmaxf(vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])), 0.0f);
+            const float cb = fmaxf(vdot(n, f3(s_dirs[3 * di + 3], s_dirs[3 * di + 4], s_dirs[3 * di + 5])), 0.0f);
+            csum = csum + ca;
+            csum = csum + cb;
+            // both cosines zero (about half of the directions: the lower hemisphere): fma(0, texel, acc) == acc for the
+            // finite, non-negative texels a cascade holds, so the pair is skipped — lanes of a warp are neighbouring
+            // pixels with similar normals, the branch is mostly uniform
+            if (!(ca > 0.0f || cb > 0.0f)) continue;
+    #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint4 r = s_tex[lk[k] * stride + (di >> 1)];
+                const float4 a = unpack_half4(make_uint2(r.x, r.y)), b = unpack_half4(make_uint2(r.z, r.w));
+                acc[k] = f3(fmaf(ca, a.x, acc[k].x), fmaf(ca, a.y, acc[k].y), fmaf(ca, a.z, acc[k].z));
+                acc[k] = f3(fmaf(cb, b.x, acc[k].x), fmaf(cb, b.y, acc[k].y), fmaf(cb, b.z, acc[k].z));
+            }
+        }
+        float3 E = f3(0.f, 0.f, 0.f);
+        if (S > 0.0f) {
+            const float q = csum > 0.0f ? RC_PI_F / csum : 0.0f;
+    #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float wd = (w[k] / S) * q;
+                E = f3(fmaf(wd, acc[k].x, E.x), fmaf(wd, acc[k].y, E.y), fmaf(wd, acc[k].z, E.z));
+            }
+        }
+        v = pack_half4(fminf(E.x, 65504.0f), fminf(E.y, 65504.0f), fminf(E.z, 65504.0f), 1.0f);
+    }
+    return v;
+}
+
+
 // Shared-memory staged gather.  A block owns 32x8 pixels; the <= (32/P0+2) x (8/P0+2) level-0 probes its
 // pixels interpolate between are copied once, coalesced (one 128-byte line per probe at D0 = 4), into
 // shared memory with a 16-byte pad per probe (so that the 8-9 probes a warp touches fall into different
@@ -1011,58 +1101,8 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
     const int tx = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ty = blockIdx.y * 8 + (threadIdx.x >> 5);
     const bool inside = tx < tile.w && ty < tile.h;
-    uint2 v = make_uint2(0u, 0u);            // pixels without geometry: (0,0,0,0)
     const size_t o = inside ? (size_t)ty * tile.w + tx : 0;
-    const float dep = inside ? depth[o] : -1.0f;
-    if (dep >= 0.0f) {
-        const int x = tile.x0 + tx, y = tile.y0 + ty;
-        const float3 d = primary_dir(cam, x, y);
-        const float3 hp = vfma(dep, d, cam.eye);
-        const float3 n = oct_decode(normal[o]);
-        int x0, x1, y0, y1;
-        float wx0, wx1, wy0, wy1;
-        gather_axis(x, l0.P, l0.gw, x0, x1, wx0, wx1);
-        gather_axis(y, l0.P, l0.gh, y0, y1, wy0, wy1);
-        const int lk[4] = {(y0 - rmin) * ncols + (x0 - cmin), (y0 - rmin) * ncols + (x1 - cmin),
-                           (y1 - rmin) * ncols + (x0 - cmin), (y1 - rmin) * ncols + (x1 - cmin)};
-        float w[4];
-        w[0] = (wx0 * wy0) * plane_weight(n, hp, s_org[lk[0]]);
-        w[1] = (wx1 * wy0) * plane_weight(n, hp, s_org[lk[1]]);
-        w[2] = (wx0 * wy1) * plane_weight(n, hp, s_org[lk[2]]);
-        w[3] = (wx1 * wy1) * plane_weight(n, hp, s_org[lk[3]]);
-        const float S = ((w[0] + w[1]) + w[2]) + w[3];
-        // S9: one cosine per direction, shared by the four probes; normalised quadrature q = pi / sum(cos)
-        float3 acc[4] = {f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 0.f)};
-        float csum = 0.0f;
-    #pragma unroll
-        for (int di = 0; di < DD; di += 2) {
-            const float ca = fmaxf(vdot(n, f3(s_dirs[3 * di], s_dirs[3 * di + 1], s_dirs[3 * di + 2])), 0.0f);
-            const float cb = fmaxf(vdot(n, f3(s_dirs[3 * di + 3], s_dirs[3 * di + 4], s_dirs[3 * di + 5])), 0.0f);
-            csum = csum + ca;
-            csum = csum + cb;
-            // both cosines zero (about half of the directions: the lower hemisphere): fma(0, texel, acc) == acc for the
-            // finite, non-negative texels a cascade holds, so the pair is skipped — lanes of a warp are neighbouring
-            // pixels with similar normals, the branch is mostly uniform
-            if (!(ca > 0.0f || cb > 0.0f)) continue;
-    #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint4 r = s_tex[lk[k] * stride + (di >> 1)];
-                const float4 a = unpack_half4(make_uint2(r.x, r.y)), b = unpack_half4(make_uint2(r.z, r.w));
-                acc[k] = f3(fmaf(ca, a.x, acc[k].x), fmaf(ca, a.y, acc[k].y), fmaf(ca, a.z, acc[k].z));
-                acc[k] = f3(fmaf(cb, b.x, acc[k].x), fmaf(cb, b.y, acc[k].y), fmaf(cb, b.z, acc[k].z));
-            }
-        }
-        float3 E = f3(0.f, 0.f, 0.f);
-        if (S > 0.0f) {
-            const float q = csum > 0.0f ? RC_PI_F / csum : 0.0f;
-    #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float wd = (w[k] / S) * q;
-                E = f3(fmaf(wd, acc[k].x, E.x), fmaf(wd, acc[k].y, E.y), fmaf(wd, acc[k].z, E.z));
-            }
-        }
-        v = pack_half4(fminf(E.x, 65504.0f), fminf(E.y, 65504.0f), fminf(E.z, 65504.0f), 1.0f);
-    }
+    const uint2 v = gather_pixel<DDT>(cam, l0, tile, tx, ty, inside, o, depth, normal, s_tex, s_org, s_dirs, cmin, rmin, ncols);
     if (inside) out[o] = v;
     if (peer.world) {
         // Fused final-image all-gather: the tile is stored straight into every rank's full-frame
@@ -1072,6 +1112,96 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
             const size_t fo = (size_t)(tile.y0 + ty) * peer.W + (tile.x0 + tx);
             for (int d = 0; d < peer.world; d++) peer.frame[d][fo] = v;
         }
+    }
+}
+
+// ------------------------------------------------------------------ gather, software-pipelined (default D0 = 4)
+// k_gather's blocks run load -> barrier -> compute, and the ncu source view of the 4K frame puts 38 % of the kernel's
+// stall samples on that load phase (the probes of a tile come from L2 / HBM; four resident blocks per SM do not cover
+// it: issue slots are busy 65 % of the time).  Here a block walks a column of `tiles` vertically adjacent 32x8 pixel
+// tiles with two shared-memory buffers: the probes of tile j+1 are fetched with cp.async (16 bytes per request,
+// no registers, no waiting) while tile j is being computed.  The arithmetic is gather_pixel's: bit-identical output.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct GatherWindow { int cmin, rmin, ncols, nrows; };   // level-0 probes a 32x8 pixel tile interpolates between
+
+__device__ __forceinline__ GatherWindow gather_window(const DLevel& l0, const TileRect& tile, int X0, int Y0)
+{
+    const int X1 = min(X0 + 31, tile.x0 + tile.w - 1), Y1 = min(Y0 + 7, tile.y0 + tile.h - 1);
+    int cmin, cmax, rmin, rmax, unused;
+    float fu0, fu1;
+    gather_axis(X0, l0.P, l0.gw, cmin, unused, fu0, fu1);
+    gather_axis(X1, l0.P, l0.gw, unused, cmax, fu0, fu1);
+    gather_axis(Y0, l0.P, l0.gh, rmin, unused, fu0, fu1);
+    gather_axis(Y1, l0.P, l0.gh, unused, rmax, fu0, fu1);
+    GatherWindow g;
+    g.cmin = cmin; g.rmin = rmin; g.ncols = cmax - cmin + 1; g.nrows = rmax - rmin + 1;
+    return g;
+}
+
+__global__ void __launch_bounds__(kBlock) k_gather_pipe(DCamera cam, DLevel l0, TileRect tile, const float4* __restrict__ origin0,
+                                                        const uint2* __restrict__ texels0, const float* __restrict__ dirs0,
+                                                        const float* __restrict__ depth, const uint32_t* __restrict__ normal,
+                                                        uint2* __restrict__ out, int max_probes, int tiles,
+                                                        unsigned int* __restrict__ counts_in, unsigned int* __restrict__ counts_out,
+                                                        PeerOut peer)
+{
+    constexpr int DD = 16, H2 = DD >> 1, stride = H2 + 1;
+    extern __shared__ uint4 s_mem[];
+    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) {   // see k_gather
+        counts_out[threadIdx.x] = counts_in[threadIdx.x];
+        counts_in[threadIdx.x] = 0u;
+    }
+    const size_t buf_u4 = (size_t)max_probes * (stride + 1);            // texels + one float4 origin per probe
+    float* s_dirs = reinterpret_cast<float*>(s_mem + 2 * buf_u4);      // [DD][3]
+    const uint4* tex4 = reinterpret_cast<const uint4*>(texels0);
+    const int X0 = tile.x0 + blockIdx.x * 32;
+    const int row0 = blockIdx.y * tiles;                                // first tile row of this block
+    const int ntiles = min(tiles, (tile.h + 7) / 8 - row0);             // block-uniform
+
+    // asynchronous copy of tile j's probe window into buffer b (one warp per probe row, as in k_gather)
+    auto stage = [&](int j, int b) {
+        const GatherWindow g = gather_window(l0, tile, X0, tile.y0 + (row0 + j) * 8);
+        uint4* s_tex = s_mem + b * buf_u4;
+        float4* s_org = reinterpret_cast<float4*>(s_tex + (size_t)max_probes * stride);
+        for (int pr = threadIdx.x >> 5; pr < g.nrows; pr += kBlock / 32) {
+            const size_t rowbase = (size_t)(g.rmin + pr - l0.py0) * l0.sw + (g.cmin - l0.px0);
+            for (int idx = threadIdx.x & 31; idx < g.ncols * H2; idx += 32) {
+                const int pc = idx / H2, k = idx - pc * H2;
+                cp_async16(s_tex + (pr * g.ncols + pc) * stride + k, tex4 + (rowbase + pc) * H2 + k);
+            }
+            for (int pc = threadIdx.x & 31; pc < g.ncols; pc += 32) cp_async16(s_org + pr * g.ncols + pc, origin0 + rowbase + pc);
+        }
+        cp_async_commit();
+    };
+
+    stage(0, 0);
+    for (int k = threadIdx.x; k < 3 * DD; k += kBlock) s_dirs[k] = dirs0[k];
+    for (int j = 0; j < ntiles; j++) {
+        if (j + 1 < ntiles) { stage(j + 1, (j + 1) & 1); cp_async_wait<1>(); }   // tile j has landed, tile j+1 is in flight
+        else cp_async_wait<0>();
+        __syncthreads();
+        const GatherWindow g = gather_window(l0, tile, X0, tile.y0 + (row0 + j) * 8);
+        const uint4* s_tex = s_mem + (j & 1) * buf_u4;
+        const float4* s_org = reinterpret_cast<const float4*>(s_tex + (size_t)max_probes * stride);
+        const int tx = blockIdx.x * 32 + (threadIdx.x & 31);
+        const int ty = (row0 + j) * 8 + (threadIdx.x >> 5);
+        const bool inside = tx < tile.w && ty < tile.h;
+        const size_t o = inside ? (size_t)ty * tile.w + tx : 0;
+        const uint2 v = gather_pixel<16>(cam, l0, tile, tx, ty, inside, o, depth, normal, s_tex, s_org, s_dirs, g.cmin, g.rmin, g.ncols);
+        if (inside) out[o] = v;
+        if (peer.world && inside) {   // fused final-image exchange, see k_gather
+            const size_t fo = (size_t)(tile.y0 + ty) * peer.W + (tile.x0 + tx);
+            for (int d = 0; d < peer.world; d++) peer.frame[d][fo] = v;
+        }
+        __syncthreads();   // everyone is done with buffer j & 1 before tile j+2 is staged into it
     }
 }
 
@@ -1259,10 +1389,22 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
 }
 
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
-                 const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, cudaStream_t st)
+                 const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, bool pdl,
+                 bool trigger, bool dir_major, cudaStream_t st)
 {
     const size_t total = (size_t)lv.sw * lv.sh * ((Dr * Dr + 31) / 32);
-    if (total) k_need<<<blocks_for(total), kBlock, 0, st>>>(lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count, clear ? 1 : 0);
+    if (!total) return;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks_for(total));
+    cfg.blockDim = dim3(kBlock);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_need, lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count, clear ? 1 : 0,
+                       trigger ? 1 : 0, dir_major ? 1 : 0);
 }
 
 void launch_march_all(const DScene& s, const DLights& L, const DLevelSet& ls, const int* levels, int n, const int* map,
@@ -1348,12 +1490,19 @@ void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* 
 
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
                    const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
-                   unsigned int* counts_out, const PeerOut& peer, cudaStream_t st)
+                   unsigned int* counts_out, const PeerOut& peer, int tiles_per_block, cudaStream_t st)
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
     const int DD = l0.D * l0.D;
     const int max_probes = ((32 + l0.P - 1) / l0.P + 2) * ((8 + l0.P - 1) / l0.P + 2);
     const size_t smem = (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
+    if (DD == 16 && tiles_per_block > 1) {   // software-pipelined column of tiles (two staging buffers)
+        const size_t smem2 = 2 * (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
+        dim3 grid2((tile.w + 31) / 32, ((tile.h + 7) / 8 + tiles_per_block - 1) / tiles_per_block);
+        k_gather_pipe<<<grid2, kBlock, smem2, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, tiles_per_block,
+                                                   counts_in, counts_out, peer);
+        return;
+    }
     if (DD == 16) {
         k_gather<16><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out, peer);
         return;

@@ -39,7 +39,11 @@ void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileR
 // [level 0 -> 1], 2 expanded 2x; up_words = mask words per upper probe) through k_link's tables; clear: zero the
 // consumed words (levels >= 1, whose masks are accumulated with atomicOr and must be empty for the next frame)
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
-                 const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, cudaStream_t st);
+                 const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, bool pdl,
+                 bool trigger, bool dir_major, cudaStream_t st);
+// pdl: programmatic dependent launch on the previous level's k_need (the origins / link tables must be older);
+// trigger: the next launch in the stream is a pdl k_need, so this one may release it early;
+// dir_major: order each warp's list entries by request (direction) first, probe second
 // deferred fs_main: albedo / direct colour from the stored visibility (on demand)
 void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,
                    const float2* bary, uint2* albedo, uint2* direct, cudaStream_t st);
@@ -87,9 +91,10 @@ int march_persist_blocks_per_sm();
 void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, float4* avg_out, cudaStream_t st);
 void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st);
+// tiles_per_block > 1 (and D0 = 4): software-pipelined variant, a block walks a column of that many 32x8 pixel tiles
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
                    const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
-                   unsigned int* counts_out, const PeerOut& peer, cudaStream_t st);
+                   unsigned int* counts_out, const PeerOut& peer, int tiles_per_block, cudaStream_t st);
 void launch_peer_begin(const PeerOut& peer, uint32_t* my_ctrl, cudaStream_t st);
 void launch_peer_publish(const PeerOut& peer, cudaStream_t st);
 void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t st);

@@ -121,6 +121,18 @@ struct rc_ctx {
     std::vector<size_t> need_offset, list_offset;   // words / entries before level i
     std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
     int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
+    int list_dir_major = 0;                         // bit i: level i's ray list is ordered direction-major inside each warp's share
+    int need_pdl = 0;                               // 1: the k_need chain (levels >= 1) uses programmatic dependent launch
+    // k_gather_pipe: a block walks that many 32x8 pixel tiles with the next tile's probes prefetched; 1 = k_gather;
+    // 0 = auto: 4 on large frames, 2 on small ones (measured: 4K 0.292 -> 0.252 ms with 4; 1080p 0.057 -> 0.050 ms with 2,
+    // 0.054 with 4 — too few blocks per SM left)
+    int gather_tiles = 0;
+    int gather_tiles_eff() const
+    {
+        if (gather_tiles > 0) return gather_tiles;
+        const size_t t = (size_t)((tile.w + 31) / 32) * ((tile.h + 7) / 8);
+        return t >= 16384 ? 4 : 2;
+    }
     // rc_render records the frame's ~18 launches into a CUDA graph (stream capture) and submits it with ONE
     // cudaGraphLaunch; every frame is re-captured and the executable graph updated in place
     // (cudaGraphExecUpdate: camera, lights, grid sizes and the output slot are node parameters).
@@ -688,6 +700,9 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_MARCH_ENTRY")) c->march_entry = atoi(e) < -1 ? -1 : atoi(e);
         if (const char* e = getenv("RC_MARCH_BATCH")) c->march_batch = atoi(e) > 0 ? 1 : 0;
         if (const char* e = getenv("RC_CULL")) c->cull = atoi(e) != 0;
+        if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
+        if (const char* e = getenv("RC_LIST_DIRMAJOR")) c->list_dir_major = (int)strtol(e, nullptr, 0);
+        if (const char* e = getenv("RC_GATHER_TILES")) c->gather_tiles = atoi(e) < 0 ? 0 : (atoi(e) > 64 ? 64 : atoi(e));
         if (const char* e = getenv("RC_GRAPH")) c->use_graph = atoi(e) != 0;
         cudaDeviceProp prop;
         int bps = march_persist_blocks_per_sm();
@@ -785,7 +800,8 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
             launch_need(L, c->need_res[i], has_upper, (up_res * up_res + 31) / 32, c->d_origin.p + L.probe_offset,
                         c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, c->d_need.p + c->need_offset[i],
                         has_upper ? c->d_need.p + c->need_offset[i + 1] : nullptr, c->d_list.p + c->list_offset[i],
-                        c->d_ray_count.p + i, i >= 1, st);
+                        c->d_ray_count.p + i, i >= 1, c->need_pdl && i >= 1, c->need_pdl && i + 1 < n_lists,
+                        ((c->list_dir_major >> i) & 1) != 0, st);
             c->launches++;
         }
     }
@@ -878,6 +894,9 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "march_entry" && value >= -1) c->march_entry = value;
     else if (k == "march_batch" && value >= 0 && value <= 1) c->march_batch = value;
     else if (k == "cull" && value >= 0 && value <= 1) c->cull = value;
+    else if (k == "gather_tiles" && value >= 0 && value <= 64) c->gather_tiles = value;
+    else if (k == "need_pdl" && value >= 0 && value <= 1) c->need_pdl = value;
+    else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
     else if (k == "graph" && value >= 0 && value <= 1) c->use_graph = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
@@ -917,7 +936,7 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
         c->launches++;
     }
     launch_gather(c->cam, L0, c->tile, c->d_origin.p + L0.probe_offset, c->d_cascade.p + L0.texel_offset, c->d_dirs.p,
-                  c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, po, st);
+                  c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, po, c->gather_tiles_eff(), st);
     c->launches++;
     if (c->peer.world) {
         launch_peer_publish(po, st);

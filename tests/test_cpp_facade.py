@@ -140,7 +140,7 @@ def test_headless_driver_frames_equal_python_mirror(tmp_path):
     lo, hi = list(info.bbox_min), list(info.bbox_max)
     for frame in (5, 6):
         pos, tgt, zn, zf = rc.scenes.orbit_camera(lo, hi, frame)
-        assert np.allclose(lines[frame - 5]["eye"], pos, rtol=0, atol=0)
+        assert np.array_equal(np.array(lines[frame - 5]["eye"], dtype=np.float32), pos)   # %.9g round-trips a float32
         st.uniform_camera = rc.UniformCamera.look_at(pos, tgt, rc.Projection.new(W, H, 45.0, zn, zf))
         st.light_position = rc.scenes.bench_light(lo, hi)
         r.update(st)
