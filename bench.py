@@ -332,8 +332,10 @@ def run_product(args):
                 "achieved": march_bytes_per_launch / (avg_march_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": march_bytes_per_launch,
                 "avg_launch_ms": avg_march_launch_ms}
-        tpath = os.path.join(ROOT, "profiles", "r1_g_traffic.json")
-        if os.path.exists(tpath):      # dram bytes per launch from the committed ncu --set full capture of this workload
+        import glob
+        tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+        tpath = tpaths[-1] if tpaths else ""
+        if tpath:      # dram bytes per launch from the latest committed ncu --set full capture of this workload
             with open(tpath) as fh:
                 tj = json.load(fh)
             if wl in tj:
@@ -359,6 +361,7 @@ def run_product(args):
                        "l2": "flushed between timed steps (256 MiB memset)",
                        "parallelism": "1 GPU" if world == 1 else f"multi-view batch, one orbit view per rank x{world}",
                        "merge": "separate kernels" if args.separate_merge else "fused into march",
+                       "gather": "k_gather_pipe: software-pipelined column of 32x8 tiles per block (cp.async prefetch)",
                        "submission": "one CUDA graph per frame (stream capture + cudaGraphExecUpdate)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 80 + 16 * n_lights, "d2h_bytes_per_step": host_bytes,

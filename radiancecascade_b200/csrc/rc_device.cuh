@@ -130,6 +130,9 @@ __device__ __forceinline__ void tri_test(const float4* __restrict__ g, float3 o,
 // first, padded with kDoneLink — a set of subtrees that together hold every triangle within reach of the
 // probe's interval.  The traversal then starts with those links on its stack instead of at the root, skipping
 // the upper levels of the tree that every ray of the probe would walk through identically.
+#ifndef RC_DIST_STACK
+#define RC_DIST_STACK 0   // 1: the traversal stack also keeps each deferred subtree's entry distance (A/B build: make EXTRA=-DRC_DIST_STACK=1)
+#endif
 constexpr int RC_ENTRY_SLOTS = 8;
 constexpr int kDoneLinkC = (int)0x80000000;
 
@@ -146,17 +149,28 @@ __device__ __forceinline__ Hit trace_inv(const DScene& s, float3 o, float3 d, fl
     // triangle tests — with 1.5-3 active lanes (profiles/r1_a_*).
     constexpr int kDoneLink = kDoneLinkC;   // never a real leaf code (first < 2^28)
     int stack[48];
+#if RC_DIST_STACK
+    // entry distance of every deferred subtree: when it is popped after a closer hit has been found it is dropped
+    // without visiting its node (its children could only fail the same n <= min(far, h.t) test: child boxes lie
+    // inside the parent's, and the slab arithmetic is monotonic) — same hits, fewer node visits
+    float dstack[48];
+#define RC_PUSH(link, dist) do { stack[sp] = (link); dstack[sp] = (dist); sp++; } while (0)
+#define RC_POP() do { cur = kDoneLink; while (sp) { --sp; if (!(dstack[sp] > h.t)) { cur = stack[sp]; break; } } } while (0)
+#else
+#define RC_PUSH(link, dist) do { stack[sp++] = (link); } while (0)
+#define RC_POP() do { cur = sp ? stack[--sp] : kDoneLink; } while (0)
+#endif
     int sp = 0;
     int cur = 0;
     if (entry) {
         const int4 ea = __ldg(entry), eb = __ldg(entry + 1);
-        if (eb.w != kDoneLink) stack[sp++] = eb.w;
-        if (eb.z != kDoneLink) stack[sp++] = eb.z;
-        if (eb.y != kDoneLink) stack[sp++] = eb.y;
-        if (eb.x != kDoneLink) stack[sp++] = eb.x;
-        if (ea.w != kDoneLink) stack[sp++] = ea.w;
-        if (ea.z != kDoneLink) stack[sp++] = ea.z;
-        if (ea.y != kDoneLink) stack[sp++] = ea.y;
+        if (eb.w != kDoneLink) RC_PUSH(eb.w, 0.0f);
+        if (eb.z != kDoneLink) RC_PUSH(eb.z, 0.0f);
+        if (eb.y != kDoneLink) RC_PUSH(eb.y, 0.0f);
+        if (eb.x != kDoneLink) RC_PUSH(eb.x, 0.0f);
+        if (ea.w != kDoneLink) RC_PUSH(ea.w, 0.0f);
+        if (ea.z != kDoneLink) RC_PUSH(ea.z, 0.0f);
+        if (ea.y != kDoneLink) RC_PUSH(ea.y, 0.0f);
         cur = ea.x;
     }
     while (cur != kDoneLink) {
@@ -181,17 +195,19 @@ __device__ __forceinline__ Hit trace_inv(const DScene& s, float3 o, float3 d, fl
             // child was measured: +-1 %, not kept)
             const bool first1 = hit1 && (!hit0 || n1 < n0);
             const int nearc = first1 ? c1 : c0, farc = first1 ? c0 : c1;
-            if (hit0 && hit1) stack[sp++] = farc;
+            if (hit0 && hit1) RC_PUSH(farc, first1 ? n0 : n1);
             if (hit0 || hit1) cur = nearc;
-            else cur = sp ? stack[--sp] : kDoneLink;
+            else RC_POP();
         }
         while (cur < 0 && cur != kDoneLink) {
             const uint32_t leaf = (uint32_t)~cur;
             const uint32_t first = leaf >> 3, cnt = leaf & 7u;
             for (uint32_t i = 0; i < cnt; i++) tri_test(s.tri_geom + 3 * (size_t)(first + i), o, d, tmin, tmax, h);
-            cur = sp ? stack[--sp] : kDoneLink;
+            RC_POP();
         }
     }
+#undef RC_PUSH
+#undef RC_POP
     if (h.prim == 0xffffffffu) h.t = -1.0f;
     return h;
 }
