@@ -3,7 +3,7 @@
 tag=${1:-r1h}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu_${tag}.txt 2>&1
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_${tag}.log 2>&1
+( time timeout 900 python -m pytest tests -m gpu -q --maxfail=5 ) > gpurun_out/pytest_gpu_${tag}.log 2>&1
 echo "pytest exit: $?" >> gpurun_out/pytest_gpu_${tag}.log
 tail -5 gpurun_out/pytest_gpu_${tag}.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${tag}.log 2>&1
