@@ -150,7 +150,9 @@ rc_status rc_read_target(rc_ctx* ctx, rc_target which, void* host_dst, size_t by
 /* Pipelined read-back of RC_TARGET_IRRADIANCE (double-buffered on the device): enqueues the copy of the
  * frame just rendered on a separate copy stream and returns a ticket; the next rc_update / rc_render may be
  * issued immediately and overlaps the copy.  rc_read_wait(ticket) blocks until host_dst is complete.
- * host_dst should be page-locked, and at most two copies may be outstanding (one per buffer). */
+ * host_dst should be page-locked, and at most two copies may be outstanding (one per buffer).  To keep the GPU's
+ * queue full, submit frame i (rc_update, rc_render) BEFORE waiting for the read-back of frame i-2 and only then call
+ * rc_read_target_async for frame i (bench.py e2e loop); the device side is ordered by the library. */
 rc_status rc_read_target_async(rc_ctx* ctx, rc_target which, void* host_dst, size_t bytes, uint32_t* ticket);
 rc_status rc_read_wait(rc_ctx* ctx, uint32_t ticket);
 /* Size in bytes rc_read_target needs for `which`. */
@@ -169,7 +171,8 @@ rc_status rc_level_times(rc_ctx* ctx, float* ms, uint32_t n);
  * traversal at per-probe BVH entry frontiers, "march_batch" 0/1 (all levels in one launch + separate merges),
  * "cull" 0/1 (direction culling), "graph" 0/1 (submit the frame as one CUDA graph), "gather_tiles" 0 auto / 1 the
  * one-tile-per-block gather / n tiles per block with prefetch, "list_dir_major" bit i: level i's ray list is ordered
- * direction-major, "need_pdl" 0/1 (programmatic dependent launch along the k_need chain). */
+ * direction-major, "need_pdl" 0/1 (programmatic dependent launch along the k_need chain), "copy_blocks" 0 = the copy
+ * engine / n = rc_read_target_async stores the frame into page-locked memory from n resident blocks. */
 rc_status rc_set_tuning(rc_ctx* ctx, const char* key, int value);
 /* Number of kernels rc_render launches per frame. */
 rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);

@@ -262,3 +262,15 @@ class OracleScene:
 
 def num_threads() -> int:
     return int(lib().rco_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the oracle's loops (overrides OMP_NUM_THREADS, which torchrun sets to 1 for its workers)."""
+    lib().rco_set_num_threads(C.c_int(int(n)))
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1

@@ -797,6 +797,17 @@ int rco_num_threads(void)
 #endif
 }
 
+/* Thread count of the OpenMP loops (the timing arm of bench.py uses every host core even when a launcher such as
+ * torchrun exported OMP_NUM_THREADS=1 for its worker processes). */
+void rco_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 void rco_scene_bbox(const rco_scene* s, float out6[6])
 {
     out6[0] = s->bbmin.x; out6[1] = s->bbmin.y; out6[2] = s->bbmin.z;

@@ -1250,6 +1250,14 @@ __global__ void k_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl)
     __threadfence_system();
 }
 
+// ------------------------------------------------------------------ read-back by SMs (rc_read_target_async, optional)
+// Streams a finished target into page-locked host memory with plain 16-byte stores (posted PCIe writes) from a
+// few resident blocks, as an alternative to the copy engine (rc_set_tuning "copy_blocks").
+__global__ void __launch_bounds__(kBlock) k_copy_to_host(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n16; i += (size_t)gridDim.x * kBlock) dst[i] = ld_u4(src + i);
+}
+
 // ------------------------------------------------------------------ display composite (outside the hot path)
 __device__ __forceinline__ unsigned char srgb8(float x)
 {
@@ -1518,6 +1526,11 @@ void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const fl
 void launch_peer_begin(const PeerOut& peer, uint32_t* my_ctrl, cudaStream_t st) { k_peer_begin<<<1, 32, 0, st>>>(peer, my_ctrl); }
 void launch_peer_publish(const PeerOut& peer, cudaStream_t st) { k_peer_publish<<<1, 32, 0, st>>>(peer); }
 void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t st) { k_peer_wait<<<1, 32, 0, st>>>(world, seq, my_ctrl); }
+
+void launch_copy_to_host(const void* src, void* dst_host_mapped, size_t bytes, int blocks, cudaStream_t st)
+{
+    k_copy_to_host<<<blocks, kBlock, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst_host_mapped), bytes / 16);
+}
 
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
                       uchar4* composite, uchar4* direct_srgb, cudaStream_t st)

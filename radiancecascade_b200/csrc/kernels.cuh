@@ -98,6 +98,8 @@ void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const fl
 void launch_peer_begin(const PeerOut& peer, uint32_t* my_ctrl, cudaStream_t st);
 void launch_peer_publish(const PeerOut& peer, cudaStream_t st);
 void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t st);
+// SM-driven device -> pinned-host copy (bytes % 16 == 0, dst = device-visible address of page-locked host memory)
+void launch_copy_to_host(const void* src, void* dst_host_mapped, size_t bytes, int blocks, cudaStream_t st);
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
                       uchar4* composite, uchar4* direct_srgb, cudaStream_t st);
 void launch_trace_rays(const DScene& s, const float* rays, uint32_t n, float* hits, cudaStream_t st);

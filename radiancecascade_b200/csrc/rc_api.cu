@@ -122,6 +122,9 @@ struct rc_ctx {
     std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
     int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
     int list_dir_major = 0;                         // bit i: level i's ray list is ordered direction-major inside each warp's share
+    // rc_read_target_async: 0 = copy engine (cudaMemcpyAsync); n > 0 = n resident blocks of k_copy_to_host store the
+    // target into the page-locked destination
+    int copy_blocks = 0;
     int need_pdl = 0;                               // 1: the k_need chain (levels >= 1) uses programmatic dependent launch
     // k_gather_pipe: a block walks that many 32x8 pixel tiles with the next tile's probes prefetched; 1 = k_gather;
     // 0 = auto: 4 on large frames, 2 on small ones (measured: 4K 0.292 -> 0.252 ms with 4; 1080p 0.057 -> 0.050 ms with 2,
@@ -674,7 +677,11 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
     if (cudaSetDevice(c->device) != cudaSuccess) st = RC_ERR_CUDA;
     if (st == RC_OK && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) st = RC_ERR_CUDA;
     if (st == RC_OK) for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
-    if (st == RC_OK && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) st = RC_ERR_CUDA;
+    if (st == RC_OK) {   // lowest priority: an SM-driven read-back must not take SMs from the frame that is being rendered
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, lo) != cudaSuccess) st = RC_ERR_CUDA;
+    }
     if (st == RC_OK && cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming) != cudaSuccess) st = RC_ERR_CUDA;
     if (st == RC_OK) for (auto& e : c->ev_copy_done) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { st = RC_ERR_CUDA; break; }
     if (st == RC_OK) for (auto& e : c->ev_level) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
@@ -701,6 +708,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_MARCH_BATCH")) c->march_batch = atoi(e) > 0 ? 1 : 0;
         if (const char* e = getenv("RC_CULL")) c->cull = atoi(e) != 0;
         if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
+        if (const char* e = getenv("RC_COPY_BLOCKS")) c->copy_blocks = atoi(e) < 0 ? 0 : (atoi(e) > 1024 ? 1024 : atoi(e));
         if (const char* e = getenv("RC_LIST_DIRMAJOR")) c->list_dir_major = (int)strtol(e, nullptr, 0);
         if (const char* e = getenv("RC_GATHER_TILES")) c->gather_tiles = atoi(e) < 0 ? 0 : (atoi(e) > 64 ? 64 : atoi(e));
         if (const char* e = getenv("RC_GRAPH")) c->use_graph = atoi(e) != 0;
@@ -896,6 +904,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "cull" && value >= 0 && value <= 1) c->cull = value;
     else if (k == "gather_tiles" && value >= 0 && value <= 64) c->gather_tiles = value;
     else if (k == "need_pdl" && value >= 0 && value <= 1) c->need_pdl = value;
+    else if (k == "copy_blocks" && value >= 0 && value <= 1024) c->copy_blocks = value;
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
     else if (k == "graph" && value >= 0 && value <= 1) c->use_graph = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
@@ -1135,7 +1144,19 @@ rc_status rc_read_target_async(rc_ctx* c, rc_target which, void* host_dst, size_
     const int slot = c->irr_slot;
     CU_OK(c, cudaEventRecord(c->ev_frame_done, st));
     CU_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_frame_done, 0));
-    CU_OK(c, cudaMemcpyAsync(host_dst, c->irr(), need, cudaMemcpyDeviceToHost, c->copy_stream));
+    bool by_sm = false;
+    if (c->copy_blocks > 0 && need % 16 == 0) {   // SM-driven copy: only into page-locked memory the device can address
+        cudaPointerAttributes pa{};
+        void* dev_view = nullptr;
+        if (cudaPointerGetAttributes(&pa, host_dst) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+            cudaHostGetDevicePointer(&dev_view, host_dst, 0) == cudaSuccess && dev_view) {
+            launch_copy_to_host(c->irr(), dev_view, need, c->copy_blocks, c->copy_stream);
+            by_sm = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (!by_sm) CU_OK(c, cudaMemcpyAsync(host_dst, c->irr(), need, cudaMemcpyDeviceToHost, c->copy_stream));
     CU_OK(c, cudaEventRecord(c->ev_copy_done[slot], c->copy_stream));
     c->copy_pending[slot] = true;
     *ticket = (uint32_t)slot;

@@ -193,6 +193,20 @@ class DefaultRenderer:
         self._check(self._lib.rc_update(self._h, C.byref(uc.raw), lights, len(pts), flags))
         state.normal_map_changed = False
 
+    def pack_update(self, state: AppState):
+        """The arguments of rc_update for `state`, built ahead of time: (rc_camera, rc_light[n], n, flags)."""
+        uc = state.uniform_camera or UniformCamera.from_camera_project(state.camera, state.projection)
+        pts = [state.light_position] + list(state.extra_lights)
+        lights = (_ffi.rc_light * len(pts))()
+        for i, p in enumerate(pts):
+            lights[i].position = (C.c_float * 4)(p[0], p[1], p[2], 1.0)
+        return uc.raw, lights, len(pts), (_ffi.RC_UPD_ENABLE_NORMAL_MAP if state.enable_normal_map else 0)
+
+    def update_packed(self, packed) -> None:
+        """rc_update with arguments from pack_update (the per-frame host -> device write, nothing else)."""
+        cam, lights, n, flags = packed
+        self._check(self._lib.rc_update(self._h, C.byref(cam), lights, n, flags))
+
     # RenderStage::resize (src/renderer.rs:615-618)
     def resize(self, width: int, height: int) -> None:
         self._check(self._lib.rc_resize(self._h, width, height))
