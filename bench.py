@@ -368,7 +368,10 @@ def run_product(args):
         gather["frac"] = gather["achieved"] / peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "value_marched": world * traced / (ms_per_step * 1e-3) / 1e9,
+            "ms_per_step": ms_per_step,
+            "ms_per_step_stats": {"median": float(np.median(ms_steps)), "p10": float(np.percentile(ms_steps, 10)),
+                                  "p90": float(np.percentile(ms_steps, 90)), "note": "rank 0, per-step CUDA-event times along the orbit"},
+            "value_marched": world * traced / (ms_per_step * 1e-3) / 1e9,
             "all_rays": {"value": world * rays / (nocull_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": nocull_ms,
                          "note": "direction culling off (rc_set_tuning cull 0): every texel of every level marched; irradiance bit-identical"},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
