@@ -37,8 +37,10 @@ def test_reference_arm_prints_one_contract_line():
 
 
 def test_reference_arm_under_torchrun_only_rank0_works():
+    import socket
+    sk = socket.socket(); sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]; sk.close()
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29533", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "cube_512",
+                          "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "cube_512",
                           "--cpu-sample-div", "4", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     d = _check_line(out.stdout, 2)
