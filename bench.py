@@ -391,7 +391,7 @@ def run_product(args):
                 roof["traffic"] = tj[wl]["k_march_dram_bytes_per_launch"]
                 roof["traffic_source"] = tj["source"].replace("<workload>", wl)
         roof["frac"] = roof["achieved"] / peak
-        gather = {"kernel": "k_gather", "bound": "hbm", "achieved": gather_bytes / (st_mean["gather"] * 1e-3) / 1e9, "peak": peak,
+        gather = {"kernel": "k_gather_pipe", "bound": "hbm", "achieved": gather_bytes / (st_mean["gather"] * 1e-3) / 1e9, "peak": peak,
                   "unit": "GB/s", "bytes": gather_bytes}
         gather["frac"] = gather["achieved"] / peak
         line = {
