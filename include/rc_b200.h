@@ -181,6 +181,11 @@ rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
  * every other texel of the cascade is left unspecified.  UINT32_MAX where the level was not culled (every texel
  * marched), 0 for a top level that is constant and never materialised.  Waits for the frame to finish. */
 rc_status rc_rays_marched(rc_ctx* ctx, uint32_t* rays, uint32_t n);
+/* Debug / parity entry: the ray list of `level` as the last culled frame built it (an index table: must match the
+ * culling rule of include/rc_spec.h bit for bit, in any order).  Entry = probe * R^2 + r with probe the sub-grid
+ * linear probe index; level 0: R = D_0, r = texel (dy * D_0 + dx); level i >= 1: R = D_{i-1}, r = the 2x2 quad of
+ * level-i texels below direction r of level i-1.  *count = entries of the list; at most bytes / 4 are copied. */
+rc_status rc_get_ray_list(rc_ctx* ctx, uint32_t level, uint32_t* entries, size_t bytes, uint32_t* count);
 
 /* ---- Tiled multi-GPU: final-image exchange through NVLink peer memory (one context per GPU, one process each,
  * all on one node).  Replaces the all-gather of the finished tiles: k_gather stores every pixel of this rank's tile

@@ -216,6 +216,16 @@ class OracleScene:
         return dict(depth=depth.reshape(sh), prim=prim.reshape(sh), normal=normal.reshape(sh),
                     albedo=albedo.reshape(sh + (4,)), direct=direct.reshape(sh + (4,)))
 
+    def pixel_masks(self, p: Params, gb) -> np.ndarray:
+        """uint32[tile_h][tile_w]: level-0 directions with a positive cosine at each pixel (direction culling, S9)."""
+        lv0 = self.levels(p)[0]
+        d0 = self.directions(lv0.D)
+        depth = np.ascontiguousarray(gb["depth"], np.float32).reshape(-1)
+        normal = np.ascontiguousarray(gb["normal"], np.uint32).reshape(-1)
+        out = np.zeros(p.tile_w * p.tile_h, np.uint32)
+        lib().rco_pixel_masks(C.byref(p), _p(d0), _p(depth), _p(normal), _p(out))
+        return out.reshape(p.tile_h, p.tile_w)
+
     def render(self, p: Params, cam, lights, flags=1, keep_raw=False, want_hits=False):
         """Full frame per rc_spec.h: G-buffer, probes, march, top-down merge, gather."""
         cam = np.ascontiguousarray(cam, dtype=np.float32)

@@ -788,6 +788,24 @@ void rco_gather(const rco_params* p, const float cam[20],
     }
 }
 
+/* Direction culling (kernels.cu k_gbuffer), restated for the tests: per pixel the mask of level-0 directions the gather
+ * above weights with cs_d = max(dot(n, w_d), 0) > 0 — bit d set iff dot(n, w_d) > 0 with the decoded stored normal. */
+void rco_pixel_masks(const rco_params* p, const float* dirs0, const float* depth, const uint32_t* normal, uint32_t* mask)
+{
+    rco_level L; rco_level_layout(p, 0, &L);
+    int DD = L.D * L.D;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < p->tile_w * p->tile_h; i++) {
+        uint32_t m = 0u;
+        if (!(depth[i] < 0.0f) && DD <= 32) {
+            v3 n = oct_decode(normal[i]);
+            for (int di = 0; di < DD; di++)
+                if (vdot(n, V(dirs0[3 * di], dirs0[3 * di + 1], dirs0[3 * di + 2])) > 0.0f) m |= 1u << di;
+        }
+        mask[i] = m;
+    }
+}
+
 int rco_num_threads(void)
 {
 #ifdef _OPENMP

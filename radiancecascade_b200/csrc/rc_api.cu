@@ -1295,6 +1295,22 @@ rc_status rc_rays_marched(rc_ctx* c, uint32_t* rays, uint32_t n)
     return RC_OK;
 }
 
+rc_status rc_get_ray_list(rc_ctx* c, uint32_t level, uint32_t* entries, size_t bytes, uint32_t* count)
+{
+    if (!c || !count || level >= c->N) return RC_ERR_INVALID_ARG;
+    if (!c->ev_recorded || !c->frame_culled) { c->error = "rc_get_ray_list needs a rendered frame with direction culling on"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    CU_OK(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
+    uint32_t n = (level + 1 == c->N && c->top_fillable()) ? 0u : c->h_ray_count[level];
+    if (n == 0xffffffffu) n = 0u;
+    *count = n;
+    const size_t cap = c->list_offset[level + 1] - c->list_offset[level];
+    size_t copy = n < bytes / 4 ? n : bytes / 4;
+    if (copy > cap) copy = cap;
+    if (entries && copy) CU_OK(c, cudaMemcpy(entries, c->d_list.p + c->list_offset[level], copy * 4, cudaMemcpyDeviceToHost));
+    return RC_OK;
+}
+
 rc_status rc_get_levels(rc_ctx* c, rc_level_info* out, uint32_t max_levels, uint32_t* num_levels)
 {
     if (!c) return RC_ERR_INVALID_ARG;

@@ -321,6 +321,15 @@ class DefaultRenderer:
         self._check(self._lib.rc_rays_marched(self._h, v, n))
         return [None if int(x) == 0xFFFFFFFF else int(x) for x in v]
 
+    def ray_list(self, level: int) -> np.ndarray:
+        """The level's ray list of the last culled frame (uint32 entries, unordered; include/rc_b200.h rc_get_ray_list)."""
+        n = C.c_uint32()
+        self._check(self._lib.rc_get_ray_list(self._h, level, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            self._check(self._lib.rc_get_ray_list(self._h, level, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(n)))
+        return out
+
     def launch_count(self) -> int:
         n = C.c_uint32()
         self._check(self._lib.rc_launch_count(self._h, C.byref(n)))

@@ -385,6 +385,30 @@ def test_ray_list_order_and_need_pdl_do_not_change_the_frame(name, W, H):
     assert float(res[0][1].view(np.float16)[..., :3].astype(np.float32).max()) > 0.0
 
 
+@pytest.mark.culled
+@pytest.mark.parametrize("name,W,H", [("living_room", 256, 144), ("teapot", 200, 120), ("test_room", 132, 100), ("cube", 96, 96)])
+def test_ray_lists_match_the_culling_rule_bit_exactly(name, W, H):
+    """The per-level ray lists are index tables: as sets they must equal the numpy restatement of the culling rule
+    (tests/common.py predict_ray_lists) entry for entry — nothing the irradiance needs is missing, nothing else is marched."""
+    from common import predict_ray_lists
+    osc = oracle_scene(name)
+    st, cam, lights = frame_setup(name, W, H)
+    r = render_product(name, W, H, st)
+    marched = r.rays_marched()
+    N = len(marched)
+    n_lists = N - 1 if marched[-1] == 0 else N
+    p = osc.params(W, H, store_half=True)
+    out = osc.render(p, cam, lights)
+    want = predict_ray_lists(osc, p, out, r.read_target(_ffi.RC_TARGET_DEPTH), r.read_target(_ffi.RC_TARGET_NORMAL), n_lists)
+    total = 0
+    for i in range(n_lists):
+        got = np.sort(r.ray_list(i))
+        assert got.shape == want[i].shape and np.array_equal(got, want[i]), (i, got.size, want[i].size)
+        assert marched[i] == got.size * (4 if i >= 1 else 1)
+        total += got.size
+    assert total > 0
+
+
 def test_resize_matches_fresh_context():
     st, _, _ = frame_setup("cube", 96, 64)
     a = render_product("cube", 96, 64, st)
