@@ -11,6 +11,7 @@
 // empty texture exactly as the reference does for an undecodable file (src/renderer.rs:424-430).
 #include <cstdint>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -82,7 +83,7 @@ struct BitReader {
     void reset() { buf = 0; cnt = 0; hit_marker = false; }
 };
 
-inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }   // callers guarantee 1 <= s <= 15
 
 int decode_symbol(BitReader& br, const Huff& h)
 {
@@ -122,11 +123,14 @@ struct Decoder {
     std::string err;
 
     bool fail(const char* m) { err = m; return false; }
+    bool bad_stream = false;   // set by the entropy decoders on a symbol no valid 8-bit stream can contain
+    bool corrupt(const char* m) { if (!bad_stream) { bad_stream = true; err = m; } return false; }
 
     // ---- entropy decoding of one block ----------------------------------------------
     bool block_baseline(BitReader& br, Component& c, int16_t* b)
     {
         const int s = decode_symbol(br, dc[c.td]);
+        if (s > 11) return corrupt("DC coefficient category above 11");          // 8-bit JPEG: DC differences need <= 11 bits
         const int diff = s ? extend(br.get(s), s) : 0;
         c.pred += diff;
         b[0] = (int16_t)c.pred;
@@ -134,6 +138,7 @@ struct Decoder {
             const int rs = decode_symbol(br, ac[c.ta]);
             const int r = rs >> 4, sz = rs & 15;
             if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
+            if (sz > 10) return corrupt("AC coefficient category above 10");
             k += r;
             if (k > 63) break;
             b[kZigzag[k]] = (int16_t)extend(br.get(sz), sz);
@@ -145,6 +150,7 @@ struct Decoder {
     void block_dc_first(BitReader& br, Component& c, int16_t* b, int al)
     {
         const int s = decode_symbol(br, dc[c.td]);
+        if (s > 11) { corrupt("DC coefficient category above 11"); return; }
         const int diff = s ? extend(br.get(s), s) : 0;
         c.pred += diff;
         b[0] = (int16_t)(c.pred * (1 << al));
@@ -161,6 +167,7 @@ struct Decoder {
                 if (r < 15) { eobrun = (1 << r) - 1; if (r) eobrun += br.get(r); break; }
                 k += 16;
             } else {
+                if (s > 10) { corrupt("AC coefficient category above 10"); return; }
                 k += r;
                 if (k > 63) break;
                 b[kZigzag[k]] = (int16_t)(extend(br.get(s), s) * (1 << al));
@@ -251,7 +258,7 @@ struct Decoder {
         const uint8_t* q = br.p;
         while (q + 1 < end && !(q[0] == 0xff && q[1] != 0 && q[1] != 0xff && !(q[1] >= 0xd0 && q[1] <= 0xd7))) q++;
         p = q;
-        return true;
+        return !bad_stream;
     }
 
     // ---- islow inverse DCT (13-bit fixed point, two passes) ------------------------------
@@ -339,7 +346,7 @@ struct Decoder {
                 while (s < se_) {
                     const int pq = s[0] >> 4, tq = s[0] & 15;
                     s++;
-                    if (tq > 3) return fail("bad DQT");
+                    if (tq > 3 || pq > 1 || s + (pq ? 128 : 64) > se_) return fail("bad DQT");
                     for (int i = 0; i < 64; i++) {
                         qt[tq][kZigzag[i]] = pq ? (uint16_t)((s[0] << 8) | s[1]) : s[0];
                         s += pq ? 2 : 1;
@@ -348,6 +355,7 @@ struct Decoder {
                 }
             } else if (m == 0xc4) {                                // DHT
                 while (s < se_) {
+                    if (s + 17 > se_) return fail("bad DHT");
                     const int tc = s[0] >> 4, th = s[0] & 15;
                     s++;
                     if (th > 3 || tc > 1) return fail("bad DHT");
@@ -363,21 +371,25 @@ struct Decoder {
                     h.build();
                 }
             } else if (m == 0xc0 || m == 0xc1 || m == 0xc2) {      // SOF0/1/2
+                if (have_frame) return fail("more than one frame header");
+                if (s + 6 > se_) return fail("truncated SOF");
                 progressive = (m == 0xc2);
                 if (s[0] != 8) return fail("only 8-bit JPEG is supported");
                 height = (s[1] << 8) | s[2];
                 width = (s[3] << 8) | s[4];
                 ncomp = s[5];
                 if ((ncomp != 1 && ncomp != 3) || !width || !height) return fail("unsupported JPEG component count");
+                if (s + 6 + 3 * ncomp > se_) return fail("truncated SOF");
                 for (int i = 0; i < ncomp; i++) {
                     comp[i].id = s[6 + 3 * i];
                     comp[i].h = s[7 + 3 * i] >> 4;
                     comp[i].v = s[7 + 3 * i] & 15;
                     comp[i].tq = s[8 + 3 * i];
-                    if (!comp[i].h || !comp[i].v || comp[i].tq > 3) return fail("bad SOF");
+                    if (!comp[i].h || !comp[i].v || comp[i].h > 4 || comp[i].v > 4 || comp[i].tq > 3) return fail("bad SOF");
                     hmax = comp[i].h > hmax ? comp[i].h : hmax;
                     vmax = comp[i].v > vmax ? comp[i].v : vmax;
                 }
+                if ((size_t)width * height > ((size_t)1 << 28)) return fail("JPEG larger than 2^28 pixels");
                 mcus_x = (width + 8 * hmax - 1) / (8 * hmax);
                 mcus_y = (height + 8 * vmax - 1) / (8 * vmax);
                 for (int i = 0; i < ncomp; i++) {
@@ -391,13 +403,15 @@ struct Decoder {
             } else if (m == 0xc3 || (m >= 0xc5 && m <= 0xcf && m != 0xc8 && m != 0xcc)) {
                 return fail("unsupported JPEG process (lossless / hierarchical / arithmetic)");
             } else if (m == 0xdd) {                                // DRI
+                if (s + 2 > se_) return fail("truncated DRI");
                 restart_interval = (s[0] << 8) | s[1];
             } else if (m == 0xee && len >= 14 && !memcmp(s, "Adobe", 5)) {
                 adobe_transform = s[11];
             } else if (m == 0xda) {                                // SOS
                 if (!have_frame) return fail("SOS before SOF");
+                if (s + 1 > se_) return fail("truncated SOS");
                 const int ns = s[0];
-                if (ns < 1 || ns > ncomp) return fail("bad SOS");
+                if (ns < 1 || ns > ncomp || s + 4 + 2 * ns > se_) return fail("bad SOS");
                 int sc[3];
                 for (int i = 0; i < ns; i++) {
                     int ci = -1;
@@ -409,6 +423,18 @@ struct Decoder {
                     sc[i] = ci;
                 }
                 const int ss = s[1 + 2 * ns], se = s[2 + 2 * ns], ah = s[3 + 2 * ns] >> 4, al = s[3 + 2 * ns] & 15;
+                if (progressive) {
+                    // spectral selection / successive approximation of ITU T.81 G.1.1.1: 0 <= Ss <= Se <= 63, a DC scan has
+                    // Se = 0, an AC scan names one component; Al <= 13 keeps 1 << al inside an int16 coefficient
+                    if (ss > se || se > 63 || al > 13 || ah > 13) return fail("bad progressive scan parameters");
+                    if (ss == 0 && se != 0) return fail("progressive DC scan with Se != 0");
+                    if (ss > 0 && ns != 1) return fail("progressive AC scan over several components");
+                }
+                for (int i = 0; i < ns; i++) {
+                    const Component& cc = comp[sc[i]];
+                    if ((!progressive || ss == 0) && !dc[cc.td].present && !(progressive && ah != 0)) return fail("scan uses a missing DC table");
+                    if ((!progressive || ss > 0) && !ac[cc.ta].present) return fail("scan uses a missing AC table");
+                }
                 const uint8_t* q = se_;
                 if (!decode_scan(q, end, ns, sc, progressive ? ss : 0, progressive ? se : 63, progressive ? ah : 0, progressive ? al : 0))
                     return false;
@@ -525,7 +551,12 @@ bool decode_jpeg(const std::vector<uint8_t>& file, Image& out, std::string* why)
     d.data = file.data();
     d.size = file.size();
     memset(d.qt, 0, sizeof(d.qt));
-    if (!d.run(out)) { if (why) *why = d.err; return false; }
+    try {
+        if (!d.run(out)) { if (why) *why = d.err; return false; }
+    } catch (const std::bad_alloc&) {      // a header may announce up to 65535 x 65535 samples
+        if (why) *why = "out of memory while decoding the JPEG";
+        return false;
+    }
     return true;
 }
 

@@ -1504,22 +1504,27 @@ void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const fl
     const int DD = l0.D * l0.D;
     const int max_probes = ((32 + l0.P - 1) / l0.P + 2) * ((8 + l0.P - 1) / l0.P + 2);
     const size_t smem = (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
+    // dynamic shared memory above the 48 KB default must be opted into per kernel AND per device (the attribute is
+    // per-context state); a window that does not fit the SM at all is reported as a launch error by the runtime
+    auto opt_in = [](const void* fn, size_t bytes) {
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
     if (DD == 16 && tiles_per_block > 1) {   // software-pipelined column of tiles (two staging buffers)
         const size_t smem2 = 2 * (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
-        dim3 grid2((tile.w + 31) / 32, ((tile.h + 7) / 8 + tiles_per_block - 1) / tiles_per_block);
-        k_gather_pipe<<<grid2, kBlock, smem2, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, tiles_per_block,
-                                                   counts_in, counts_out, peer);
-        return;
+        if (smem2 <= 200 * 1024) {
+            dim3 grid2((tile.w + 31) / 32, ((tile.h + 7) / 8 + tiles_per_block - 1) / tiles_per_block);
+            opt_in((const void*)k_gather_pipe, smem2);
+            k_gather_pipe<<<grid2, kBlock, smem2, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, tiles_per_block,
+                                                       counts_in, counts_out, peer);
+            return;
+        }
     }
     if (DD == 16) {
+        opt_in((const void*)k_gather<16>, smem);
         k_gather<16><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out, peer);
         return;
     }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    opt_in((const void*)k_gather<0>, smem);
     k_gather<0><<<grid, kBlock, smem, st>>>(cam, l0, tile, origin0, texels0, dirs0, depth, normal, out, max_probes, counts_in, counts_out, peer);
 }
 

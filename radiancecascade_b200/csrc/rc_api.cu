@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -346,6 +347,13 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
     if (N > RC_MAX_LEVELS || D0 < 2 || (D0 & 1) || P0 < 1 || (D0 << (N - 1)) > 4096) {
         c->error = "unsupported cascade parameters (need even D0 >= 2, N <= 10, D_top <= 4096)";
         return RC_ERR_INVALID_ARG;
+    }
+    {   // the gather stages the level-0 probes of a 32x8 pixel tile in shared memory (kernels.cu launch_gather)
+        const size_t max_probes = (size_t)((32 + P0 - 1) / P0 + 2) * ((8 + P0 - 1) / P0 + 2), DD = (size_t)D0 * D0;
+        if (max_probes * ((DD / 2 + 1) * 16 + 16) + DD * 12 > 227u * 1024u) {
+            c->error = "unsupported cascade parameters: the gather's probe window (P0, D0) exceeds 227 KB of shared memory";
+            return RC_ERR_INVALID_ARG;
+        }
     }
     c->N = N;
     c->levels.assign(N, DLevel{});
@@ -686,8 +694,13 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
     if (st == RC_OK) for (auto& e : c->ev_copy_done) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { st = RC_ERR_CUDA; break; }
     if (st == RC_OK) for (auto& e : c->ev_level) if (cudaEventCreate(&e) != cudaSuccess) { st = RC_ERR_CUDA; break; }
     if (st != RC_OK) c->error = "CUDA context / stream creation failed";
-    if (st == RC_OK) st = load_scene(c);
-    if (st == RC_OK) st = setup_frame(c, cfg->width, cfg->height);
+    try {                       // never let an exception (std::bad_alloc from a hostile asset) cross the C ABI
+        if (st == RC_OK) st = load_scene(c);
+        if (st == RC_OK) st = setup_frame(c, cfg->width, cfg->height);
+    } catch (const std::exception& e) {
+        c->error = std::string("rc_create: ") + e.what();
+        st = RC_ERR_SCENE_LOAD;
+    }
     if (st != RC_OK) { g_create_error = c->error; destroy_ctx(c); return st; }
     {   // tuning knobs (A/B runs): RC_MARCH_MAP = one char per level, L linear / D direction tile / P probe tile
         const char* mm = getenv("RC_MARCH_MAP");
@@ -749,6 +762,10 @@ rc_status rc_resize(rc_ctx* c, uint32_t width, uint32_t height)
     c->cfg.width = width; c->cfg.height = height;
     c->cfg.tile_w = c->cfg.tile_h = 0;   // a resize resets the tile to the full frame
     c->have_camera = false;              // aspect changed: the caller must rc_update (Projection::resize)
+    // the peer exchange buffers were sized for the old frame (rc_peer_export) and every rank's mapping of them is
+    // stale: detach, so that the gather cannot store a larger frame into them; the caller re-exports / re-attaches
+    peer_release(c);
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     return setup_frame(c, width, height);
 }
 
@@ -938,6 +955,7 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
     const DLevel& L0 = c->levels[0];
     PeerOut po{};
     if (c->peer.world) {
+        if ((size_t)c->W * c->H * sizeof(uint2) > c->peer.slot_bytes) { c->error = "peer frame buffers are smaller than the frame (re-export after a resize)"; return RC_ERR_STATE; }
         c->peer.seq++;
         po.world = c->peer.world; po.rank = c->peer.rank; po.W = (int)c->W; po.seq = c->peer.seq;
         for (int r = 0; r < c->peer.world; r++) { po.frame[r] = c->peer.frame(r, c->peer.seq); po.ctrl[r] = c->peer.ctrl(r); }
@@ -1370,7 +1388,13 @@ rc_status rc_scene_load(const char* obj_path, uint32_t flags, rc_scene** out)
     if (!obj_path || !out) return RC_ERR_INVALID_ARG;
     *out = nullptr;
     rc_scene* s = new rc_scene();
-    rc_status st = load_host_scene(obj_path, flags, s);
+    rc_status st;
+    try {
+        st = load_host_scene(obj_path, flags, s);
+    } catch (const std::exception& e) {
+        s->error = std::string("rc_scene_load: ") + e.what();
+        st = RC_ERR_SCENE_LOAD;
+    }
     if (st != RC_OK) { g_create_error = s->error; delete s; return st; }
     *out = s;
     return RC_OK;
@@ -1404,7 +1428,12 @@ rc_status rc_decode_image_file(const char* path, uint8_t* rgba, size_t bytes, ui
 {
     if (!path) return RC_ERR_INVALID_ARG;
     std::string why;
-    std::shared_ptr<Image> img = load_image_rgba8(path, &why);
+    std::shared_ptr<Image> img;
+    try {
+        img = load_image_rgba8(path, &why);
+    } catch (const std::exception& e) {
+        why = e.what();
+    }
     if (!img) { g_create_error = why; return RC_ERR_SCENE_LOAD; }
     if (width) *width = img->width;
     if (height) *height = img->height;

@@ -152,6 +152,86 @@ def test_synthetic_jpeg_variants(tmp_path, mode, subsampling, progressive, size)
     assert np.array_equal(decode_image_file(p), _pil_rgba(p))
 
 
+def test_hostile_jpeg_headers_are_rejected(tmp_path):
+    """Textures come from untrusted MTL paths: scans with out-of-range spectral selection / successive approximation,
+    truncated DQT / SOF / DRI segments and impossible coefficient categories must fail cleanly (RcError), never write
+    outside the 64-coefficient block (heap overwrite through Se > 63 in a refinement scan)."""
+    from PIL import Image
+    from radiancecascade_b200.renderer import decode_image_file
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    good = str(tmp_path / "good.jpg")
+    Image.fromarray(img, "RGB").save(good, "JPEG", quality=80, progressive=True)
+    data = bytearray(open(good, "rb").read())
+    assert decode_image_file(good).shape == (48, 64, 4)
+
+    def segments(buf):
+        i = 2
+        while i + 4 <= len(buf):
+            assert buf[i] == 0xFF
+            m = buf[i + 1]
+            ln = (buf[i + 2] << 8) | buf[i + 3]
+            yield i, m, ln
+            if m == 0xDA:
+                j = i + 2 + ln          # skip the entropy-coded data
+                while j + 1 < len(buf) and not (buf[j] == 0xFF and buf[j + 1] not in (0, 0xFF) and not 0xD0 <= buf[j + 1] <= 0xD7):
+                    j += 1
+                i = j
+            else:
+                i += 2 + ln
+
+    sos = [(i, ln) for i, m, ln in segments(data) if m == 0xDA]
+    assert len(sos) >= 4
+    bad = []
+    for k, (i, ln) in enumerate(sos):
+        ns = data[i + 4]
+        ss_at = i + 5 + 2 * ns
+        if data[ss_at] > 0 and data[ss_at + 2] >> 4:       # an AC refinement scan: Se -> 255
+            b = bytearray(data); b[ss_at + 1] = 255; bad.append(("se255_refine", b)); break
+    for k, (i, ln) in enumerate(sos):
+        ns = data[i + 4]
+        ss_at = i + 5 + 2 * ns
+        if data[ss_at] > 0:                                 # first AC scan: Se -> 200, and Ss > Se
+            b = bytearray(data); b[ss_at + 1] = 200; bad.append(("se200", b))
+            b = bytearray(data); b[ss_at] = 40; b[ss_at + 1] = 10; bad.append(("ss_gt_se", b))
+            b = bytearray(data); b[ss_at + 2] = 0x0F; bad.append(("al15", b))
+            break
+    i, ln = sos[0]
+    b = bytearray(data); b[i + 5 + 2 * data[i + 4] + 1] = 5; bad.append(("dc_scan_se5", b))
+    for i, m, ln in segments(data):
+        if m == 0xDB:
+            b = bytearray(data); b[i + 2:i + 4] = (10).to_bytes(2, "big"); del b[i + 12:i + 2 + ln]; bad.append(("short_dqt", b)); break
+    for i, m, ln in segments(data):
+        if m == 0xC2:
+            b = bytearray(data); b[i + 2:i + 4] = (4).to_bytes(2, "big"); del b[i + 6:i + 2 + ln]; bad.append(("short_sof", b))
+            b = bytearray(data); b[i + 5:i + 9] = bytes([0xFF, 0xFF, 0xFF, 0xFF]); bad.append(("huge_sof", b)); break
+    assert len(bad) >= 7
+    for name, b in bad:
+        q = str(tmp_path / f"{name}.jpg")
+        open(q, "wb").write(bytes(b))
+        with pytest.raises(rc.RcError):
+            decode_image_file(q)
+    # truncation anywhere must never crash: either a clean error or a (partially grey) image
+    for cut in range(20, len(data), max(1, len(data) // 97)):
+        q = str(tmp_path / "cut.jpg")
+        open(q, "wb").write(bytes(data[:cut]))
+        try:
+            decode_image_file(q)
+        except rc.RcError:
+            pass
+    # random byte corruption of the entropy-coded segments / tables: same requirement
+    for t in range(60):
+        b = bytearray(data)
+        for _ in range(4):
+            b[int(rng.integers(2, len(b)))] = int(rng.integers(0, 256))
+        q = str(tmp_path / "fuzz.jpg")
+        open(q, "wb").write(bytes(b))
+        try:
+            decode_image_file(q)
+        except rc.RcError:
+            pass
+
+
 def test_png_variants(tmp_path):
     from PIL import Image
     from radiancecascade_b200.renderer import decode_image_file
