@@ -1205,6 +1205,260 @@ __global__ void __launch_bounds__(kBlock) k_gather_pipe(DCamera cam, DLevel l0, 
     }
 }
 
+// ------------------------------------------------------------------ gather on the tensor cores (default D0 = 4, P0 = 4)
+// The 16 pixels x in [4bx+2, 4bx+6), y in [4by+2, 4by+6) of a "cell" interpolate between the same four level-0 probes
+// (S1), so S9 for a cell is a small dense contraction:  X_k[pixel][ch] = sum_d cs_d[pixel] * c_k,d[ch]  for each of the
+// four probes k, then E[pixel] = sum_k a_k[pixel] * X_k[pixel]  with  a_k = (w_k / S) * (pi / C).  The cascade texels
+// already ARE float16, so the inner sum is mma.sync.m16n8k16 (f16 x f16 -> f32) with the probe's 128 bytes used as the
+// B operand exactly as they lie in memory:
+//   B  rows k' = 0..7:  the probe's 16-byte rows (texel pair 2k', 2k'+1; 8 halves = r g b a r g b a), read with one
+//      ldmatrix.x4.trans per cell (the four probes = the four 8x8 matrices);  rows 8..15: the same rows with the halves
+//      rotated by four (the value the lane 16 away holds -> one shuffle), so the ODD texel of a pair lands in columns 0..3
+//   A  cols 0..7 = cs of the even texels, cols 8..15 = cs of the odd texels, rounded to float16 (the only rounding that
+//      differs from the scalar kernels; S10's tolerance covers it: |dE| <= 2^-11 * E)
+//   C  columns 0..3 = X_k (r, g, b, a); the thread pair (lane&3) in {0, 1} owns them and finishes E in float32.
+// 8 warp-level MMAs + ~40 other instructions replace the 192 FFMA + 128 half->float conversions + 32 LDS.128 that every
+// pixel of k_gather spends on the same sums (ncu: 821 warp-instructions per 32 pixels, issue-bound).
+// Per-pixel terms (hit point, decoded normal, the four plane weights, the 16 cosines) are computed by the lane that owns
+// the pixel (two cells = 32 pixels per warp) and handed to the fragment owners through shared memory.  The per-pixel
+// reciprocals (1/(1 + K h^2/l2), 1/S, pi/C) and the ray normalisation use the SFU approximations (2 ulp): none of them
+// feeds an index table, and S10 bounds the irradiance error.  The decoded normal and the cosines use the exact expressions
+// of S9 — the culling masks (k_gbuffer) are derived from the very same values.
+// Staging: the probe window of a block's 8x2 cells (<= 9 x 3 probes, rows contiguous in the probe-major cascade) is
+// fetched by ONE thread with cp.async.bulk (TMA, 1-D) into shared memory, completion on an mbarrier, double-buffered
+// along the column of tiles the block walks — no per-thread copy instructions, no registers.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RC_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RC_MBAR_DONE;\n"
+        "bra RC_MBAR_WAIT;\n"
+        "RC_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
+{
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct Dirs16 { float v[48]; };   // level-0 directions, by value in the kernel parameter block (constant bank)
+
+constexpr int kGmCellsX = 8, kGmCellsY = 2;                        // cells per block tile: 32 x 8 pixels, 8 warps x 2 cells
+constexpr int kGmCols = kGmCellsX + 1, kGmRows = kGmCellsY + 1;    // probe window of a tile
+
+struct GatherMmaSmem {
+    uint4 tex[2][kGmRows * kGmCols * 8];      // [buffer][probe][8 rows of 16 bytes]
+    float4 org[2][kGmRows * kGmCols];
+    uint4 cs_lo[256];                         // per pixel: halves cs0 cs2 cs1 cs3 | cs4 cs6 cs5 cs7
+    uint4 pad;                                // 64 bytes between the two arrays: lo -> banks 0..15, hi -> 16..31
+    uint4 pad2[3];
+    uint4 cs_hi[256];                         //            cs8 cs10 cs9 cs11 | cs12 cs14 cs13 cs15
+    float4 a[256];                            // a_k = (w_k / S) * (pi / C)
+    float alpha[256];
+    unsigned long long bar[2];
+};
+
+template <bool SYM>
+__global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, TileRect tile, Dirs16 dirs, const float* __restrict__ axis_nx,
+                                                    const float* __restrict__ axis_ny, const float4* __restrict__ origin0,
+                                                    const uint2* __restrict__ texels0, const float* __restrict__ depth,
+                                                    const uint32_t* __restrict__ normal, uint2* __restrict__ out, int cbx0, int cby0,
+                                                    int nsteps_total, int steps_per_block, unsigned int* __restrict__ counts_in,
+                                                    unsigned int* __restrict__ counts_out, PeerOut peer)
+{
+    extern __shared__ __align__(128) unsigned char gm_raw[];
+    GatherMmaSmem& sm = *reinterpret_cast<GatherMmaSmem*>(gm_raw);
+    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) {   // see k_gather
+        counts_out[threadIdx.x] = counts_in[threadIdx.x];
+        counts_in[threadIdx.x] = 0u;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bxB = cbx0 + blockIdx.x * kGmCellsX;                           // first cell column of this block
+    const int step0 = blockIdx.y * steps_per_block;
+    const int nsteps = min(steps_per_block, nsteps_total - step0);          // block-uniform
+    // probes the context holds (a multi-GPU tile holds a sub-grid; every probe a pixel of the tile needs is inside it)
+    const int pxlo = l0.px0, pxhi = l0.px0 + l0.sw - 1, pylo = l0.py0, pyhi = l0.py0 + l0.sh - 1;
+    auto clampx = [&](int v) { return min(max(min(max(v, 0), l0.gw - 1), pxlo), pxhi); };
+    auto clampy = [&](int v) { return min(max(min(max(v, 0), l0.gh - 1), pylo), pyhi); };
+    const int pc_lo = clampx(bxB), ncols = clampx(bxB + kGmCellsX) - pc_lo + 1;
+
+    auto issue = [&](int s) {   // one thread: TMA bulk copies of step s's probe rows into buffer s & 1
+        const int byS = cby0 + (step0 + s) * kGmCellsY;
+        const int pr_lo = clampy(byS), nrows = clampy(byS + kGmCellsY) - pr_lo + 1;
+        const int b = s & 1;
+        mbar_expect_tx(&sm.bar[b], (unsigned)(nrows * ncols * 144));
+        for (int r = 0; r < nrows; r++) {
+            const size_t p0 = (size_t)(pr_lo + r - l0.py0) * l0.sw + (pc_lo - l0.px0);
+            bulk_g2s(&sm.tex[b][r * kGmCols * 8], texels0 + p0 * 16, (unsigned)(ncols * 128), &sm.bar[b]);
+            bulk_g2s(&sm.org[b][r * kGmCols], origin0 + p0, (unsigned)(ncols * 16), &sm.bar[b]);
+        }
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && nsteps > 0) issue(0);
+
+    // this warp's two cells and this lane's pixel in them
+    const int c = lane >> 4, m = lane & 15, mx = m & 3, my = m >> 2;
+    const int bx_own = bxB + 2 * (warp & 3) + c;                    // cell column of the pixel this lane owns
+    const int x = 4 * bx_own + 2 + mx;
+    const bool x_in = x >= tile.x0 && x < tile.x0 + tile.w;
+    const float nx = x_in ? __ldg(axis_nx + x) : 0.0f;
+    const float fx = (float)mx * 0.25f, fy = (float)my * 0.25f;     // S1: f = ((x - P/2) mod P) / P, exact
+    const float bil[4] = {(1.0f - fx) * (1.0f - fy), fx * (1.0f - fy), (1.0f - fx) * fy, fx * fy};
+    const int g = lane >> 2, j = lane & 3;
+    const int rec = warp * 32;
+
+    for (int s = 0; s < nsteps; s++) {
+        if (threadIdx.x == 0 && s + 1 < nsteps) issue(s + 1);       // buffer (s+1)&1 was released by the barrier that ended step s-1
+        const int b = s & 1;
+        const int byS = cby0 + (step0 + s) * kGmCellsY;
+        const int by = byS + (warp >> 2);
+        const int pr_lo = clampy(byS);
+        mbar_wait(&sm.bar[b], (unsigned)((s >> 1) & 1));
+        const uint4* s_tex = sm.tex[b];
+        const float4* s_org = sm.org[b];
+
+        // ---- phase 1: per-pixel terms, one lane per pixel
+        {
+            const int y = 4 * by + 2 + my;
+            const bool inside = x_in && y >= tile.y0 && y < tile.y0 + tile.h;
+            const size_t o = inside ? (size_t)(y - tile.y0) * tile.w + (x - tile.x0) : 0;
+            const float dep = inside ? depth[o] : -1.0f;
+            float cs[16];
+            float4 ak = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < 16; d++) cs[d] = 0.0f;
+            if (dep >= 0.0f) {
+                const float ny = __ldg(axis_ny + y);
+                const float3 q = f3(fmaf(nx, cam.dx.x, fmaf(ny, cam.dy.x, cam.dc.x)), fmaf(nx, cam.dx.y, fmaf(ny, cam.dy.y, cam.dc.y)),
+                                    fmaf(nx, cam.dx.z, fmaf(ny, cam.dy.z, cam.dc.z)));
+                const float rl = rsqrtf(vdot(q, q));
+                const float3 hp = vfma(dep * rl, q, cam.eye);
+                const float3 n = oct_decode(normal[o]);
+                const int lx0 = clampx(bx_own) - pc_lo, lx1 = clampx(bx_own + 1) - pc_lo;
+                const int ly0 = clampy(by) - pr_lo, ly1 = clampy(by + 1) - pr_lo;
+                const int lk[4] = {ly0 * kGmCols + lx0, ly0 * kGmCols + lx1, ly1 * kGmCols + lx0, ly1 * kGmCols + lx1};
+                float w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float4 ok = s_org[lk[k]];
+                    const float3 delta = vsub(xyz(ok), hp);
+                    const float l2 = vdot(delta, delta), hh = vdot(n, delta);
+                    // S8: 1 / (1 + K h^2 / l2) == l2 / (l2 + K h^2)
+                    const float gk = l2 > 0.0f ? l2 * fast_rcp(fmaf(RC_PLANE_K * hh, hh, l2)) : 1.0f;
+                    w[k] = ok.w != 0.0f ? bil[k] * gk : 0.0f;
+                }
+                const float S = ((w[0] + w[1]) + w[2]) + w[3];
+                if (SYM) {
+                    // the S3 table for D = 4 is point-symmetric: w_d' = -w_d for the pairs below (checked on the host), and
+                    // dot(n, -w) == -dot(n, w) exactly, so 8 dot products give all 16 cosines
+#define RC_CS_PAIR(A, B)                                                                                          \
+    {                                                                                                             \
+        const float dt = vdot(n, f3(dirs.v[3 * (A)], dirs.v[3 * (A) + 1], dirs.v[3 * (A) + 2]));                   \
+        cs[A] = fmaxf(dt, 0.0f);                                                                                  \
+        cs[B] = fmaxf(-dt, 0.0f);                                                                                 \
+    }
+                    RC_CS_PAIR(5, 15) RC_CS_PAIR(6, 12) RC_CS_PAIR(9, 3) RC_CS_PAIR(10, 0)
+                    RC_CS_PAIR(1, 14) RC_CS_PAIR(2, 13) RC_CS_PAIR(4, 11) RC_CS_PAIR(7, 8)
+#undef RC_CS_PAIR
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 16; d++) cs[d] = fmaxf(vdot(n, f3(dirs.v[3 * d], dirs.v[3 * d + 1], dirs.v[3 * d + 2])), 0.0f);
+                }
+                float C = 0.0f;
+#pragma unroll
+                for (int d = 0; d < 16; d++) C = C + cs[d];
+                const float SC = S * C;
+                const float qs = SC > 0.0f ? RC_PI_F * fast_rcp(SC) : 0.0f;      // (1/S) * (pi/C)
+                ak = make_float4(w[0] * qs, w[1] * qs, w[2] * qs, w[3] * qs);
+            }
+            sm.cs_lo[rec + lane] = make_uint4(pack_h2(cs[0], cs[2]), pack_h2(cs[1], cs[3]), pack_h2(cs[4], cs[6]), pack_h2(cs[5], cs[7]));
+            sm.cs_hi[rec + lane] = make_uint4(pack_h2(cs[8], cs[10]), pack_h2(cs[9], cs[11]), pack_h2(cs[12], cs[14]), pack_h2(cs[13], cs[15]));
+            sm.a[rec + lane] = ak;
+            sm.alpha[rec + lane] = dep >= 0.0f ? 1.0f : 0.0f;
+        }
+        __syncwarp();
+
+        // ---- phase 2: two cells per warp, four MMAs each
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int bx = bxB + 2 * (warp & 3) + cc;
+            const int r0 = rec + cc * 16 + g, r1 = r0 + 8;          // pixel records of fragment rows g and g + 8
+            const uint2* csrc0 = reinterpret_cast<const uint2*>(j < 2 ? &sm.cs_lo[r0] : &sm.cs_hi[r0]) + (j & 1);
+            const uint2* csrc1 = reinterpret_cast<const uint2*>(j < 2 ? &sm.cs_lo[r1] : &sm.cs_hi[r1]) + (j & 1);
+            const uint2 A0 = *csrc0, A1 = *csrc1;                   // .x: even texels 4j, 4j+2;  .y: odd texels 4j+1, 4j+3
+            const float4 a0 = sm.a[r0], a1 = sm.a[r1];
+            // ldmatrix: lane l supplies the address of row (l & 7) of matrix (l >> 3) = probe (l >> 3) of the cell
+            const int q = lane >> 3;
+            const int lxq = clampx(bx + (q & 1)) - pc_lo, lyq = clampy(by + (q >> 1)) - pr_lo;
+            const unsigned addr = smem_u32(&s_tex[(lyq * kGmCols + lxq) * 8 + (lane & 7)]);
+            uint32_t bq[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(bq[0]), "=r"(bq[1]), "=r"(bq[2]), "=r"(bq[3]) : "r"(addr));
+            float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+            const float wa[4] = {a0.x, a0.y, a0.z, a0.w}, wb[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t brot = __shfl_xor_sync(0xffffffffu, bq[k], 16);   // the same rows, halves rotated by four
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                             : "r"(A0.x), "r"(A1.x), "r"(A0.y), "r"(A1.y), "r"(bq[k]), "r"(brot));
+                e0 = fmaf(wa[k], c0, e0); e1 = fmaf(wa[k], c1, e1);
+                e2 = fmaf(wb[k], c2, e2); e3 = fmaf(wb[k], c3, e3);
+            }
+            // ---- phase 3: lanes j = 0 (r, g) and j = 1 (b, alpha) store fragment rows g and g + 8
+            if (j < 2) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int mm = g + 8 * h;
+                    const int px = 4 * bx + 2 + (mm & 3), py = 4 * by + 2 + (mm >> 2);
+                    if (px < tile.x0 || px >= tile.x0 + tile.w || py < tile.y0 || py >= tile.y0 + tile.h) continue;
+                    const float al = sm.alpha[rec + cc * 16 + mm];
+                    const float va = h ? e2 : e0, vb = h ? e3 : e1;
+                    // pixels without geometry have a_k = 0 -> E = 0, alpha 0: (0,0,0,0) as S9 demands
+                    const uint32_t v = pack_h2(fminf(va, 65504.0f), j == 0 ? fminf(vb, 65504.0f) : al);
+                    const size_t o = (size_t)(py - tile.y0) * tile.w + (px - tile.x0);
+                    reinterpret_cast<uint32_t*>(out + o)[j] = v;
+                    if (peer.world) {   // fused final-image exchange, see k_gather
+                        const size_t fo = (size_t)py * peer.W + px;
+                        for (int d = 0; d < peer.world; d++) reinterpret_cast<uint32_t*>(peer.frame[d] + fo)[j] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // every warp is done with buffer s & 1 (step s + 2 overwrites it) and with its pixel records
+    }
+}
+
 // ------------------------------------------------------------------ peer-memory frame exchange (tiled multi-GPU)
 // Control block of a rank (uint32 words, in its IPC-shared allocation): [kPeerArrived + r] = last frame rank r has
 // delivered into THIS rank's frame buffers; [kPeerReleased + r] = last frame rank r has finished consuming (so that
@@ -1496,12 +1750,43 @@ void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* 
     k_merge<<<blocks_for(n), kBlock, 0, st>>>(lv, up.D, sky, origin, texels, up_avg, link_idx, link_w);
 }
 
+// The pairs of antipodal level-0 directions k_gather_mma<true> relies on (S3 table, D = 4)
+bool gather_dirs_symmetric(const float* d)
+{
+    static const int pairs[8][2] = {{5, 15}, {6, 12}, {9, 3}, {10, 0}, {1, 14}, {2, 13}, {4, 11}, {7, 8}};
+    for (auto& pr : pairs)
+        for (int k = 0; k < 3; k++)
+            if (!(d[3 * pr[0] + k] == -d[3 * pr[1] + k])) return false;   // +0 == -0: only the sign of a zero may differ
+    return true;
+}
+
+static inline int floor_div_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
                    const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
-                   unsigned int* counts_out, const PeerOut& peer, int tiles_per_block, cudaStream_t st)
+                   unsigned int* counts_out, const PeerOut& peer, int tiles_per_block, const GatherMma& mma, cudaStream_t st)
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
     const int DD = l0.D * l0.D;
+    if (mma.enabled && DD == 16 && l0.P == 4 && mma.dirs0_host && mma.axis_nx && mma.axis_ny) {
+        // cells of the global 4x4-pixel cell grid (origin at pixel (2, 2)) the tile touches
+        const int cbx0 = floor_div_i(tile.x0 - 2, 4), cbx1 = floor_div_i(tile.x0 + tile.w - 1 - 2, 4);
+        const int cby0 = floor_div_i(tile.y0 - 2, 4), cby1 = floor_div_i(tile.y0 + tile.h - 1 - 2, 4);
+        const int ncx = cbx1 - cbx0 + 1, ncy = cby1 - cby0 + 1;
+        const int nsteps = (ncy + kGmCellsY - 1) / kGmCellsY;
+        const int spb = tiles_per_block > 0 ? tiles_per_block : 1;
+        dim3 g2((ncx + kGmCellsX - 1) / kGmCellsX, (nsteps + spb - 1) / spb);
+        Dirs16 dv;
+        for (int k = 0; k < 48; k++) dv.v[k] = mma.dirs0_host[k];
+        const size_t smem = sizeof(GatherMmaSmem);
+        if (mma.symmetric)
+            k_gather_mma<true><<<g2, 256, smem, st>>>(cam, l0, tile, dv, mma.axis_nx, mma.axis_ny, origin0, texels0, depth, normal, out, cbx0, cby0,
+                                                      nsteps, spb, counts_in, counts_out, peer);
+        else
+            k_gather_mma<false><<<g2, 256, smem, st>>>(cam, l0, tile, dv, mma.axis_nx, mma.axis_ny, origin0, texels0, depth, normal, out, cbx0, cby0,
+                                                       nsteps, spb, counts_in, counts_out, peer);
+        return;
+    }
     const int max_probes = ((32 + l0.P - 1) / l0.P + 2) * ((8 + l0.P - 1) / l0.P + 2);
     const size_t smem = (size_t)max_probes * ((DD / 2 + 1) * 16 + 16) + (size_t)DD * 3 * sizeof(float);
     // dynamic shared memory above the 48 KB default must be opted into per kernel AND per device (the attribute is

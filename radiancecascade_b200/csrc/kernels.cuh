@@ -91,10 +91,15 @@ int march_persist_blocks_per_sm();
 void launch_fill_top(const DLevel& lv, float3 sky, const float4* origin, uint2* texels, float4* avg_out, cudaStream_t st);
 void launch_merge(const DLevel& lv, const DLevel& up, float3 sky, const float4* origin, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, cudaStream_t st);
+// Tensor-core gather (k_gather_mma; D0 = 4, P0 = 4 only): dirs0_host = the level-0 direction table on the host (it travels in
+// the kernel parameter block), axis_nx / axis_ny = device tables of S4's nx(x), ny(y) for the full frame, symmetric =
+// gather_dirs_symmetric(dirs0_host).  enabled = 0 (or other cascade parameters) selects the scalar kernels.
+struct GatherMma { int enabled; int symmetric; const float* dirs0_host; const float* axis_nx; const float* axis_ny; };
+bool gather_dirs_symmetric(const float* dirs0_host);
 // tiles_per_block > 1 (and D0 = 4): software-pipelined variant, a block walks a column of that many 32x8 pixel tiles
 void launch_gather(const DCamera& cam, const DLevel& l0, TileRect tile, const float4* origin0, const uint2* texels0,
                    const float* dirs0, const float* depth, const uint32_t* normal, uint2* out, unsigned int* counts_in,
-                   unsigned int* counts_out, const PeerOut& peer, int tiles_per_block, cudaStream_t st);
+                   unsigned int* counts_out, const PeerOut& peer, int tiles_per_block, const GatherMma& mma, cudaStream_t st);
 void launch_peer_begin(const PeerOut& peer, uint32_t* my_ctrl, cudaStream_t st);
 void launch_peer_publish(const PeerOut& peer, cudaStream_t st);
 void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t st);

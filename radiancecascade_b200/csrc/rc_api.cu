@@ -137,6 +137,10 @@ struct rc_ctx {
         const size_t t = (size_t)((tile.w + 31) / 32) * ((tile.h + 7) / 8);
         return t >= 16384 ? 4 : 2;
     }
+    // k_gather_mma (tensor-core gather, D0 = 4 and P0 = 4): 1 = default, 0 = the scalar kernels (A/B, exact S9 arithmetic)
+    int gather_mma = 1;
+    bool gather_sym = false;                        // the level-0 direction table is point-symmetric (gather_dirs_symmetric)
+    DevBuf<float> d_axis;                           // S4: nx(x) for x < W, then ny(y) for y < H
     // rc_render records the frame's ~18 launches into a CUDA graph (stream capture) and submits it with ONE
     // cudaGraphLaunch; every frame is re-captured and the executable graph updated in place
     // (cudaGraphExecUpdate: camera, lights, grid sizes and the output slot are node parameters).
@@ -415,6 +419,13 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
     if (!c->h_ray_count) CU_OK(c, cudaHostAlloc((void**)&c->h_ray_count, RC_MAX_LEVELS * sizeof(unsigned int), cudaHostAllocMapped));
     for (uint32_t i = 0; i < RC_MAX_LEVELS; i++) c->h_ray_count[i] = 0xffffffffu;
     CU_OK(c, c->d_dirs.upload(all_dirs));
+    {   // S4's per-column / per-row terms, evaluated once with the very expressions primary_dir uses
+        std::vector<float> axis((size_t)W + H);
+        for (uint32_t x = 0; x < W; x++) axis[x] = (float)(2 * (int)x + 1) / (float)(int)W - 1.0f;
+        for (uint32_t y = 0; y < H; y++) axis[(size_t)W + y] = 1.0f - (float)(2 * (int)y + 1) / (float)(int)H;
+        CU_OK(c, c->d_axis.upload(axis));
+        c->gather_sym = c->levels[0].D == 4 && gather_dirs_symmetric(c->dirs_host[0].data());
+    }
     {
         std::vector<float4> q(2 * (all_dirs.size() / 3));
         auto safe_inv = [](float d) { return 1.0f / (std::fabs(d) > 1e-20f ? d : std::copysign(1e-20f, d)); };   // rc_device.cuh safe_inv
@@ -640,7 +651,7 @@ void destroy_ctx(rc_ctx* c)
     if (c->h_ray_count) cudaFreeHost(c->h_ray_count);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     peer_release(c); c->d_ray_count.release();
-    c->d_dirs.release(); c->d_dirq.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
+    c->d_dirs.release(); c->d_dirq.release(); c->d_axis.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_frame_done) cudaEventDestroy(c->ev_frame_done);
@@ -723,6 +734,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
         if (const char* e = getenv("RC_COPY_BLOCKS")) c->copy_blocks = atoi(e) < 0 ? 0 : (atoi(e) > 1024 ? 1024 : atoi(e));
         if (const char* e = getenv("RC_LIST_DIRMAJOR")) c->list_dir_major = (int)strtol(e, nullptr, 0);
+        if (const char* e = getenv("RC_GATHER_MMA")) c->gather_mma = atoi(e) != 0;
         if (const char* e = getenv("RC_GATHER_TILES")) c->gather_tiles = atoi(e) < 0 ? 0 : (atoi(e) > 64 ? 64 : atoi(e));
         if (const char* e = getenv("RC_GRAPH")) c->use_graph = atoi(e) != 0;
         cudaDeviceProp prop;
@@ -920,6 +932,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "march_batch" && value >= 0 && value <= 1) c->march_batch = value;
     else if (k == "cull" && value >= 0 && value <= 1) c->cull = value;
     else if (k == "gather_tiles" && value >= 0 && value <= 64) c->gather_tiles = value;
+    else if (k == "gather_mma" && value >= 0 && value <= 1) c->gather_mma = value;
     else if (k == "need_pdl" && value >= 0 && value <= 1) c->need_pdl = value;
     else if (k == "copy_blocks" && value >= 0 && value <= 1024) c->copy_blocks = value;
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
@@ -963,7 +976,8 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
         c->launches++;
     }
     launch_gather(c->cam, L0, c->tile, c->d_origin.p + L0.probe_offset, c->d_cascade.p + L0.texel_offset, c->d_dirs.p,
-                  c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, po, c->gather_tiles_eff(), st);
+                  c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, po, c->gather_tiles_eff(),
+                  GatherMma{c->gather_mma, c->gather_sym ? 1 : 0, c->dirs_host[0].data(), c->d_axis.p, c->d_axis.p + c->W}, st);
     c->launches++;
     if (c->peer.world) {
         launch_peer_publish(po, st);

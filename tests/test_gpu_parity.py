@@ -361,6 +361,40 @@ def test_pipelined_gather_equals_classic(name, W, H, tiles):
 
 
 @pytest.mark.culled
+@pytest.mark.parametrize("name,W,H,tile", [("cube", 200, 120, None), ("test_room", 333, 77, None), ("teapot", 256, 256, (37, 21, 150, 99)),
+                                           ("living_room", 480, 270, (2, 2, 4, 4)), ("living_room", 480, 270, (476, 266, 4, 4)),
+                                           ("sonic", 97, 131, None)])
+def test_tensor_core_gather_matches_scalar_gather(name, W, H, tile):
+    """k_gather_mma (default for D0 = 4, P0 = 4: the per-cell contraction on mma.sync with float16 cosines, SFU reciprocals,
+    probes staged by TMA bulk copies) against the scalar kernels that evaluate S9 operation for operation.  The only
+    roundings that differ are the float16 cosines (2^-11 relative) and 2-ulp reciprocals: |dE| <= 2e-3 * peak, alpha equal,
+    and the result does not depend on how many tiles a block walks."""
+    st, _, _ = frame_setup(name, W, H)
+    cc = rc.CascadeConfig(tile=tile) if tile else None
+    r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name), cc)
+    r.update(st)
+    out = {}
+    for mma, tiles in ((0, 1), (1, 1), (1, 3), (1, 64)):
+        r.set_tuning("gather_mma", mma)
+        r.set_tuning("gather_tiles", tiles)
+        r.render()
+        out[(mma, tiles)] = r.read_target(_ffi.RC_TARGET_IRRADIANCE).copy()
+    ref = half_to_f32(out[(0, 1)])
+    peak = float(ref[..., :3].max())
+    got = half_to_f32(out[(1, 1)])
+    assert np.array_equal(got[..., 3], ref[..., 3])
+    if name != "living_room" or tile is None:
+        assert peak > 0
+    assert float(np.abs(got[..., :3] - ref[..., :3]).max()) <= 2e-3 * max(peak, 1e-6)
+    assert np.array_equal(out[(1, 1)].view(np.uint16), out[(1, 3)].view(np.uint16))
+    assert np.array_equal(out[(1, 1)].view(np.uint16), out[(1, 64)].view(np.uint16))
+    if tile:    # a screen-space tile is the crop of the full frame, bit for bit (cells are anchored to the frame)
+        full = render_product(name, W, H, st).read_target(_ffi.RC_TARGET_IRRADIANCE)
+        x0, y0, w, h = tile
+        assert np.array_equal(out[(1, 1)].view(np.uint16), full[y0:y0 + h, x0:x0 + w].view(np.uint16))
+
+
+@pytest.mark.culled
 @pytest.mark.parametrize("name,W,H", [("living_room", 480, 270), ("teapot", 384, 216), ("cube", 130, 94)])
 def test_ray_list_order_and_need_pdl_do_not_change_the_frame(name, W, H):
     """The per-level ray lists are sets: ordering each warp's share direction-major (k_need dir_major, so that k_march
