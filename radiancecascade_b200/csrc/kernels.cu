@@ -1273,11 +1273,11 @@ constexpr int kGmCols = kGmCellsX + 1, kGmRows = kGmCellsY + 1;    // probe wind
 struct GatherMmaSmem {
     uint4 tex[2][kGmRows * kGmCols * 8];      // [buffer][probe][8 rows of 16 bytes]
     float4 org[2][kGmRows * kGmCols];
-    uint4 cs_lo[256];                         // per pixel: halves cs0 cs2 cs1 cs3 | cs4 cs6 cs5 cs7
-    uint4 pad;                                // 64 bytes between the two arrays: lo -> banks 0..15, hi -> 16..31
-    uint4 pad2[3];
-    uint4 cs_hi[256];                         //            cs8 cs10 cs9 cs11 | cs12 cs14 cs13 cs15
-    float4 a[256];                            // a_k = (w_k / S) * (pi / C)
+    // A operands, one 16-byte record per (warp, cell, fragment row g, lane-in-quad j), stored at slot j ^ ((g >> 1) & 3):
+    //   .x = cs halves (4j, 4j+2) of pixel row g, .y = the same of row g + 8, .z / .w = halves (4j+1, 4j+3) of rows g / g + 8
+    // — exactly the four registers mma.m16n8k16 wants, so the fragment owner fetches them with one LDS.128
+    uint4 afrag[8 * 2 * 8 * 4];
+    float4 a[256];                            // a_k = (w_k / S) * (pi / C) per pixel
     float alpha[256];
     unsigned long long bar[2];
 };
@@ -1301,9 +1301,10 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
     const int step0 = blockIdx.y * steps_per_block;
     const int nsteps = min(steps_per_block, nsteps_total - step0);          // block-uniform
     // probes the context holds (a multi-GPU tile holds a sub-grid; every probe a pixel of the tile needs is inside it)
-    const int pxlo = l0.px0, pxhi = l0.px0 + l0.sw - 1, pylo = l0.py0, pyhi = l0.py0 + l0.sh - 1;
-    auto clampx = [&](int v) { return min(max(min(max(v, 0), l0.gw - 1), pxlo), pxhi); };
-    auto clampy = [&](int v) { return min(max(min(max(v, 0), l0.gh - 1), pylo), pyhi); };
+    const int cxlo = max(0, l0.px0), cxhi = min(l0.gw, l0.px0 + l0.sw) - 1;
+    const int cylo = max(0, l0.py0), cyhi = min(l0.gh, l0.py0 + l0.sh) - 1;
+    auto clampx = [&](int v) { return min(max(v, cxlo), cxhi); };
+    auto clampy = [&](int v) { return min(max(v, cylo), cyhi); };
     const int pc_lo = clampx(bxB), ncols = clampx(bxB + kGmCellsX) - pc_lo + 1;
 
     auto issue = [&](int s) {   // one thread: TMA bulk copies of step s's probe rows into buffer s & 1
@@ -1325,46 +1326,70 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
     __syncthreads();
     if (threadIdx.x == 0 && nsteps > 0) issue(0);
 
-    // this warp's two cells and this lane's pixel in them
+    // ---- per-thread invariants
+    // phase 1: this lane owns pixel (mx, my) of cell c of the warp's cell pair
     const int c = lane >> 4, m = lane & 15, mx = m & 3, my = m >> 2;
-    const int bx_own = bxB + 2 * (warp & 3) + c;                    // cell column of the pixel this lane owns
+    const int bx_own = bxB + 2 * (warp & 3) + c;
     const int x = 4 * bx_own + 2 + mx;
     const bool x_in = x >= tile.x0 && x < tile.x0 + tile.w;
     const float nx = x_in ? __ldg(axis_nx + x) : 0.0f;
     const float fx = (float)mx * 0.25f, fy = (float)my * 0.25f;     // S1: f = ((x - P/2) mod P) / P, exact
     const float bil[4] = {(1.0f - fx) * (1.0f - fy), fx * (1.0f - fy), (1.0f - fx) * fy, fx * fy};
-    const int g = lane >> 2, j = lane & 3;
+    const int lx0 = clampx(bx_own) - pc_lo, lx1 = clampx(bx_own + 1) - pc_lo;
+    const int wrow = warp >> 2;                                      // cell row of this warp inside the tile
+    // the A records this lane WRITES: pixel row (gw = m & 7, hw = m >> 3) of cell c; slot j' = j ^ ((gw >> 1) & 3)
+    const int gw = m & 7, hw = m >> 3;
+    uint32_t* const afw = reinterpret_cast<uint32_t*>(&sm.afrag[((warp * 2 + c) * 8 + gw) * 4]) + hw;
+    const int swz_w = (gw >> 1) & 3;
+    // phase 2: fragment row g, quad lane j
+    const int g = lane >> 2, j = lane & 3, q = lane >> 3;
     const int rec = warp * 32;
+    const uint4* const afr0 = &sm.afrag[((warp * 2 + 0) * 8 + g) * 4 + (j ^ ((g >> 1) & 3))];
+    const uint4* const afr1 = &sm.afrag[((warp * 2 + 1) * 8 + g) * 4 + (j ^ ((g >> 1) & 3))];
+    const int lxq0 = clampx(bxB + 2 * (warp & 3) + (q & 1)) - pc_lo, lxq1 = clampx(bxB + 2 * (warp & 3) + 1 + (q & 1)) - pc_lo;
+    // phase 3: lanes j < 2 store pixel column (g & 3) of both cells, pixel rows (g >> 2) and (g >> 2) + 2
+    const int sx0 = 4 * (bxB + 2 * (warp & 3)) + 2 + (g & 3) - tile.x0, sx1 = sx0 + 4;
+    const bool sx0_ok = j < 2 && sx0 >= 0 && sx0 < tile.w, sx1_ok = j < 2 && sx1 >= 0 && sx1 < tile.w;
+    uint32_t* const out32 = reinterpret_cast<uint32_t*>(out);
+
+    // prefetch of the G-buffer of the lane's pixel, one step ahead
+    auto gload = [&](int s, float& dep, uint32_t& nrm, int& y) {
+        y = 4 * (cby0 + (step0 + s) * kGmCellsY + wrow) + 2 + my;
+        dep = -1.0f; nrm = 0u;
+        if (x_in && y >= tile.y0 && y < tile.y0 + tile.h) {
+            const size_t o = (size_t)(y - tile.y0) * tile.w + (x - tile.x0);
+            dep = __ldg(depth + o);
+            nrm = __ldg(normal + o);
+        }
+    };
+    float dep_n = -1.0f; uint32_t nrm_n = 0u; int y_n = 0;
+    if (nsteps > 0) gload(0, dep_n, nrm_n, y_n);
 
     for (int s = 0; s < nsteps; s++) {
         if (threadIdx.x == 0 && s + 1 < nsteps) issue(s + 1);       // buffer (s+1)&1 was released by the barrier that ended step s-1
         const int b = s & 1;
-        const int byS = cby0 + (step0 + s) * kGmCellsY;
-        const int by = byS + (warp >> 2);
+        const int byS = cby0 + (step0 + s) * kGmCellsY, by = byS + wrow;
         const int pr_lo = clampy(byS);
+        const int ly0 = clampy(by) - pr_lo, ly1 = clampy(by + 1) - pr_lo;
+        const float dep = dep_n; const uint32_t nrm = nrm_n; const int y = y_n;
+        if (s + 1 < nsteps) gload(s + 1, dep_n, nrm_n, y_n);
         mbar_wait(&sm.bar[b], (unsigned)((s >> 1) & 1));
         const uint4* s_tex = sm.tex[b];
         const float4* s_org = sm.org[b];
 
         // ---- phase 1: per-pixel terms, one lane per pixel
         {
-            const int y = 4 * by + 2 + my;
-            const bool inside = x_in && y >= tile.y0 && y < tile.y0 + tile.h;
-            const size_t o = inside ? (size_t)(y - tile.y0) * tile.w + (x - tile.x0) : 0;
-            const float dep = inside ? depth[o] : -1.0f;
             float cs[16];
             float4 ak = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int d = 0; d < 16; d++) cs[d] = 0.0f;
             if (dep >= 0.0f) {
                 const float ny = __ldg(axis_ny + y);
-                const float3 q = f3(fmaf(nx, cam.dx.x, fmaf(ny, cam.dy.x, cam.dc.x)), fmaf(nx, cam.dx.y, fmaf(ny, cam.dy.y, cam.dc.y)),
-                                    fmaf(nx, cam.dx.z, fmaf(ny, cam.dy.z, cam.dc.z)));
-                const float rl = rsqrtf(vdot(q, q));
-                const float3 hp = vfma(dep * rl, q, cam.eye);
-                const float3 n = oct_decode(normal[o]);
-                const int lx0 = clampx(bx_own) - pc_lo, lx1 = clampx(bx_own + 1) - pc_lo;
-                const int ly0 = clampy(by) - pr_lo, ly1 = clampy(by + 1) - pr_lo;
+                const float3 qd = f3(fmaf(nx, cam.dx.x, fmaf(ny, cam.dy.x, cam.dc.x)), fmaf(nx, cam.dx.y, fmaf(ny, cam.dy.y, cam.dc.y)),
+                                     fmaf(nx, cam.dx.z, fmaf(ny, cam.dy.z, cam.dc.z)));
+                const float rl = rsqrtf(vdot(qd, qd));
+                const float3 hp = vfma(dep * rl, qd, cam.eye);
+                const float3 n = oct_decode(nrm);
                 const int lk[4] = {ly0 * kGmCols + lx0, ly0 * kGmCols + lx1, ly1 * kGmCols + lx0, ly1 * kGmCols + lx1};
                 float w[4];
 #pragma unroll
@@ -1400,26 +1425,28 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
                 const float qs = SC > 0.0f ? RC_PI_F * fast_rcp(SC) : 0.0f;      // (1/S) * (pi/C)
                 ak = make_float4(w[0] * qs, w[1] * qs, w[2] * qs, w[3] * qs);
             }
-            sm.cs_lo[rec + lane] = make_uint4(pack_h2(cs[0], cs[2]), pack_h2(cs[1], cs[3]), pack_h2(cs[4], cs[6]), pack_h2(cs[5], cs[7]));
-            sm.cs_hi[rec + lane] = make_uint4(pack_h2(cs[8], cs[10]), pack_h2(cs[9], cs[11]), pack_h2(cs[12], cs[14]), pack_h2(cs[13], cs[15]));
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                uint32_t* dst = afw + 4 * (jj ^ swz_w);
+                dst[0] = pack_h2(cs[4 * jj], cs[4 * jj + 2]);           // even texels of the pairs 2jj, 2jj+1
+                dst[2] = pack_h2(cs[4 * jj + 1], cs[4 * jj + 3]);       // odd texels
+            }
             sm.a[rec + lane] = ak;
             sm.alpha[rec + lane] = dep >= 0.0f ? 1.0f : 0.0f;
         }
         __syncwarp();
 
         // ---- phase 2: two cells per warp, four MMAs each
+        const int lyq = (q >> 1 ? ly1 : ly0);
+        const int py0 = 4 * by + 2 + (g >> 2) - tile.y0;             // tile row of fragment row g (row g + 8: + 2)
+        const bool r0_ok = py0 >= 0 && py0 < tile.h, r1_ok = py0 + 2 >= 0 && py0 + 2 < tile.h;
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
-            const int bx = bxB + 2 * (warp & 3) + cc;
-            const int r0 = rec + cc * 16 + g, r1 = r0 + 8;          // pixel records of fragment rows g and g + 8
-            const uint2* csrc0 = reinterpret_cast<const uint2*>(j < 2 ? &sm.cs_lo[r0] : &sm.cs_hi[r0]) + (j & 1);
-            const uint2* csrc1 = reinterpret_cast<const uint2*>(j < 2 ? &sm.cs_lo[r1] : &sm.cs_hi[r1]) + (j & 1);
-            const uint2 A0 = *csrc0, A1 = *csrc1;                   // .x: even texels 4j, 4j+2;  .y: odd texels 4j+1, 4j+3
-            const float4 a0 = sm.a[r0], a1 = sm.a[r1];
+            const uint4 A = cc ? *afr1 : *afr0;
+            const int r0 = rec + cc * 16 + g;                        // pixel records of fragment rows g (and g + 8)
+            const float4 a0 = sm.a[r0], a1 = sm.a[r0 + 8];
             // ldmatrix: lane l supplies the address of row (l & 7) of matrix (l >> 3) = probe (l >> 3) of the cell
-            const int q = lane >> 3;
-            const int lxq = clampx(bx + (q & 1)) - pc_lo, lyq = clampy(by + (q >> 1)) - pr_lo;
-            const unsigned addr = smem_u32(&s_tex[(lyq * kGmCols + lxq) * 8 + (lane & 7)]);
+            const unsigned addr = smem_u32(&s_tex[(lyq * kGmCols + (cc ? lxq1 : lxq0)) * 8 + (lane & 7)]);
             uint32_t bq[4];
             asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                          : "=r"(bq[0]), "=r"(bq[1]), "=r"(bq[2]), "=r"(bq[3]) : "r"(addr));
@@ -1431,26 +1458,25 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
                 float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
                 asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                              : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
-                             : "r"(A0.x), "r"(A1.x), "r"(A0.y), "r"(A1.y), "r"(bq[k]), "r"(brot));
+                             : "r"(A.x), "r"(A.y), "r"(A.z), "r"(A.w), "r"(bq[k]), "r"(brot));
                 e0 = fmaf(wa[k], c0, e0); e1 = fmaf(wa[k], c1, e1);
                 e2 = fmaf(wb[k], c2, e2); e3 = fmaf(wb[k], c3, e3);
             }
             // ---- phase 3: lanes j = 0 (r, g) and j = 1 (b, alpha) store fragment rows g and g + 8
-            if (j < 2) {
+            if (cc ? sx1_ok : sx0_ok) {
+                const int sx = cc ? sx1 : sx0;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const int mm = g + 8 * h;
-                    const int px = 4 * bx + 2 + (mm & 3), py = 4 * by + 2 + (mm >> 2);
-                    if (px < tile.x0 || px >= tile.x0 + tile.w || py < tile.y0 || py >= tile.y0 + tile.h) continue;
-                    const float al = sm.alpha[rec + cc * 16 + mm];
+                    if (!(h ? r1_ok : r0_ok)) continue;
                     const float va = h ? e2 : e0, vb = h ? e3 : e1;
-                    // pixels without geometry have a_k = 0 -> E = 0, alpha 0: (0,0,0,0) as S9 demands
-                    const uint32_t v = pack_h2(fminf(va, 65504.0f), j == 0 ? fminf(vb, 65504.0f) : al);
-                    const size_t o = (size_t)(py - tile.y0) * tile.w + (px - tile.x0);
-                    reinterpret_cast<uint32_t*>(out + o)[j] = v;
+                    // pixels without geometry have a_k = 0 -> E = 0 and alpha 0: (0,0,0,0) as S9 demands
+                    const float second = j == 0 ? fminf(vb, 65504.0f) : sm.alpha[r0 + 8 * h];
+                    const uint32_t v = pack_h2(fminf(va, 65504.0f), second);
+                    const unsigned o2 = ((unsigned)(py0 + 2 * h) * (unsigned)tile.w + (unsigned)sx) * 2u + (unsigned)j;
+                    out32[o2] = v;
                     if (peer.world) {   // fused final-image exchange, see k_gather
-                        const size_t fo = (size_t)py * peer.W + px;
-                        for (int d = 0; d < peer.world; d++) reinterpret_cast<uint32_t*>(peer.frame[d] + fo)[j] = v;
+                        const size_t fo = ((size_t)(py0 + 2 * h + tile.y0) * peer.W + (sx + tile.x0)) * 2 + j;
+                        for (int d = 0; d < peer.world; d++) reinterpret_cast<uint32_t*>(peer.frame[d])[fo] = v;
                     }
                 }
             }

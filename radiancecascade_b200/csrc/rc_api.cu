@@ -135,6 +135,7 @@ struct rc_ctx {
     {
         if (gather_tiles > 0) return gather_tiles;
         const size_t t = (size_t)((tile.w + 31) / 32) * ((tile.h + 7) / 8);
+        if (gather_mma && levels[0].D == 4 && levels[0].P == 4) return t >= 16384 ? 8 : 4;   // k_gather_mma: steps per block (A/B r2d)
         return t >= 16384 ? 4 : 2;
     }
     // k_gather_mma (tensor-core gather, D0 = 4 and P0 = 4): 1 = default, 0 = the scalar kernels (A/B, exact S9 arithmetic)

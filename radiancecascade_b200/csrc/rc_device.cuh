@@ -404,9 +404,21 @@ __device__ __forceinline__ uint32_t oct_encode(float3 n)
     const int iy = __float2int_rn(fminf(fmaxf(py, -1.0f), 1.0f) * 32767.0f);
     return ((uint32_t)(uint16_t)(int16_t)ix) | (((uint32_t)(uint16_t)(int16_t)iy) << 16);
 }
+// a / 32767 for an integer-valued |a| <= 32768, correctly rounded: the division's own Newton sequence (reciprocal refined
+// once, quotient corrected once with the exact remainder) without the generic operand check (FCHK) and its out-of-line
+// slow path, which every zero numerator took — i.e. every axis-aligned normal (ncu: half of the living-room pixels).
+// Bit-equal to a / 32767.0f for all 65536 inputs: tests/cpp/div32767_check.c (run by tests/test_abi.py).
+__host__ __device__ __forceinline__ float div32767(float a)
+{
+    const float r0 = 3.0518509447574615479e-05f;                 // 0x38000100
+    const float r = fmaf(fmaf(r0, -32767.0f, 1.0f), r0, r0);
+    const float q = a * r;
+    return fmaf(r, fmaf(q, -32767.0f, a), q);
+}
+
 __device__ __forceinline__ float3 oct_decode(uint32_t e)
 {
-    const float px = (float)(int16_t)(e & 0xffffu) / 32767.0f, py = (float)(int16_t)(e >> 16) / 32767.0f;
+    const float px = div32767((float)(int16_t)(e & 0xffffu)), py = div32767((float)(int16_t)(e >> 16));
     const float z = 1.0f - fabsf(px) - fabsf(py);
     float x = px, y = py;
     if (z < 0.0f) {

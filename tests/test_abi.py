@@ -97,3 +97,12 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(d, f), errors="replace").read()
                 assert "oracle" not in text.replace("rc_oracle.c with OpenMP", ""), os.path.join(d, f)
+
+
+def test_div32767_sequence_is_the_correctly_rounded_division(tmp_path):
+    """rc_device.cuh div32767 (oct_decode's division without the generic slow path) == a / 32767.0f for all int16 a."""
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "div32767_check.c")
+    exe = str(tmp_path / "div32767_check")
+    subprocess.check_call(["gcc", "-O1", "-ffp-contract=off", "-o", exe, src, "-lm"])
+    assert subprocess.run([exe], capture_output=True, text=True).stdout.strip() == "0"
