@@ -122,7 +122,8 @@ struct rc_ctx {
     std::vector<size_t> need_offset, list_offset;   // words / entries before level i
     std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
     int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
-    int list_dir_major = 0;                         // bit i: level i's ray list is ordered direction-major inside each warp's share
+    int list_dir_major = 0;
+    int list_tiled = 1;                             // levels >= 2: ray lists in 4x2 quad-tile order (k_need tile_order)                         // bit i: level i's ray list is ordered direction-major inside each warp's share
     // rc_read_target_async: 0 = copy engine (cudaMemcpyAsync); n > 0 = n resident blocks of k_copy_to_host store the
     // target into the page-locked destination
     int copy_blocks = 0;
@@ -734,6 +735,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_CULL")) c->cull = atoi(e) != 0;
         if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
         if (const char* e = getenv("RC_COPY_BLOCKS")) c->copy_blocks = atoi(e) < 0 ? 0 : (atoi(e) > 1024 ? 1024 : atoi(e));
+        if (const char* e = getenv("RC_LIST_TILED")) c->list_tiled = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
         if (const char* e = getenv("RC_LIST_DIRMAJOR")) c->list_dir_major = (int)strtol(e, nullptr, 0);
         if (const char* e = getenv("RC_GATHER_MMA")) c->gather_mma = atoi(e) != 0;
         if (const char* e = getenv("RC_GATHER_TILES")) c->gather_tiles = atoi(e) < 0 ? 0 : (atoi(e) > 64 ? 64 : atoi(e));
@@ -839,7 +841,7 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
                         c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, c->d_need.p + c->need_offset[i],
                         has_upper ? c->d_need.p + c->need_offset[i + 1] : nullptr, c->d_list.p + c->list_offset[i],
                         c->d_ray_count.p + i, i >= 1, c->need_pdl && i >= 1, c->need_pdl && i + 1 < n_lists,
-                        ((c->list_dir_major >> i) & 1) != 0, st);
+                        ((c->list_dir_major >> i) & 1) != 0, i >= 1 ? c->list_tiled : 0, st);
             c->launches++;
         }
     }
@@ -937,6 +939,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "need_pdl" && value >= 0 && value <= 1) c->need_pdl = value;
     else if (k == "copy_blocks" && value >= 0 && value <= 1024) c->copy_blocks = value;
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
+    else if (k == "list_tiled" && value >= 0 && value <= 2) c->list_tiled = value;
     else if (k == "graph" && value >= 0 && value <= 1) c->use_graph = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;

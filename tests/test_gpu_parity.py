@@ -402,8 +402,9 @@ def test_ray_list_order_and_need_pdl_do_not_change_the_frame(name, W, H):
     must leave every marched texel and the irradiance bit-identical."""
     st, _, _ = frame_setup(name, W, H)
     res = []
-    for order, pdl in ((0, 0), (7, 0), (63, 1), (0, 1)):
+    for order, pdl, tiled in ((0, 0, 0), (7, 0, 1), (63, 1, 0), (0, 1, 2), (0, 0, 2), (0, 0, 1)):
         r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name))
+        r.set_tuning("list_tiled", tiled)
         r.set_tuning("list_dir_major", order)
         r.set_tuning("need_pdl", pdl)
         r.update(st)
