@@ -138,6 +138,11 @@ rc_status rc_update(rc_ctx* ctx, const rc_camera* cam, const rc_light* lights,
 /* ≙ RenderStage::resize (src/renderer.rs:615-618) + Projection::resize. */
 rc_status rc_resize(rc_ctx* ctx, uint32_t width, uint32_t height);
 
+/* Multi-GPU (no reference counterpart): move this context's screen-space tile inside the unchanged frame, e.g. to re-balance
+ * the tiles of a tiled frame from measured frame times.  Cheap: device buffers are grow-only and reused, camera / lights /
+ * peer mappings / tuning stay; waits for frames in flight.  w == h == 0 selects the full frame. */
+rc_status rc_set_tile(rc_ctx* ctx, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h);
+
 /* ≙ RenderStage::render (src/renderer.rs:559-613): enqueues the frame on
  * `stream` (a cudaStream_t, NULL = context stream); does not synchronise and
  * does not allocate.  Stages: G-buffer, probe placement, per-level march

@@ -241,6 +241,8 @@ public:
     }
     // RenderStage::resize (src/renderer.rs:615-618)
     void resize(uint32_t width, uint32_t height) override { check(rc_resize(ctx_, width, height), "rc_resize"); }
+    // multi-GPU: move this context's screen-space tile inside the frame (w == h == 0: the full frame)
+    void set_tile(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h) { check(rc_set_tile(ctx_, x0, y0, w, h), "rc_set_tile"); }
     // RenderStage::render (src/renderer.rs:559-613): enqueues only, the caller owns the stream
     void render(AppState&, void* stream = nullptr) override { check(rc_render(ctx_, stream), "rc_render"); }
 

@@ -68,6 +68,7 @@ SYMBOLS = {
     "rc_destroy": (None, [_P]),
     "rc_update": (C.c_int32, [_P, C.POINTER(rc_camera), C.POINTER(rc_light), C.c_uint32, C.c_uint32]),
     "rc_resize": (C.c_int32, [_P, C.c_uint32, C.c_uint32]),
+    "rc_set_tile": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "rc_render": (C.c_int32, [_P, _P]),
     "rc_render_begin": (C.c_int32, [_P, _P]),
     "rc_render_level": (C.c_int32, [_P, C.c_uint32, _P]),

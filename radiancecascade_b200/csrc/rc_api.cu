@@ -35,13 +35,19 @@ struct HostModel {
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
+    bool fresh = false;              // the last alloc() had to take new memory (contents undefined)
+    // grow-only: a request that fits the current allocation reuses it (rc_set_tile re-tiles a context every few
+    // frames and must not touch the allocator)
     cudaError_t alloc(size_t count)
     {
+        fresh = false;
+        if (count <= cap && p) { n = count; return cudaSuccess; }
         release();
-        n = count;
         if (!count) return cudaSuccess;
-        return cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) { n = cap = count; fresh = true; }
+        return e;
     }
     cudaError_t upload(const std::vector<T>& v)
     {
@@ -49,13 +55,15 @@ struct DevBuf {
         if (e != cudaSuccess || v.empty()) return e;
         return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     }
-    cudaError_t alloc_zero(size_t count)
+    // zero-filled when new memory was taken, or when `always` (a reused buffer keeps its — finite — contents otherwise)
+    cudaError_t alloc_zero(size_t count, bool always = true)
     {
         cudaError_t e = alloc(count);
         if (e != cudaSuccess || !count) return e;
+        if (!always && !fresh) return cudaSuccess;
         return cudaMemset(p, 0, count * sizeof(T));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
 };
 
 }  // namespace
@@ -140,6 +148,8 @@ struct rc_ctx {
         return t >= 16384 ? 4 : 2;
     }
     // k_gather_mma (tensor-core gather, D0 = 4 and P0 = 4): 1 = default, 0 = the scalar kernels (A/B, exact S9 arithmetic)
+    // 0: render without the peer-memory stores although peers are attached (every rank must switch in the same frame)
+    int peer_stores = 1;
     int gather_mma = 1;
     bool gather_sym = false;                        // the level-0 direction table is point-symmetric (gather_dirs_symmetric)
     DevBuf<float> d_axis;                           // S4: nx(x) for x < W, then ny(y) for y < H
@@ -337,7 +347,7 @@ void level_rects(uint32_t W, uint32_t H, uint32_t P0, uint32_t N, TileRect t, st
     }
 }
 
-rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
+rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H, bool retile = false)
 {
     c->W = W; c->H = H;
     const rc_config& cfg = c->cfg;
@@ -391,7 +401,9 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
         I.t_begin = L.t0; I.t_end = L.t1;
     }
     const size_t npx = (size_t)t.w * t.h;
-    CU_OK(c, c->d_cascade.alloc_zero(texels));
+    // retile (rc_set_tile): buffers that are merely reused keep their contents — every value ever stored in them is finite,
+    // which is all the zero-weight reads of culled texels need; the request masks are all-zero between frames (k_need)
+    CU_OK(c, c->d_cascade.alloc_zero(texels, !retile));
     CU_OK(c, c->d_origin.alloc(probes));
     CU_OK(c, c->d_normal.alloc(probes));
     CU_OK(c, c->d_link_idx.alloc(probes));
@@ -404,7 +416,7 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
         avgs += (size_t)c->levels[i].sw * c->levels[i].sh * ((size_t)c->levels[i].D * c->levels[i].D / 4);
     }
     // zero-initialised: culled texels / averages are only ever multiplied by zero weights, so they must stay finite
-    CU_OK(c, c->d_avg.alloc_zero(avgs ? avgs : 1));
+    CU_OK(c, c->d_avg.alloc_zero(avgs ? avgs : 1, !retile));
     c->need_offset.assign(N + 1, 0);
     c->list_offset.assign(N + 1, 0);
     c->need_res.assign(N, 0);
@@ -415,20 +427,20 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H)
         c->need_offset[i + 1] = c->need_offset[i] + np * (size_t)((Dr * Dr + 31) / 32);
         c->list_offset[i + 1] = c->list_offset[i] + np * (size_t)(Dr * Dr);
     }
-    CU_OK(c, c->d_need.alloc_zero(c->need_offset[N]));
+    CU_OK(c, c->d_need.alloc_zero(c->need_offset[N], !retile));
     CU_OK(c, c->d_list.alloc(c->list_offset[N]));
-    CU_OK(c, c->d_ray_count.alloc_zero(RC_MAX_LEVELS));
+    CU_OK(c, c->d_ray_count.alloc_zero(RC_MAX_LEVELS, !retile));
     if (!c->h_ray_count) CU_OK(c, cudaHostAlloc((void**)&c->h_ray_count, RC_MAX_LEVELS * sizeof(unsigned int), cudaHostAllocMapped));
-    for (uint32_t i = 0; i < RC_MAX_LEVELS; i++) c->h_ray_count[i] = 0xffffffffu;
-    CU_OK(c, c->d_dirs.upload(all_dirs));
-    {   // S4's per-column / per-row terms, evaluated once with the very expressions primary_dir uses
+    if (!retile) for (uint32_t i = 0; i < RC_MAX_LEVELS; i++) c->h_ray_count[i] = 0xffffffffu;   // (a re-tiled context keeps its grid-size estimates)
+    if (!retile) CU_OK(c, c->d_dirs.upload(all_dirs));
+    if (!retile) {   // S4's per-column / per-row terms, evaluated once with the very expressions primary_dir uses
         std::vector<float> axis((size_t)W + H);
         for (uint32_t x = 0; x < W; x++) axis[x] = (float)(2 * (int)x + 1) / (float)(int)W - 1.0f;
         for (uint32_t y = 0; y < H; y++) axis[(size_t)W + y] = 1.0f - (float)(2 * (int)y + 1) / (float)(int)H;
         CU_OK(c, c->d_axis.upload(axis));
         c->gather_sym = c->levels[0].D == 4 && gather_dirs_symmetric(c->dirs_host[0].data());
     }
-    {
+    if (!retile) {
         std::vector<float4> q(2 * (all_dirs.size() / 3));
         auto safe_inv = [](float d) { return 1.0f / (std::fabs(d) > 1e-20f ? d : std::copysign(1e-20f, d)); };   // rc_device.cuh safe_inv
         for (size_t k = 0; k < all_dirs.size() / 3; k++) {
@@ -784,6 +796,20 @@ rc_status rc_resize(rc_ctx* c, uint32_t width, uint32_t height)
     return setup_frame(c, width, height);
 }
 
+rc_status rc_set_tile(rc_ctx* c, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    if ((w == 0) != (h == 0) || (w && (x0 + w > c->W || y0 + h > c->H))) { c->error = "rc_set_tile: tile outside the frame"; return RC_ERR_INVALID_ARG; }
+    cudaSetDevice(c->device);
+    // the buffers are re-laid-out in place: every frame in flight must have finished with them
+    if (c->last_stream) CU_OK(c, cudaStreamSynchronize(c->last_stream));
+    CU_OK(c, cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CU_OK(c, cudaStreamSynchronize(c->copy_stream));
+    c->cfg.tile_x0 = x0; c->cfg.tile_y0 = y0; c->cfg.tile_w = w; c->cfg.tile_h = h;
+    c->composite_valid = c->direct_valid = false;
+    return setup_frame(c, c->W, c->H, true);      // camera, lights, peers and tuning are untouched
+}
+
 // stage-timing events: inside a stream capture they must become EXTERNAL event-record nodes, otherwise the host
 // cannot synchronise on / time them (cudaErrorInvalidValue)
 static cudaError_t record_event(rc_ctx* c, cudaEvent_t ev, cudaStream_t st)
@@ -936,6 +962,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "cull" && value >= 0 && value <= 1) c->cull = value;
     else if (k == "gather_tiles" && value >= 0 && value <= 64) c->gather_tiles = value;
     else if (k == "gather_mma" && value >= 0 && value <= 1) c->gather_mma = value;
+    else if (k == "peer_stores" && value >= 0 && value <= 1) c->peer_stores = value;
     else if (k == "need_pdl" && value >= 0 && value <= 1) c->need_pdl = value;
     else if (k == "copy_blocks" && value >= 0 && value <= 1024) c->copy_blocks = value;
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
@@ -971,7 +998,7 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
     }
     const DLevel& L0 = c->levels[0];
     PeerOut po{};
-    if (c->peer.world) {
+    if (c->peer.world && c->peer_stores) {
         if ((size_t)c->W * c->H * sizeof(uint2) > c->peer.slot_bytes) { c->error = "peer frame buffers are smaller than the frame (re-export after a resize)"; return RC_ERR_STATE; }
         c->peer.seq++;
         po.world = c->peer.world; po.rank = c->peer.rank; po.W = (int)c->W; po.seq = c->peer.seq;
@@ -983,7 +1010,7 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
                   c->d_depth.p, c->d_nrm.p, c->irr(), c->d_ray_count.p, c->frame_culled ? c->h_ray_count : nullptr, po, c->gather_tiles_eff(),
                   GatherMma{c->gather_mma, c->gather_sym ? 1 : 0, c->dirs_host[0].data(), c->d_axis.p, c->d_axis.p + c->W}, st);
     c->launches++;
-    if (c->peer.world) {
+    if (po.world) {
         launch_peer_publish(po, st);
         c->launches++;
     }

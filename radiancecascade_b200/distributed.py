@@ -52,6 +52,79 @@ def partition_grid(width: int, height: int, nx: int, ny: int, align: int = 4) ->
     return [(cx, ry, cw, rh) for (ry, rh) in rows for (cx, cw) in cols]
 
 
+def strips_from_cuts(width: int, height: int, cuts: Sequence[int]) -> List[Tile]:
+    """Full-width strips from the interior cut rows (ascending, exclusive of 0 and height)."""
+    ys = [0] + [int(c) for c in cuts] + [height]
+    assert all(b > a for a, b in zip(ys, ys[1:])), ys
+    return [(0, a, width, b - a) for a, b in zip(ys, ys[1:])]
+
+
+class StripBalancer:
+    """Cost-balanced horizontal cuts from measured frame times (SURVEY §8e "cost-balanced cuts").
+
+    Equal-height strips of one frame are badly balanced: on living_room 3840x2160 cut 8 ways the slowest strip
+    takes 0.48 ms against a mean of 0.32 ms (profiles/r2_tile_timelines.md) — the cost of a ray differs 3x
+    between the upper and the lower half of the screen, so neither rows nor ray counts predict it.  Each rank
+    therefore reports the device time of its last frame; every rank runs this same deterministic update on
+    the all-gathered times: per strip, cost density = (t - fixed) / rows (the fixed part — the short
+    dependent kernels every tile runs regardless of its size — does not move with the cut); the new cuts
+    equalise the integral of that piecewise-constant density, moved only `damping` of the way (the density
+    inside a strip is not constant, so a full step overshoots), aligned to `align` rows."""
+
+    def __init__(self, width: int, height: int, n: int, align: int = 4, min_rows: int = 16, fixed_ms: float = 0.07,
+                 damping: float = 0.7):
+        self.W, self.H, self.n = width, height, n
+        self.align, self.min_rows, self.fixed_ms, self.damping = align, max(min_rows, align), fixed_ms, damping
+        self.tiles = partition_strips(width, height, n, align)
+        self.version = 0
+
+    def cuts(self) -> List[int]:
+        return [t[1] for t in self.tiles[1:]]
+
+    def update(self, times_ms: Sequence[float]) -> bool:
+        """New tiles from every rank's last frame time (rank order).  Returns True when a cut moved."""
+        n = self.n
+        assert len(times_ms) == n
+        if n == 1:
+            return False
+        rows = [t[3] for t in self.tiles]
+        dens = [max(float(t) - self.fixed_ms, 0.05 * max(float(t), 1e-6)) / h for t, h in zip(times_ms, rows)]
+        total = sum(d * h for d, h in zip(dens, rows))
+        target = total / n
+        # walk the cumulative cost
+        new_cuts, acc, k, y = [], 0.0, 0, 0
+        want = target
+        for r in range(n):
+            h, d = rows[r], dens[r]
+            while len(new_cuts) < n - 1 and acc + d * h >= want - 1e-12:
+                frac = (want - acc) / (d * h) if d * h > 0 else 0.0
+                new_cuts.append(y + frac * h)
+                want += target
+            acc += d * h
+            y += h
+        while len(new_cuts) < n - 1:
+            new_cuts.append(float(self.H))
+        old = self.cuts()
+        moved = []
+        for o, c in zip(old, new_cuts):
+            v = o + self.damping * (c - o)
+            moved.append(int(round(v / self.align)) * self.align)
+        # keep every strip at least min_rows tall, front to back then back to front
+        lo = 0
+        for i in range(n - 1):
+            moved[i] = max(moved[i], lo + self.min_rows)
+            lo = moved[i]
+        hi = self.H
+        for i in range(n - 2, -1, -1):
+            moved[i] = min(moved[i], hi - self.min_rows)
+            hi = moved[i]
+        if moved == old or any(b <= a for a, b in zip([0] + moved, moved + [self.H])):
+            return False
+        self.tiles = strips_from_cuts(self.W, self.H, moved)
+        self.version += 1
+        return True
+
+
 def halo_overhead(width: int, height: int, tiles: Sequence[Tile], p0: int = 4, levels: int = 6) -> float:
     """Redundant work of halo recomputation: (probe-directions summed over tiles) / (full frame) - 1,
     from the same footprint recursion librc_b200 uses (rc_spec.h S1)."""
@@ -136,9 +209,10 @@ class TiledRenderer:
     final all-gather.  Needs a CUDA device (no CPU fallback)."""
 
     def __init__(self, rank: int, world: int, device: int, size: Tuple[int, int], state, path: str,
-                 cascade=None, grid: Optional[Tuple[int, int]] = None):
+                 cascade=None, grid: Optional[Tuple[int, int]] = None, balance: bool = False):
         from .renderer import CascadeConfig, DefaultRenderer
         W, H = size
+        self.balancer = StripBalancer(W, H, world) if (balance and not grid) else None
         self.tiles = partition_grid(W, H, *grid) if grid else partition_strips(W, H, world)
         self.rank, self.world, self.size = rank, world, (W, H)
         cc = cascade or CascadeConfig()
@@ -148,6 +222,22 @@ class TiledRenderer:
     def render(self, state, stream: Optional[int] = None):
         self.renderer.update(state)
         self.renderer.render(stream)
+
+    def rebalance(self, times_ms: Sequence[float]) -> bool:
+        """Move the strip cuts from every rank's last frame time (identical input on every rank -> identical tiles);
+        re-tiles this rank's context in place (rc_set_tile).  Returns True when the tiles changed."""
+        if self.balancer is None or not self.balancer.update(times_ms):
+            return False
+        self.tiles = list(self.balancer.tiles)
+        self.renderer.set_tile(self.tiles[self.rank])
+        return True
+
+    def all_gather_times(self, my_ms: float, group=None) -> List[float]:
+        """Host-side all-gather of one float per rank (control plane: a gloo group when given, else the default group)."""
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, float(my_ms), group=group)
+        return [float(x) for x in out]
 
     def attach_peers(self, group=None):
         """Exchange CUDA IPC handles (host-side all-gather of 64-byte blobs) and map every rank's frame buffers:
@@ -162,8 +252,12 @@ class TiledRenderer:
 
     def gather_peer(self, stream: Optional[int] = None):
         """Fused path: enqueue the wait for all ranks' tiles of the last frame and return the assembled frame
-        (torch view of this rank's peer buffer, float16 [H][W][4]); consume it on `stream` before the next render."""
+        (torch view of this rank's peer buffer, float16 [H][W][4]); consume it on `stream` before the next render.
+        `stream` defaults to torch's current stream — the stream the caller's consumer kernels run on; render on the
+        same stream (the release handshake assumes render and consumption are stream-ordered)."""
         import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
         self.renderer.peer_wait(stream)
         ptr, nbytes, _ = self.renderer.peer_frame()
         W, H = self.size

@@ -212,6 +212,11 @@ class DefaultRenderer:
         self._check(self._lib.rc_resize(self._h, width, height))
         self.width, self.height = width, height
 
+    def set_tile(self, tile: Optional[Tuple[int, int, int, int]]) -> None:
+        """Move this context's screen-space tile (x0, y0, w, h) inside the frame; None = the full frame (rc_set_tile)."""
+        x0, y0, w, h = tile if tile else (0, 0, 0, 0)
+        self._check(self._lib.rc_set_tile(self._h, x0, y0, w, h))
+
     # RenderStage::render (src/renderer.rs:559-613): enqueue only
     def render(self, stream: Optional[int] = None) -> None:
         self._check(self._lib.rc_render(self._h, C.c_void_p(stream) if stream else None))

@@ -54,3 +54,16 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=ROOT,
                          timeout=300)
     assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """The CPU arm is the oracle alone: after timing a frame through bench.cpu_oracle_frames the process has not mapped
+    librc_b200.so (the arm used to import the product for scene paths and the orbit camera)."""
+    code = ("import sys; sys.path.insert(0, %r); import bench\n"
+            "res, _ = bench.cpu_oracle_frames('cube_512', 1, 0, 4)\n"
+            "assert res['value'] > 0\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'liboracle' in maps, 'the oracle must have run'\n"
+            "assert 'librc_b200' not in maps, 'the reference arm loaded the product library'\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]

@@ -1,5 +1,7 @@
-"""Tiled multi-GPU frame, exchanged by an NCCL all-gather and by the peer-memory stores fused into
-the gather kernel: needs >= 2 CUDA devices."""
+"""Tiled multi-GPU frame, exchanged by an NCCL all-gather and by the peer-memory stores fused into the gather
+kernel, with the strip cuts moving between frames (rc_set_tile): needs >= 2 CUDA devices.  Every frame uses a different
+camera and is compared with its own single-GPU frame, so a stale buffer slot, an early read or a broken arrive / release
+handshake cannot hide behind identical pixels."""
 import os
 import socket
 
@@ -18,44 +20,73 @@ def _worker(rank, world, port, W, H, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    st, _, _ = frame_setup("teapot", W, H)
-    tr = rd.TiledRenderer(rank, world, rank, (W, H), st, rc.scenes.scene_path("teapot"))
+    name = "teapot"
+    st, _, _ = frame_setup(name, W, H, frame=0)
+    tr = rd.TiledRenderer(rank, world, rank, (W, H), st, rc.scenes.scene_path(name), balance=True)
+    ref = rc.DefaultRenderer.new(rank, (W, H), st, rc.scenes.scene_path(name)) if rank == 0 else None
+    stream = torch.cuda.Stream()
+    ok, why = True, ""
+
+    def want_frame(state):
+        ref.update(state); ref.render()
+        return ref.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)
+
+    # (1) NCCL all-gather of the strips
     tr.render(st)
     full = tr.gather()
-    ok = True
-    want = None
-    if rank == 0:
-        ref = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path("teapot"))
-        ref.update(st); ref.render()
-        want = ref.read_target(_ffi.RC_TARGET_IRRADIANCE)
-        ok = bool(np.array_equal(full.cpu().numpy().view(np.uint16), want.view(np.uint16)))
-    # the same frame through the peer-memory exchange fused into the gather kernel (no collective): three frames,
-    # so that both buffer slots and the release / arrive handshake are exercised
+    if rank == 0 and not np.array_equal(full.cpu().numpy().view(np.uint16), want_frame(st)):
+        ok, why = False, "nccl all-gather frame differs"
+    # (2) the peer-memory exchange fused into the gather kernel: six frames, each with its own camera, the cuts moved twice
     tr.attach_peers()
-    for _ in range(3):
-        tr.render(st)
-        peer_full = tr.gather_peer().clone()
+    for f in range(6):
+        stf, _, _ = frame_setup(name, W, H, frame=3 + 5 * f)
+        with torch.cuda.stream(stream):
+            tr.render(stf, stream.cuda_stream)
+            got = tr.gather_peer(stream.cuda_stream).clone()       # consumed on the render stream, before the next render
+        stream.synchronize()
+        if rank == 0 and not np.array_equal(got.cpu().numpy().view(np.uint16), want_frame(stf)):
+            ok, why = False, f"peer frame {f} differs"
+        if f in (1, 3):      # uneven "measured" times: every rank computes the same new cuts and re-tiles in place
+            times = [1.0 + 0.8 * r for r in range(world)] if f == 1 else [1.6 - 0.5 * r for r in range(world)]
+            moved = tr.rebalance(tr.all_gather_times(times[rank]))
+            if not moved:
+                ok, why = False, "the balancer did not move the cuts"
     torch.cuda.synchronize()
     _, _, timeouts = tr.renderer.peer_frame(check=True)
     if rank == 0:
-        ok = ok and timeouts == 0 and bool(np.array_equal(peer_full.cpu().numpy().view(np.uint16), want.view(np.uint16)))
-        q.put(ok)
+        if timeouts != 0:
+            ok, why = False, f"{timeouts} flag time-outs"
+        q.put((ok, why))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_tiled_frame_equals_single_gpu():
+def _run(world, W, H):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 384, 216, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, W, H, q)) for r in range(world)]
     for p in procs:
         p.start()
-    ok = q.get(timeout=300)
+    ok, why = q.get(timeout=600)
     for p in procs:
-        p.join(timeout=60)
-    assert ok
+        p.join(timeout=120)
+    assert ok, why
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_tiled_frame_equals_single_gpu():
+    _run(2, 384, 216)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
+def test_four_gpu_tiled_frame_equals_single_gpu():
+    _run(4, 640, 360)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 8, reason="needs 8 GPUs")
+def test_eight_gpu_tiled_frame_equals_single_gpu():
+    _run(8, 960, 544)

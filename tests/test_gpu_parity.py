@@ -444,6 +444,27 @@ def test_ray_lists_match_the_culling_rule_bit_exactly(name, W, H):
     assert total > 0
 
 
+@pytest.mark.culled
+def test_set_tile_equals_fresh_tile_context():
+    """rc_set_tile re-lays-out a context in place (grow-only buffers, stale but finite contents): every tile rendered that
+    way equals the crop of the full frame bit for bit, also after growing, shrinking and going back to the full frame."""
+    name, W, H = "living_room", 320, 180
+    st, _, _ = frame_setup(name, W, H)
+    full = render_product(name, W, H, st).read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)
+    r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name), rc.CascadeConfig(tile=(0, 0, W, 44)))
+    r.update(st)
+    for tile in ((0, 0, W, 44), (0, 44, W, 92), (0, 136, W, 44), (64, 30, 100, 50), None, (0, 100, W, 80), (3, 5, 7, 9)):
+        r.set_tile(tile)
+        for _ in range(2):
+            r.render()
+        x0, y0, w, h = tile if tile else (0, 0, W, H)
+        assert r.tile() == (x0, y0, w, h)
+        got = r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)
+        assert np.array_equal(got, full[y0:y0 + h, x0:x0 + w]), tile
+    with pytest.raises(rc.RcError):
+        r.set_tile((0, 0, W + 1, 10))
+
+
 def test_resize_matches_fresh_context():
     st, _, _ = frame_setup("cube", 96, 64)
     a = render_product("cube", 96, 64, st)
