@@ -545,7 +545,9 @@ def run_tiled(args):
     def rebalance_from(e0, e1):
         """times of the frame just rendered -> new cuts (every rank computes the same ones)"""
         stream.synchronize()
-        return tr.rebalance(tr.all_gather_times(e0.elapsed_time(e1), group=ctl))
+        moved = tr.rebalance(tr.all_gather_times(e0.elapsed_time(e1), group=ctl))
+        dist.barrier(group=ctl)          # nobody starts the next frame while a rank is still re-tiling
+        return moved
 
     # the frame a single GPU would render: its marched-ray count per step is the work unit of `value`
     useful = []
@@ -591,6 +593,7 @@ def run_tiled(args):
         if tr.balancer is not None and args.rebalance_every > 0 and (i + 1) % args.rebalance_every == 0 and i + 1 < args.steps:
             if tr.rebalance(tr.all_gather_times(e0.elapsed_time(e1), group=ctl)):
                 rebalances += 1
+            dist.barrier(group=ctl)      # nobody starts the next frame while a rank is still re-tiling
     torch.cuda.synchronize(); dist.barrier()
     per_step = torch.tensor([[a.elapsed_time(c), a.elapsed_time(b)] for a, b, c in evs], device="cuda", dtype=torch.float64)
     mx = per_step.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)        # per step: the slowest rank
@@ -612,6 +615,11 @@ def run_tiled(args):
     dist.barrier()
     if rank != 0:
         shm = shared_memory.SharedMemory(name=shm_name)
+        try:      # only the creator may unlink: keep this process's resource tracker from trying (and warning) at exit
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:       # noqa: BLE001
+            pass
     host = np.ndarray((2, H, W, 4), dtype=np.float16, buffer=shm.buf)
     base_ptr = host.ctypes.data
     cudart = torch.cuda.cudart()

@@ -198,6 +198,8 @@ rc_status rc_get_ray_list(rc_ctx* ctx, uint32_t level, uint32_t* entries, size_t
  * flag; rc_peer_wait enqueues the acquire of all ranks' flags.  Two buffer slots alternate, and a rank announces
  * that it is done with frame n when it starts frame n+1 in stream order — so consume the assembled frame on the
  * stream you render on, before the next rc_render.
+ * By default the tiles are gathered on rank 0 only (final image gather); rc_set_tuning("peer_broadcast", 1) on every rank
+ * makes every rank receive the whole frame (all-gather, N times the traffic).
  *   rc_peer_export  allocates this rank's buffers and returns their 64-byte CUDA IPC handle
  *   rc_peer_attach  handles = world x 64 bytes, rank-ordered (exchange them with any host-side all-gather)
  *   rc_peer_wait    enqueue: wait until every rank's tile of the last rendered frame has arrived here

@@ -1157,7 +1157,7 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
         // k_peer_publish, the next kernel in the stream, raises the "delivered" flags once this grid has retired.
         if (inside) {
             const size_t fo = (size_t)(tile.y0 + ty) * peer.W + (tile.x0 + tx);
-            for (int d = 0; d < peer.world; d++) peer.frame[d][fo] = v;
+            for (int d = 0; d < peer.world; d++) if ((peer.dst_mask >> d) & 1u) peer.frame[d][fo] = v;
         }
     }
 }
@@ -1246,7 +1246,7 @@ __global__ void __launch_bounds__(kBlock) k_gather_pipe(DCamera cam, DLevel l0, 
         if (inside) out[o] = v;
         if (peer.world && inside) {   // fused final-image exchange, see k_gather
             const size_t fo = (size_t)(tile.y0 + ty) * peer.W + (tile.x0 + tx);
-            for (int d = 0; d < peer.world; d++) peer.frame[d][fo] = v;
+            for (int d = 0; d < peer.world; d++) if ((peer.dst_mask >> d) & 1u) peer.frame[d][fo] = v;
         }
         __syncthreads();   // everyone is done with buffer j & 1 before tile j+2 is staged into it
     }
@@ -1326,6 +1326,7 @@ struct GatherMmaSmem {
     uint4 afrag[8 * 2 * 8 * 4];
     float4 a[256];                            // a_k = (w_k / S) * (pi / C) per pixel
     float alpha[256];
+    uint2 outt[8 * 32];                       // the step's 32 x 8 pixel tile of results, row-major, for coalesced 16-byte stores
     unsigned long long bar[2];
 };
 
@@ -1394,10 +1395,6 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
     const uint4* const afr0 = &sm.afrag[((warp * 2 + 0) * 8 + g) * 4 + (j ^ ((g >> 1) & 3))];
     const uint4* const afr1 = &sm.afrag[((warp * 2 + 1) * 8 + g) * 4 + (j ^ ((g >> 1) & 3))];
     const int lxq0 = clampx(bxB + 2 * (warp & 3) + (q & 1)) - pc_lo, lxq1 = clampx(bxB + 2 * (warp & 3) + 1 + (q & 1)) - pc_lo;
-    // phase 3: lanes j < 2 store pixel column (g & 3) of both cells, pixel rows (g >> 2) and (g >> 2) + 2
-    const int sx0 = 4 * (bxB + 2 * (warp & 3)) + 2 + (g & 3) - tile.x0, sx1 = sx0 + 4;
-    const bool sx0_ok = j < 2 && sx0 >= 0 && sx0 < tile.w, sx1_ok = j < 2 && sx1 >= 0 && sx1 < tile.w;
-    uint32_t* const out32 = reinterpret_cast<uint32_t*>(out);
 
     // prefetch of the G-buffer of the lane's pixel, one step ahead
     auto gload = [&](int s, float& dep, uint32_t& nrm, int& y) {
@@ -1485,8 +1482,6 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
 
         // ---- phase 2: two cells per warp, four MMAs each
         const int lyq = (q >> 1 ? ly1 : ly0);
-        const int py0 = 4 * by + 2 + (g >> 2) - tile.y0;             // tile row of fragment row g (row g + 8: + 2)
-        const bool r0_ok = py0 >= 0 && py0 < tile.h, r1_ok = py0 + 2 >= 0 && py0 + 2 < tile.h;
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
             const uint4 A = cc ? *afr1 : *afr0;
@@ -1509,21 +1504,41 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
                 e0 = fmaf(wa[k], c0, e0); e1 = fmaf(wa[k], c1, e1);
                 e2 = fmaf(wb[k], c2, e2); e3 = fmaf(wb[k], c3, e3);
             }
-            // ---- phase 3: lanes j = 0 (r, g) and j = 1 (b, alpha) store fragment rows g and g + 8
-            if (cc ? sx1_ok : sx0_ok) {
-                const int sx = cc ? sx1 : sx0;
+            // ---- phase 3: lanes j = 0 (r, g) and j = 1 (b, alpha) put fragment rows g and g + 8 into the block's output tile
+            if (j < 2) {
+                const int tx = 8 * (warp & 3) + 4 * cc + (g & 3);       // pixel column inside the 32 x 8 tile
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    if (!(h ? r1_ok : r0_ok)) continue;
                     const float va = h ? e2 : e0, vb = h ? e3 : e1;
                     // pixels without geometry have a_k = 0 -> E = 0 and alpha 0: (0,0,0,0) as S9 demands
                     const float second = j == 0 ? fminf(vb, 65504.0f) : sm.alpha[r0 + 8 * h];
-                    const uint32_t v = pack_h2(fminf(va, 65504.0f), second);
-                    const unsigned o2 = ((unsigned)(py0 + 2 * h) * (unsigned)tile.w + (unsigned)sx) * 2u + (unsigned)j;
-                    out32[o2] = v;
-                    if (peer.world) {   // fused final-image exchange, see k_gather
-                        const size_t fo = ((size_t)(py0 + 2 * h + tile.y0) * peer.W + (sx + tile.x0)) * 2 + j;
-                        for (int d = 0; d < peer.world; d++) reinterpret_cast<uint32_t*>(peer.frame[d])[fo] = v;
+                    const int ty = 4 * wrow + (g >> 2) + 2 * h;
+                    reinterpret_cast<uint32_t*>(&sm.outt[ty * 32 + tx])[j] = pack_h2(fminf(va, 65504.0f), second);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 4: the finished 32 x 8 tile leaves the block as 16-byte vectors (two pixels), row segments contiguous:
+        // full sectors for the local store and for the NVLink stores of the fused final-image exchange (4-byte stores from
+        // the fragment owners made the peer path slower than the whole single-GPU gather: 0.20 vs 0.157 ms per half frame)
+        if (threadIdx.x < 128) {
+            const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 2;
+            const int px = 4 * bxB + 2 + tx - tile.x0, py = 4 * byS + 2 + ty - tile.y0;      // tile coordinates of the pixel pair
+            if (py >= 0 && py < tile.h && px + 1 >= 0 && px < tile.w) {
+                const uint2 v0 = sm.outt[ty * 32 + tx], v1 = sm.outt[ty * 32 + tx + 1];
+                const bool in0 = px >= 0, in1 = px + 1 < tile.w;
+                const size_t o = (size_t)py * tile.w + (in0 ? px : px + 1);
+                // pixel pairs start at even tile columns + 2: 16-byte alignment holds when the row pitch and tile.x0 are even
+                const bool vec = in0 && in1 && !(tile.w & 1) && !((px + tile.x0) & 1) && !(tile.x0 & 1);
+                if (vec) *reinterpret_cast<uint4*>(out + o) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+                else { if (in0) out[o] = v0; if (in1) out[o + (in0 ? 1 : 0)] = v1; }
+                if (peer.world) {   // fused final-image exchange, see k_gather
+                    const size_t fo = (size_t)(py + tile.y0) * peer.W + ((in0 ? px : px + 1) + tile.x0);
+                    const bool pvec = in0 && in1 && !(peer.W & 1) && !((px + tile.x0) & 1);
+                    for (int d = 0; d < peer.world; d++) {
+                        if (!((peer.dst_mask >> d) & 1u)) continue;
+                        if (pvec) *reinterpret_cast<uint4*>(peer.frame[d] + fo) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+                        else { if (in0) peer.frame[d][fo] = v0; if (in1) peer.frame[d][fo + (in0 ? 1 : 0)] = v1; }
                     }
                 }
             }
@@ -1555,7 +1570,8 @@ __global__ void k_peer_begin(PeerOut peer, uint32_t* my_ctrl)
     if (r >= peer.world) return;
     __threadfence_system();
     *((volatile uint32_t*)(peer.ctrl[r] + kPeerReleased + peer.rank)) = peer.seq - 1u;
-    if (peer.seq >= 2u && !peer_spin(my_ctrl + kPeerReleased + r, peer.seq - 2u)) atomicAdd(my_ctrl + kPeerError, 1u);
+    // only the ranks that receive frames hold (and release) buffer slots
+    if (((peer.dst_mask >> r) & 1u) && peer.seq >= 2u && !peer_spin(my_ctrl + kPeerReleased + r, peer.seq - 2u)) atomicAdd(my_ctrl + kPeerError, 1u);
 }
 
 // after this rank's gather of frame `seq` (a kernel boundary: all of its peer stores have been performed): tell
@@ -1565,7 +1581,7 @@ __global__ void k_peer_publish(PeerOut peer)
     const int r = threadIdx.x;
     if (r >= peer.world) return;
     __threadfence_system();
-    *((volatile uint32_t*)(peer.ctrl[r] + kPeerArrived + peer.rank)) = peer.seq;
+    if ((peer.dst_mask >> r) & 1u) *((volatile uint32_t*)(peer.ctrl[r] + kPeerArrived + peer.rank)) = peer.seq;
 }
 
 // consumer side: every rank's tile of frame `seq` has landed in this rank's frame buffer

@@ -27,6 +27,7 @@ struct PeerOut {
     uint32_t* ctrl[kMaxPeers];     // rank d's control block
     int world, rank, W;
     uint32_t seq;                  // frame number, from 1
+    uint32_t dst_mask;             // ranks that receive the tiles (bit d): rank 0 alone = final image gather, all = all-gather
 };
 struct EntryPlan { unsigned group_offset[RC_MAX_LEVELS + 1]; int g[RC_MAX_LEVELS]; int n; };
 

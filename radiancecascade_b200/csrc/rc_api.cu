@@ -150,6 +150,9 @@ struct rc_ctx {
     // k_gather_mma (tensor-core gather, D0 = 4 and P0 = 4): 1 = default, 0 = the scalar kernels (A/B, exact S9 arithmetic)
     // 0: render without the peer-memory stores although peers are attached (every rank must switch in the same frame)
     int peer_stores = 1;
+    // 0 (default): the finished tiles are gathered on rank 0 (final image gather); 1: every rank receives every tile
+    // (all-gather: N times the NVLink traffic — at 8 ranks the stores cost more than the gather itself).  Same value on all ranks.
+    int peer_broadcast = 0;
     int gather_mma = 1;
     bool gather_sym = false;                        // the level-0 direction table is point-symmetric (gather_dirs_symmetric)
     DevBuf<float> d_axis;                           // S4: nx(x) for x < W, then ny(y) for y < H
@@ -963,6 +966,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "gather_tiles" && value >= 0 && value <= 64) c->gather_tiles = value;
     else if (k == "gather_mma" && value >= 0 && value <= 1) c->gather_mma = value;
     else if (k == "peer_stores" && value >= 0 && value <= 1) c->peer_stores = value;
+    else if (k == "peer_broadcast" && value >= 0 && value <= 1) c->peer_broadcast = value;
     else if (k == "need_pdl" && value >= 0 && value <= 1) c->need_pdl = value;
     else if (k == "copy_blocks" && value >= 0 && value <= 1024) c->copy_blocks = value;
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
@@ -1002,6 +1006,7 @@ rc_status rc_render_end(rc_ctx* c, void* stream)
         if ((size_t)c->W * c->H * sizeof(uint2) > c->peer.slot_bytes) { c->error = "peer frame buffers are smaller than the frame (re-export after a resize)"; return RC_ERR_STATE; }
         c->peer.seq++;
         po.world = c->peer.world; po.rank = c->peer.rank; po.W = (int)c->W; po.seq = c->peer.seq;
+        po.dst_mask = c->peer_broadcast ? ((1u << c->peer.world) - 1u) : 1u;
         for (int r = 0; r < c->peer.world; r++) { po.frame[r] = c->peer.frame(r, c->peer.seq); po.ctrl[r] = c->peer.ctrl(r); }
         launch_peer_begin(po, c->peer.ctrl(c->peer.rank), st);
         c->launches++;
@@ -1323,6 +1328,7 @@ rc_status rc_peer_wait(rc_ctx* c, void* stream)
     if (!c->peer.world || !c->peer.seq) { c->error = "rc_peer_wait: no frame has been rendered with peers attached"; return RC_ERR_STATE; }
     cudaSetDevice(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (!c->peer_broadcast && c->peer.rank != 0) return RC_OK;     // only rank 0 receives frames: nothing to wait for here
     launch_peer_wait(c->peer.world, c->peer.seq, c->peer.ctrl(c->peer.rank), st);
     CU_OK(c, cudaGetLastError());
     return RC_OK;

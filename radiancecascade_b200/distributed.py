@@ -217,7 +217,15 @@ class TiledRenderer:
         self.rank, self.world, self.size = rank, world, (W, H)
         cc = cascade or CascadeConfig()
         cc.tile = self.tiles[rank]
+        if self.balancer is not None and world > 1:
+            # the cuts will move: size the (grow-only) device buffers once for a strip of twice the average height, so that
+            # re-tiling never reaches the allocator (a cudaFree + cudaMalloc of the cascade stalls the rank for ~0.1 s)
+            rows = min(H, 2 * -(-H // world) + 64)
+            y0 = min(self.tiles[rank][1], H - rows)
+            cc.tile = (0, y0, W, rows)
         self.renderer = DefaultRenderer.new(device, (W, H), state, path, cc)
+        if cc.tile != self.tiles[rank]:
+            self.renderer.set_tile(self.tiles[rank])
 
     def render(self, state, stream: Optional[int] = None):
         self.renderer.update(state)

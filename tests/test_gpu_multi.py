@@ -39,6 +39,8 @@ def _worker(rank, world, port, W, H, q):
     # (2) the peer-memory exchange fused into the gather kernel: six frames, each with its own camera, the cuts moved twice
     tr.attach_peers()
     for f in range(6):
+        if f == 4:      # frames 0-3: final image gather on rank 0 (default); frames 4-5: every rank receives the frame
+            tr.renderer.set_tuning("peer_broadcast", 1)
         stf, _, _ = frame_setup(name, W, H, frame=3 + 5 * f)
         with torch.cuda.stream(stream):
             tr.render(stf, stream.cuda_stream)
@@ -46,6 +48,12 @@ def _worker(rank, world, port, W, H, q):
         stream.synchronize()
         if rank == 0 and not np.array_equal(got.cpu().numpy().view(np.uint16), want_frame(stf)):
             ok, why = False, f"peer frame {f} differs"
+        if f >= 4:      # all-gather mode: every rank's copy equals rank 0's
+            mine = got.contiguous()
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            if rank == 0 and not all(torch.equal(p, parts[0]) for p in parts):
+                ok, why = False, f"broadcast frame {f}: ranks disagree"
         if f in (1, 3):      # uneven "measured" times: every rank computes the same new cuts and re-tiles in place
             times = [1.0 + 0.8 * r for r in range(world)] if f == 1 else [1.6 - 0.5 * r for r in range(world)]
             moved = tr.rebalance(tr.all_gather_times(times[rank]))
