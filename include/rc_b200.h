@@ -44,6 +44,11 @@ enum {
 #define RC_CFG_SEPARATE_MERGE 0x1u /* run march and merge as separate kernels (debug / A-B) instead of the fused path */
 #define RC_CFG_NO_TEXTURES    0x2u /* ignore map_Kd / map_Bump (as if the files were missing, src/primitives.rs:390-404) */
 #define RC_CFG_HALO_EXCHANGE  0x4u /* reserved: tile mode with exchanged (not recomputed) halos; today halos are always recomputed */
+/* The reference's clip volume and depth test for primary visibility (rc_spec.h S4b): pixels and probe anchors see the closest
+ * fragment between the near and far planes of the projection inside view_proj (src/camera.rs:77-79; src/app.rs:26 near 0.1,
+ * far 100), exactly what the render pass keeps (Depth32Float, Less, clear 1.0: src/renderer.rs:354-360, 585-592).
+ * Without the flag primary rays see [0, inf): the GI benchmark cameras use far = 4 x the scene diagonal either way. */
+#define RC_CFG_RASTER_CLIP    0x8u
 
 /* rc_update flags.  bit0 ≙ AppState::enable_normal_map (src/app.rs:18, src/renderer.rs:620-631) */
 #define RC_UPD_ENABLE_NORMAL_MAP 0x1u

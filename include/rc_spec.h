@@ -59,6 +59,18 @@
  *   rho = max(|d(uv)/dx * size|, |d(uv)/dy * size|); rho <= 1 -> bilinear after the sRGB decode
  *   (texel centres at integer + 0.5), otherwise, or when a neighbour ray is parallel to the plane, nearest.
  *
+ * ---- S4b. the reference's clip volume (optional: RC_CFG_RASTER_CLIP) -------------
+ *   The reference's render pass keeps, per pixel, the closest fragment between the near and far planes of its projection
+ *   (perspective_rh, depth 0..1: src/camera.rs:77-79; Depth32Float / Less / clear 1.0: src/renderer.rs:354-360, 585-592).
+ *   With the flag every primary ray (pixels and probe anchors) is limited to that range, derived from view_proj alone:
+ *   r2 = (M[2], M[6], M[10], M[14]), r3 = (M[3], M[7], M[11], M[15])   rows 2, 3 of the column-major M
+ *   z0 = fma(r2.z,e.z, fma(r2.y,e.y, fma(r2.x,e.x, r2.w)));  w0 likewise with r3             (e = eye)
+ *   zd = dot(r2.xyz, dir);  wd = dot(r3.xyz, dir)
+ *   tmin = zd > 0 ? max(-z0/zd, 0) : 0;      g = zd - wd;  tmax = g > 0 ? (w0 - z0)/g : FLT_MAX
+ *   closest hit over [tmin, tmax).  Ties in t go to the lower triangle id = the triangle drawn first, which is what the
+ *   depth test Less keeps.  oracle/rc_oracle.c rco_raster restates the pass independently as a clipping scan-converter;
+ *   the two agree on the triangle of every pixel except edge pixels (tests/test_oracle_gi.py, tests/test_gpu_parity.py).
+ *
  * ---- S5. ray / triangle (two-sided Moller-Trumbore; cull_mode None,
  *          src/renderer.rs:332-343) ------------------------------------------
  *   triangle = (v0, e1 = v1-v0, e2 = v2-v0) with (v0,v1,v2) in the REVERSED

@@ -447,6 +447,7 @@ typedef struct {
     float sky[3];
     int tile_x0, tile_y0, tile_w, tile_h;   /* pixels produced by gather/gbuffer */
     int store_half;                          /* round stored cascade texels / outputs through float16 */
+    int clip;                                /* S4b: primary rays limited to the near / far planes of view_proj */
 } rco_params;
 
 typedef struct {
@@ -548,6 +549,20 @@ static v3 oct_decode(uint32_t e)
 
 /* G-buffer over the tile (S4).  depth[th][tw], prim[th][tw], normal[th][tw] (oct u32),
  * albedo[th][tw][4], direct[th][tw][4] (float32; rounded through half if store_half). */
+/* S4b: range of a primary ray between the near and far planes of the column-major view_proj in cam[0..15]
+ * (src/camera.rs:77-79 perspective_rh, depth 0..1): z_clip(t) = z0 + t*zd >= 0 and z_clip(t) <= w_clip(t) = w0 + t*wd */
+static inline void primary_range(const rco_params* p, const float cam[20], v3 eye, v3 d, float* tmin, float* tmax)
+{
+    *tmin = 0.0f; *tmax = FLT_MAX;
+    if (!p->clip) return;
+    const float z0 = fmaf(cam[10], eye.z, fmaf(cam[6], eye.y, fmaf(cam[2], eye.x, cam[14])));
+    const float w0 = fmaf(cam[11], eye.z, fmaf(cam[7], eye.y, fmaf(cam[3], eye.x, cam[15])));
+    const float zd = vdot(V(cam[2], cam[6], cam[10]), d), wd = vdot(V(cam[3], cam[7], cam[11]), d);
+    if (zd > 0.0f) *tmin = fmaxf(-z0 / zd, 0.0f);
+    const float g = zd - wd;
+    if (g > 0.0f) *tmax = (w0 - z0) / g;
+}
+
 void rco_gbuffer(const rco_scene* s, const rco_params* p, const float cam[20], const float* light_pos, int n_lights,
                  uint32_t flags, float* depth, uint32_t* prim, uint32_t* normal, float* albedo, float* direct)
 {
@@ -560,7 +575,9 @@ void rco_gbuffer(const rco_scene* s, const rco_params* p, const float cam[20], c
         int x = p->tile_x0 + tx, y = p->tile_y0 + ty;
         size_t o = (size_t)ty * p->tile_w + tx;
         v3 d = primary_dir(p, b, x, y);
-        rco_hit h = trace_bvh(s, eye, d, 0.0f, FLT_MAX);
+        float tmin, tmax;
+        primary_range(p, cam, eye, d, &tmin, &tmax);
+        rco_hit h = trace_bvh(s, eye, d, tmin, tmax);
         if (h.prim == 0xffffffffu) {
             depth[o] = -1.0f; prim[o] = 0xffffffffu; normal[o] = 0;
             for (int k = 0; k < 4; k++) { albedo[4 * o + k] = 0; direct[4 * o + k] = 0; }
@@ -599,7 +616,9 @@ void rco_probes(const rco_scene* s, const rco_params* p, const float cam[20], in
         int ax = px * L.P + L.P / 2, ay = py * L.P + L.P / 2;
         if (ax > p->W - 1) ax = p->W - 1; if (ay > p->H - 1) ay = p->H - 1;
         v3 d = primary_dir(p, b, ax, ay);
-        rco_hit h = trace_bvh(s, eye, d, 0.0f, FLT_MAX);
+        float tmin, tmax;
+        primary_range(p, cam, eye, d, &tmin, &tmax);
+        rco_hit h = trace_bvh(s, eye, d, tmin, tmax);
         if (h.prim == 0xffffffffu) {
             for (int k = 0; k < 4; k++) { origin[4 * o + k] = 0; nrm[4 * o + k] = 0; }
             continue;
@@ -803,6 +822,101 @@ void rco_pixel_masks(const rco_params* p, const float* dirs0, const float* depth
                 if (vdot(n, V(dirs0[3 * di], dirs0[3 * di + 1], dirs0[3 * di + 2])) > 0.0f) m |= 1u << di;
         }
         mask[i] = m;
+    }
+}
+
+/* ---- Independent restatement of the reference's render pass as a RASTERISER (src/renderer.rs:332-360, 565-593;
+ * src/shader.wgsl:30-43): every triangle is transformed by the column-major view_proj (vs_main), clipped against the
+ * near (z_clip >= 0) and far (z_clip <= w_clip) planes, projected, and scan-converted at pixel centres with
+ * perspective-correct barycentrics; depth test Less against a buffer cleared to 1.0, cull_mode None, triangles in draw
+ * order (model by model, index order) so that the first of two equal depths wins.  It shares no code with the ray caster
+ * above: tests/test_gpu_parity.py compares the product's clipped G-buffer (S4b) with it — same triangle per pixel except
+ * on edge pixels, same barycentrics and depth within float tolerance.
+ * prim [th][tw] (0xffffffff = clear colour), zndc [th][tw] (1.0 = clear), bary [th][tw][2] = (u, v) of S5. */
+typedef struct { double x, y, z, w, b[3]; } rvert;
+
+static int clip_poly(const rvert* in, int n, rvert* out, int plane /* 0: z >= 0, 1: w - z >= 0 */)
+{
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const rvert *a = &in[i], *c = &in[(i + 1) % n];
+        const double da = plane ? a->w - a->z : a->z, dc = plane ? c->w - c->z : c->z;
+        if (da >= 0.0) out[m++] = *a;
+        if ((da >= 0.0) != (dc >= 0.0)) {
+            const double t = da / (da - dc);
+            rvert v;
+            v.x = a->x + t * (c->x - a->x); v.y = a->y + t * (c->y - a->y); v.z = a->z + t * (c->z - a->z); v.w = a->w + t * (c->w - a->w);
+            for (int k = 0; k < 3; k++) v.b[k] = a->b[k] + t * (c->b[k] - a->b[k]);
+            out[m++] = v;
+        }
+    }
+    return m;
+}
+
+void rco_raster(const rco_scene* s, const rco_params* p, const float cam[20], uint32_t* prim, float* zndc, float* bary)
+{
+    const int tw = p->tile_w, th = p->tile_h;
+    for (size_t i = 0; i < (size_t)tw * th; i++) { prim[i] = 0xffffffffu; zndc[i] = 1.0f; bary[2 * i] = bary[2 * i + 1] = 0.0f; }
+    const int band = 16, nb = (th + band - 1) / band;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int bi = 0; bi < nb; bi++) {
+        const int ya = p->tile_y0 + bi * band, yb = (ya + band < p->tile_y0 + th) ? ya + band : p->tile_y0 + th;
+        for (int t = 0; t < s->n_tris; t++) {
+            if (s->skip[t]) continue;
+            rvert poly[8], tmp[8];
+            for (int k = 0; k < 3; k++) {
+                const float* v = s->verts + 17 * (size_t)s->tris[3 * (size_t)t + k];
+                rvert r;
+                r.x = (double)cam[0] * v[0] + (double)cam[4] * v[1] + (double)cam[8] * v[2] + cam[12];
+                r.y = (double)cam[1] * v[0] + (double)cam[5] * v[1] + (double)cam[9] * v[2] + cam[13];
+                r.z = (double)cam[2] * v[0] + (double)cam[6] * v[1] + (double)cam[10] * v[2] + cam[14];
+                r.w = (double)cam[3] * v[0] + (double)cam[7] * v[1] + (double)cam[11] * v[2] + cam[15];
+                r.b[0] = r.b[1] = r.b[2] = 0.0; r.b[k] = 1.0;
+                poly[k] = r;
+            }
+            int n = clip_poly(poly, 3, tmp, 0);
+            if (n < 3) continue;
+            n = clip_poly(tmp, n, poly, 1);
+            if (n < 3) continue;
+            double sx[8], sy[8], sz[8], iw[8];
+            for (int k = 0; k < n; k++) {
+                if (!(poly[k].w > 0.0)) { n = 0; break; }
+                iw[k] = 1.0 / poly[k].w;
+                sx[k] = (poly[k].x * iw[k] * 0.5 + 0.5) * p->W;
+                sy[k] = (1.0 - (poly[k].y * iw[k] * 0.5 + 0.5)) * p->H;
+                sz[k] = poly[k].z * iw[k];
+            }
+            for (int f = 1; f + 1 < n; f++) {
+                const int id[3] = { 0, f, f + 1 };
+                const double x0 = sx[id[0]], y0 = sy[id[0]], x1 = sx[id[1]], y1 = sy[id[1]], x2 = sx[id[2]], y2 = sy[id[2]];
+                double area = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+                if (area == 0.0 || area != area) continue;
+                const double sg = area < 0.0 ? -1.0 : 1.0;
+                area *= sg;
+                double fx0 = fmin(x0, fmin(x1, x2)), fx1 = fmax(x0, fmax(x1, x2)), fy0 = fmin(y0, fmin(y1, y2)), fy1 = fmax(y0, fmax(y1, y2));
+                int ix0 = (int)floor(fx0 - 0.5), ix1 = (int)ceil(fx1 - 0.5), iy0 = (int)floor(fy0 - 0.5), iy1 = (int)ceil(fy1 - 0.5);
+                if (ix0 < p->tile_x0) ix0 = p->tile_x0;
+                if (ix1 > p->tile_x0 + tw - 1) ix1 = p->tile_x0 + tw - 1;
+                if (iy0 < ya) iy0 = ya;
+                if (iy1 > yb - 1) iy1 = yb - 1;
+                for (int y = iy0; y <= iy1; y++) for (int x = ix0; x <= ix1; x++) {
+                    const double cx = x + 0.5, cy = y + 0.5;
+                    const double e0 = sg * ((x2 - x1) * (cy - y1) - (y2 - y1) * (cx - x1));
+                    const double e1 = sg * ((x0 - x2) * (cy - y2) - (y0 - y2) * (cx - x2));
+                    const double e2 = sg * ((x1 - x0) * (cy - y0) - (y1 - y0) * (cx - x0));
+                    if (e0 < 0.0 || e1 < 0.0 || e2 < 0.0) continue;
+                    const double l0 = e0 / area, l1 = e1 / area, l2 = e2 / area;
+                    const float z = (float)(l0 * sz[id[0]] + l1 * sz[id[1]] + l2 * sz[id[2]]);
+                    const size_t o = (size_t)(y - p->tile_y0) * tw + (x - p->tile_x0);
+                    if (!(z >= 0.0f && z <= 1.0f) || !(z < zndc[o])) continue;      /* viewport depth range, depth test Less */
+                    const double q0 = l0 * iw[id[0]], q1 = l1 * iw[id[1]], q2 = l2 * iw[id[2]], qs = q0 + q1 + q2;
+                    double bb[3];
+                    for (int k = 0; k < 3; k++) bb[k] = (q0 * poly[id[0]].b[k] + q1 * poly[id[1]].b[k] + q2 * poly[id[2]].b[k]) / qs;
+                    zndc[o] = z; prim[o] = (uint32_t)t;
+                    bary[2 * o] = (float)bb[1]; bary[2 * o + 1] = (float)bb[2];
+                }
+            }
+        }
     }
 }
 

@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLigh
     if (tx >= tile.w || ty >= tile.h) return;
     const size_t o = (size_t)ty * tile.w + tx;
     const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
-    const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
+    float tmin, tmax;
+    primary_range(cam, d, tmin, tmax);
+    const Hit h = trace(s, cam.eye, d, tmin, tmax);
     if (h.prim == 0xffffffffu) {
         out.depth[o] = -1.0f; out.prim[o] = 0xffffffffu; out.normal[o] = 0u; out.bary[o] = make_float2(0.f, 0.f);
         if (pixmask) pixmask[o] = 0;
@@ -201,7 +203,9 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
         t = depth[o];
         id = prim[o];
     } else {
-        const Hit h = trace(s, cam.eye, d, 0.0f, 3.402823466e+38f);
+        float tmin, tmax;
+        primary_range(cam, d, tmin, tmax);
+        const Hit h = trace(s, cam.eye, d, tmin, tmax);
         t = h.t;
         id = h.prim;
     }

@@ -319,6 +319,11 @@ bool primary_basis(const rc_camera& c, DCamera& out)
     out.dx = make_float3((float)(dx[0] * sc), (float)(dx[1] * sc), (float)(dx[2] * sc));
     out.dy = make_float3((float)(dy[0] * sc), (float)(dy[1] * sc), (float)(dy[2] * sc));
     out.dc = make_float3((float)(dc[0] * sc), (float)(dc[1] * sc), (float)(dc[2] * sc));
+    // S4b: rows 2 and 3 of the column-major view_proj, and the rows applied to (eye, 1) — float, fixed fma order
+    const float* M = c.view_proj;
+    const float ex = c.eye[0], ey = c.eye[1], ez = c.eye[2];
+    out.clip_z = make_float4(M[2], M[6], M[10], fmaf(M[10], ez, fmaf(M[6], ey, fmaf(M[2], ex, M[14]))));
+    out.clip_w = make_float4(M[3], M[7], M[11], fmaf(M[11], ez, fmaf(M[7], ey, fmaf(M[3], ex, M[15]))));
     return true;
 }
 
@@ -777,6 +782,7 @@ rc_status rc_update(rc_ctx* c, const rc_camera* cam, const rc_light* lights, uin
     if (!cam || (n_lights && !lights) || n_lights > RC_MAX_LIGHTS) { c->error = "rc_update: bad arguments"; return RC_ERR_INVALID_ARG; }
     if (!primary_basis(*cam, c->cam)) { c->error = "rc_update: singular view_proj matrix"; return RC_ERR_INVALID_ARG; }
     c->cam.W = (int)c->W; c->cam.H = (int)c->H;
+    c->cam.clip = (c->cfg.flags & RC_CFG_RASTER_CLIP) ? 1 : 0;
     c->lights.n = (int)n_lights;
     for (uint32_t i = 0; i < n_lights; i++) memcpy(c->lights.pos[i], lights[i].position, 16);
     c->lights.flags = flags;

@@ -46,6 +46,9 @@ struct DLights { float pos[RC_MAX_LIGHTS][4]; int n; uint32_t flags; };
 struct DCamera {                // rc_spec.h S4
     float3 eye, dx, dy, dc;
     int W, H;
+    // S4b (RC_CFG_RASTER_CLIP): rows 2 and 3 of view_proj, .w = the row applied to (eye, 1); clip == 0: rays see [0, FLT_MAX)
+    float4 clip_z, clip_w;
+    int clip;
 };
 
 struct DLevel {
@@ -93,6 +96,18 @@ __device__ __forceinline__ float3 primary_dir(const DCamera& c, int x, int y)
     float3 q = f3(fmaf(nx, c.dx.x, fmaf(ny, c.dy.x, c.dc.x)), fmaf(nx, c.dx.y, fmaf(ny, c.dy.y, c.dc.y)),
                   fmaf(nx, c.dx.z, fmaf(ny, c.dy.z, c.dc.z)));
     return vnormalize(q);
+}
+
+// S4b: the part of a primary ray between the near and far planes of view_proj (the reference's clip volume, depth 0..1:
+// src/camera.rs:77-79) — z_clip(t) = z0 + t*zd >= 0 and z_clip(t) <= w_clip(t) = w0 + t*wd
+__device__ __forceinline__ void primary_range(const DCamera& c, float3 d, float& tmin, float& tmax)
+{
+    tmin = 0.0f; tmax = 3.402823466e+38f;
+    if (!c.clip) return;
+    const float zd = vdot(xyz(c.clip_z), d), wd = vdot(xyz(c.clip_w), d);
+    if (zd > 0.0f) tmin = fmaxf(-c.clip_z.w / zd, 0.0f);
+    const float g = zd - wd;
+    if (g > 0.0f) tmax = (c.clip_w.w - c.clip_z.w) / g;
 }
 
 // ------------------------------------------------------------------ closest hit (S5)
