@@ -81,25 +81,11 @@ __device__ __forceinline__ void gather_axis(int coord, int P, int gmax, int& i0,
 // the very expression the gather will evaluate (decoded normal, same dot product) and stores its mask of
 // directions with cs_d > 0 (D0^2 <= 16 bits); k_probes ORs the masks of the pixels each level-0 probe serves
 // and k_need carries the result up the cascade.
-__global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out,
-                                                    int DD0, const float* __restrict__ dirs0, uint16_t* __restrict__ pixmask)
+// everything k_gbuffer stores for one pixel once its closest hit is known (shared by the BVH and the binned variant)
+__device__ __forceinline__ void gbuffer_store(const DScene& s, const DCamera& cam, const DLights& L, const TileRect& tile, const GBufferOut& out,
+                                              int DD0, const float* s_dirs, uint16_t* __restrict__ pixmask, int tx, int ty, float3 d, const Hit& h)
 {
-    __shared__ float s_dirs[3 * 16];
-    if (pixmask) {
-        if (threadIdx.x < 3 * DD0) s_dirs[threadIdx.x] = dirs0[threadIdx.x];
-        __syncthreads();
-    }
-    // a block covers 32x8 pixels; each warp an 8x4 pixel tile (compact frustum -> coherent traversal; four
-    // 32-byte row segments per store)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int ty = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
-    if (tx >= tile.w || ty >= tile.h) return;
     const size_t o = (size_t)ty * tile.w + tx;
-    const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
-    float tmin, tmax;
-    primary_range(cam, d, tmin, tmax);
-    const Hit h = trace(s, cam.eye, d, tmin, tmax);
     if (h.prim == 0xffffffffu) {
         out.depth[o] = -1.0f; out.prim[o] = 0xffffffffu; out.normal[o] = 0u; out.bary[o] = make_float2(0.f, 0.f);
         if (pixmask) pixmask[o] = 0;
@@ -130,6 +116,294 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLigh
         }
         pixmask[o] = (uint16_t)m;
     }
+}
+
+__global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out,
+                                                    int DD0, const float* __restrict__ dirs0, uint16_t* __restrict__ pixmask)
+{
+    __shared__ float s_dirs[3 * 16];
+    if (pixmask) {
+        if (threadIdx.x < 3 * DD0) s_dirs[threadIdx.x] = dirs0[threadIdx.x];
+        __syncthreads();
+    }
+    // a block covers 32x8 pixels; each warp an 8x4 pixel tile (compact frustum -> coherent traversal; four
+    // 32-byte row segments per store)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int ty = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (tx >= tile.w || ty >= tile.h) return;
+    const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
+    float tmin, tmax;
+    primary_range(cam, d, tmin, tmax);
+    const Hit h = trace(s, cam.eye, d, tmin, tmax);
+    gbuffer_store(s, cam, L, tile, out, DD0, s_dirs, pixmask, tx, ty, d, h);
+}
+
+// ------------------------------------------------------------------ primary visibility by triangle binning
+// Primary rays share their origin, so "which triangles can a pixel's ray hit" is a 2-D question: the triangles whose
+// projection covers the pixel centre.  k_bin projects every triangle with the frame's view_proj (vs_main,
+// src/shader.wgsl:30-43), and appends it to the candidate list of every 16x16-pixel tile its projection (grown by one
+// pixel) touches; k_gbuffer_binned then runs S5 — the same tri_test arithmetic as the BVH path — for every pixel of a
+// tile over the tile's staged candidates and keeps min (t, id).  Closest hits are defined over ALL triangles (S5), and
+// a triangle S5 accepts for a pixel projects onto that pixel's centre to within float rounding (sub-pixel), so the
+// conservative candidate set gives bit-identical hits.  Per pixel this costs ~10 cheaply rejected candidates instead of
+// ~11 two-box node visits + 5.5 triangle tests (ncu r1: 1410 thread-instructions per pixel, 69 % of them traversal).
+// Lists have a fixed capacity (kBinCap per tile, no count / scan / fill passes): a tile with more candidates — distant,
+// finely tessellated geometry — traces its pixels through the BVH instead, where the BVH is the better structure anyway.
+constexpr int kBinTile = 16, kBinCap = 96;
+
+struct BinTri {            // projection of one triangle: screen-space bounds (pixel-centre units) and edge functions
+    int x0, x1, y0, y1;    // inclusive pixel range, already grown by one pixel and clamped to the tile rect; x1 < x0: nothing
+    float ea[3], eb[3], ec[3];   // edge k: ea*x + eb*y + ec >= 0 inside (valid when `edges`)
+    int edges;
+};
+
+__device__ __forceinline__ BinTri bin_project(const DCamera& cam, const TileRect& tile, float4 a, float4 e1, float4 e2)
+{
+    BinTri r;
+    r.x0 = r.y0 = 0; r.x1 = r.y1 = -1; r.edges = 0;
+    const float3 v[3] = {xyz(a), vadd(xyz(a), xyz(e1)), vadd(xyz(a), xyz(e2))};
+    float cx[3], cy[3], cw[3];
+    float wmax = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        cx[k] = fmaf(cam.row_x.z, v[k].z, fmaf(cam.row_x.y, v[k].y, fmaf(cam.row_x.x, v[k].x, cam.row_x.w)));
+        cy[k] = fmaf(cam.row_y.z, v[k].z, fmaf(cam.row_y.y, v[k].y, fmaf(cam.row_y.x, v[k].x, cam.row_y.w)));
+        cw[k] = fmaf(cam.row_w.z, v[k].z, fmaf(cam.row_w.y, v[k].y, fmaf(cam.row_w.x, v[k].x, cam.row_w.w)));
+        wmax = fmaxf(wmax, fabsf(cw[k]));
+    }
+    // points in front of the eye plane: w >= weps.  A ray only ever hits points with w > 0; the slab between 0 and weps
+    // is covered by treating every triangle that reaches into it as touching the whole screen.
+    const float weps = 1e-4f * wmax + 1e-30f;
+    const bool in[3] = {cw[0] > weps, cw[1] > weps, cw[2] > weps};
+    if (!(in[0] || in[1] || in[2])) {
+        if (cw[0] > 0.0f || cw[1] > 0.0f || cw[2] > 0.0f || !(wmax == wmax)) { r.x0 = 0; r.y0 = 0; r.x1 = tile.w - 1; r.y1 = tile.h - 1; }
+        return r;
+    }
+    const float W = (float)cam.W, H = (float)cam.H;
+    float sx[3], sy[3];
+    float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+    bool clipped = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (in[k]) {
+            const float iw = 1.0f / cw[k];
+            sx[k] = (cx[k] * iw * 0.5f + 0.5f) * W - 0.5f;            // pixel-centre units: pixel px has its centre at px
+            sy[k] = (1.0f - (cy[k] * iw * 0.5f + 0.5f)) * H - 0.5f;
+            xmin = fminf(xmin, sx[k]); xmax = fmaxf(xmax, sx[k]); ymin = fminf(ymin, sy[k]); ymax = fmaxf(ymax, sy[k]);
+        }
+        // an edge that crosses the plane w = weps contributes its crossing point (the part in front of the plane is the convex
+        // hull of the kept vertices and the crossing points, so their bounding box bounds its projection)
+        const int k1 = (k + 1) % 3;
+        if (in[k] != in[k1]) {
+            clipped = true;
+            const float tt = (weps - cw[k]) / (cw[k1] - cw[k]);
+            const float px = fmaf(tt, cx[k1] - cx[k], cx[k]), py = fmaf(tt, cy[k1] - cy[k], cy[k]);
+            const float iw = 1.0f / weps;
+            const float qx = (px * iw * 0.5f + 0.5f) * W - 0.5f, qy = (1.0f - (py * iw * 0.5f + 0.5f)) * H - 0.5f;
+            xmin = fminf(xmin, qx); xmax = fmaxf(xmax, qx); ymin = fminf(ymin, qy); ymax = fmaxf(ymax, qy);
+        }
+    }
+    if (!(xmin == xmin) || !(xmax == xmax) || !(ymin == ymin) || !(ymax == ymax)) {     // NaN anywhere: the whole tile rect
+        r.x0 = 0; r.y0 = 0; r.x1 = tile.w - 1; r.y1 = tile.h - 1;
+        return r;
+    }
+    // clamp before the int conversion (projections near the eye plane reach 1e30 pixels); grown by 4 pixels when clipped
+    // (the crossing points are rounded at a much larger scale than the kept vertices)
+    const float grow = clipped ? 4.0f : 0.0f;
+    xmin = fminf(fmaxf(xmin - grow, -1.0e6f), 1.0e6f); xmax = fminf(fmaxf(xmax + grow, -1.0e6f), 1.0e6f);
+    ymin = fminf(fmaxf(ymin - grow, -1.0e6f), 1.0e6f); ymax = fminf(fmaxf(ymax + grow, -1.0e6f), 1.0e6f);
+    const int x0 = (int)floorf(xmin) - 1 - tile.x0, x1 = (int)ceilf(xmax) + 1 - tile.x0;
+    const int y0 = (int)floorf(ymin) - 1 - tile.y0, y1 = (int)ceilf(ymax) + 1 - tile.y0;
+    if (x1 < 0 || y1 < 0 || x0 >= tile.w || y0 >= tile.h) return r;
+    r.x0 = max(x0, 0); r.y0 = max(y0, 0); r.x1 = min(x1, tile.w - 1); r.y1 = min(y1, tile.h - 1);
+    // edge functions in tile-relative pixel coordinates, oriented so that the inside is >= 0
+    const float area = clipped ? 0.0f : (sx[1] - sx[0]) * (sy[2] - sy[0]) - (sx[2] - sx[0]) * (sy[1] - sy[0]);
+    if (fabsf(area) > 1e-3f && fabsf(xmin) < 3.0e4f && fabsf(xmax) < 3.0e4f && fabsf(ymin) < 3.0e4f && fabsf(ymax) < 3.0e4f) {
+        const float sg = area < 0.0f ? -1.0f : 1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i0 = (k + 1) % 3, i1 = (k + 2) % 3;
+            const float A = sg * (sy[i0] - sy[i1]), B = sg * (sx[i1] - sx[i0]);
+            // E(x, y) = A*(x - sx[i0]) + B*(y - sy[i0]) with (x, y) in frame pixels; shift to tile-relative pixels
+            r.ea[k] = A; r.eb[k] = B;
+            r.ec[k] = -(A * (sx[i0] - (float)tile.x0) + B * (sy[i0] - (float)tile.y0));
+        }
+        r.edges = 1;
+    }
+    return r;
+}
+
+// does the projected triangle (grown by ~1.5 pixels) reach the 16x16 tile (bx, by)?  Conservative: false only when the
+// whole tile lies outside one edge
+__device__ __forceinline__ bool bin_touches(const BinTri& t, int bx, int by)
+{
+    if (!t.edges) return true;
+    const float xa = (float)(bx * kBinTile) - 1.5f, xb = (float)(bx * kBinTile + kBinTile - 1) + 1.5f;
+    const float ya = (float)(by * kBinTile) - 1.5f, yb = (float)(by * kBinTile + kBinTile - 1) + 1.5f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float A = t.ea[k], B = t.eb[k];
+        const float emax = A * (A >= 0.0f ? xb : xa) + B * (B >= 0.0f ? yb : ya) + t.ec[k];
+        // slack for the rounding of the edge function itself (coordinates up to ~1e4 pixels)
+        if (emax < -1e-3f * (fabsf(A) + fabsf(B)) * 16.0f - 1e-4f * fabsf(t.ec[k])) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void bin_append(unsigned int* __restrict__ count, uint32_t* __restrict__ lists, int tile_id, uint32_t tri)
+{
+    const unsigned slot = atomicAdd(count + tile_id, 1u);
+    if (slot < (unsigned)kBinCap) lists[(size_t)tile_id * kBinCap + slot] = tri;
+}
+
+// A triangle that touches more than kBinHuge tiles (a wall seen from inside the room covers thousands) is not binned at
+// all: it goes to the frame's "huge" list (its tile range + edge functions, 64 bytes), and every tile's block tests the
+// whole list against its own tile — 256 threads, a few hundred entries, three edge evaluations each.  Walking such ranges
+// in k_bin serialised a handful of warps for a millisecond (first version: living_room 4K 1.09 ms, test_room 0.54 ms).
+constexpr int kBinHuge = 512, kBinBlock = 128;
+struct HugeTri { int bx0, bx1, by0, by1; float ea[3], eb[3], ec[3]; uint32_t tri; int edges; int pad; };
+static_assert(sizeof(HugeTri) == 64, "HugeTri is fetched as four 16-byte vectors");
+
+// One thread per leaf-ordered triangle projects it; the (triangle, tile) pairs of a block's triangles are then flattened
+// (block-wide prefix sum of the per-triangle tile counts) and dealt out to the threads pair by pair, so a triangle with 400
+// tiles and one with 1 tile cost their block the same per pair, and the appends (one returning atomic each) of different
+// threads are in flight together.  (First version: per-thread / per-warp loops — 122 us at 4K, 6 % of the warp slots busy.)
+__global__ void __launch_bounds__(kBinBlock) k_bin(DScene s, DCamera cam, TileRect tile, uint32_t n_tris, int ntx, unsigned int* __restrict__ count,
+                                                   uint32_t* __restrict__ lists, unsigned int* __restrict__ huge_count, HugeTri* __restrict__ huge)
+{
+    __shared__ BinTri s_t[kBinBlock];
+    __shared__ int s_pre[kBinBlock + 1];
+    __shared__ int s_wsum[kBinBlock / 32];
+    const uint32_t i = blockIdx.x * kBinBlock + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    BinTri t;
+    t.x0 = t.y0 = 0; t.x1 = t.y1 = -1; t.edges = 0;
+    if (i < n_tris) t = bin_project(cam, tile, __ldg(s.tri_geom + 3 * (size_t)i), __ldg(s.tri_geom + 3 * (size_t)i + 1), __ldg(s.tri_geom + 3 * (size_t)i + 2));
+    const bool any = t.x1 >= t.x0 && t.y1 >= t.y0;
+    // from here on the ranges are in TILES
+    t.x0 /= kBinTile; t.x1 /= kBinTile; t.y0 /= kBinTile; t.y1 /= kBinTile;
+    int ntl = any ? (t.x1 - t.x0 + 1) * (t.y1 - t.y0 + 1) : 0;
+    if (ntl > kBinHuge) {
+        HugeTri h;
+        h.bx0 = t.x0; h.bx1 = t.x1; h.by0 = t.y0; h.by1 = t.y1; h.tri = i; h.edges = t.edges; h.pad = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { h.ea[k] = t.ea[k]; h.eb[k] = t.eb[k]; h.ec[k] = t.ec[k]; }
+        huge[atomicAdd(huge_count, 1u)] = h;
+        ntl = 0;
+    }
+    s_t[threadIdx.x] = t;
+    // block-wide exclusive prefix sum of ntl
+    int pre = ntl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if ((int)lane >= o) pre += v; }
+    if (lane == 31) s_wsum[wid] = pre;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < kBinBlock / 32; k++) if (k < (int)wid) base += s_wsum[k];
+    s_pre[threadIdx.x] = base + pre - ntl;
+    if (threadIdx.x == kBinBlock - 1) s_pre[kBinBlock] = base + pre;
+    __syncthreads();
+    const int total = s_pre[kBinBlock];
+    for (int pidx = threadIdx.x; pidx < total; pidx += kBinBlock) {
+        int lo = 0, hi = kBinBlock - 1;          // the last m with s_pre[m] <= pidx (entries with ntl = 0 repeat a prefix: take the last)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_pre[mid] <= pidx) lo = mid; else hi = mid - 1;
+        }
+        const BinTri& b = s_t[lo];
+        const int k = pidx - s_pre[lo], wx = b.x1 - b.x0 + 1;
+        const int bx = b.x0 + k % wx, by = b.y0 + k / wx;
+        if (bin_touches(b, bx, by)) bin_append(count, lists, by * ntx + bx, blockIdx.x * kBinBlock + (uint32_t)lo);
+    }
+}
+
+// one block per 16x16-pixel tile; warps cover 8x4 pixels each.  While a candidate is staged its projection is evaluated once
+// more against the eight 8x4 sub-tiles: a warp only runs S5 for the candidates that can reach its own pixels.
+__global__ void __launch_bounds__(kBlock) k_gbuffer_binned(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out, int DD0,
+                                                           const float* __restrict__ dirs0, uint16_t* __restrict__ pixmask, int ntx,
+                                                           unsigned int* __restrict__ count, const uint32_t* __restrict__ lists,
+                                                           const unsigned int* __restrict__ huge_count, const HugeTri* __restrict__ huge)
+{
+    __shared__ float s_dirs[3 * 16];
+    __shared__ float4 s_tri[3 * kBinCap];
+    __shared__ uint32_t s_idx[kBinCap];
+    __shared__ uint32_t s_mask[kBinCap];
+    __shared__ unsigned s_n;
+    const int tile_id = blockIdx.y * ntx + blockIdx.x;
+    if (threadIdx.x == 0) { s_n = count[tile_id]; count[tile_id] = 0u; }      // consumed: the next frame's k_bin starts from empty lists
+    if (pixmask && threadIdx.x < 3 * DD0) s_dirs[threadIdx.x] = dirs0[threadIdx.x];
+    __syncthreads();
+    const unsigned n_small = s_n;
+    __syncthreads();
+    if (n_small <= (unsigned)kBinCap) {
+        for (unsigned k = threadIdx.x; k < n_small; k += kBlock) s_idx[k] = __ldg(lists + (size_t)tile_id * kBinCap + k);
+        // the frame's huge triangles, each tested against this tile
+        const unsigned nh = __ldg(huge_count);
+        const uint4* hv = reinterpret_cast<const uint4*>(huge);
+        for (unsigned k = threadIdx.x; k < nh; k += kBlock) {
+            const uint4 q0 = __ldg(hv + 4 * (size_t)k);
+            if ((int)blockIdx.x < (int)q0.x || (int)blockIdx.x > (int)q0.y || (int)blockIdx.y < (int)q0.z || (int)blockIdx.y > (int)q0.w) continue;
+            const uint4 q1 = __ldg(hv + 4 * (size_t)k + 1), q2 = __ldg(hv + 4 * (size_t)k + 2), q3 = __ldg(hv + 4 * (size_t)k + 3);
+            BinTri b;
+            b.ea[0] = __uint_as_float(q1.x); b.ea[1] = __uint_as_float(q1.y); b.ea[2] = __uint_as_float(q1.z);
+            b.eb[0] = __uint_as_float(q1.w); b.eb[1] = __uint_as_float(q2.x); b.eb[2] = __uint_as_float(q2.y);
+            b.ec[0] = __uint_as_float(q2.z); b.ec[1] = __uint_as_float(q2.w); b.ec[2] = __uint_as_float(q3.x);
+            b.edges = (int)q3.z;
+            if (!bin_touches(b, (int)blockIdx.x, (int)blockIdx.y)) continue;
+            const unsigned slot = atomicAdd(&s_n, 1u);
+            if (slot < (unsigned)kBinCap) s_idx[slot] = q3.y;
+        }
+    }
+    __syncthreads();
+    const unsigned n = s_n;
+    const bool binned = n <= (unsigned)kBinCap;
+    if (binned) {
+        for (unsigned k = threadIdx.x; k < n; k += kBlock) {
+            const uint32_t tri = s_idx[k];
+            const float4 a = __ldg(s.tri_geom + 3 * (size_t)tri), e1 = __ldg(s.tri_geom + 3 * (size_t)tri + 1), e2 = __ldg(s.tri_geom + 3 * (size_t)tri + 2);
+            s_tri[3 * k] = a; s_tri[3 * k + 1] = e1; s_tri[3 * k + 2] = e2;
+            // which of the tile's eight 8x4-pixel sub-tiles (= warps) the projection, grown by 1.5 pixels, can reach
+            const BinTri b = bin_project(cam, tile, a, e1, e2);
+            uint32_t m = 0xffu;
+            if (b.edges) {
+                m = 0u;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const float xa = (float)(blockIdx.x * kBinTile + (w & 1) * 8) - 1.5f, xb = xa + 7.0f + 3.0f;
+                    const float ya = (float)(blockIdx.y * kBinTile + (w >> 1) * 4) - 1.5f, yb = ya + 3.0f + 3.0f;
+                    bool in = true;
+#pragma unroll
+                    for (int e = 0; e < 3; e++) {
+                        const float A = b.ea[e], B = b.eb[e];
+                        const float emax = A * (A >= 0.0f ? xb : xa) + B * (B >= 0.0f ? yb : ya) + b.ec[e];
+                        if (emax < -1e-3f * (fabsf(A) + fabsf(B)) * 16.0f - 1e-4f * fabsf(b.ec[e])) in = false;
+                    }
+                    if (in) m |= 1u << w;
+                }
+            }
+            s_mask[k] = m;
+        }
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * kBinTile + (warp & 1) * 8 + (lane & 7);
+    const int ty = blockIdx.y * kBinTile + (warp >> 1) * 4 + (lane >> 3);
+    if (tx >= tile.w || ty >= tile.h) return;
+    const float3 d = primary_dir(cam, tile.x0 + tx, tile.y0 + ty);
+    float tmin, tmax;
+    primary_range(cam, d, tmin, tmax);
+    Hit h;
+    if (binned) {
+        h.t = tmax; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+        for (unsigned k = 0; k < n; k++)
+            if ((s_mask[k] >> warp) & 1u) tri_test_v(s_tri[3 * k], s_tri[3 * k + 1], s_tri[3 * k + 2], cam.eye, d, tmin, tmax, h);
+        if (h.prim == 0xffffffffu) h.t = -1.0f;
+    } else {
+        h = trace(s, cam.eye, d, tmin, tmax);
+    }
+    gbuffer_store(s, cam, L, tile, out, DD0, s_dirs, pixmask, tx, ty, d, h);
 }
 
 // fs_main for every covered pixel from the stored visibility (on demand; not part of the per-frame GI path)
@@ -1663,6 +1937,22 @@ void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileR
 {
     dim3 grid((tile.w + 31) / 32, (tile.h + 7) / 8);
     k_gbuffer<<<grid, kBlock, 0, st>>>(s, cam, L, tile, out, DD0, dirs0, DD0 <= 16 ? pixmask : nullptr);
+}
+
+size_t bin_tiles(TileRect tile) { return (size_t)((tile.w + kBinTile - 1) / kBinTile) * ((tile.h + kBinTile - 1) / kBinTile); }
+size_t bin_list_entries(TileRect tile) { return bin_tiles(tile) * kBinCap; }
+
+size_t bin_huge_bytes(uint32_t n_leaf_tris) { return (size_t)(n_leaf_tris ? n_leaf_tris : 1) * sizeof(HugeTri); }
+
+void launch_gbuffer_binned(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, int DD0,
+                           const float* dirs0, uint16_t* pixmask, uint32_t n_leaf_tris, unsigned int* bin_count, uint32_t* bin_lists,
+                           unsigned int* huge_count, void* huge, cudaStream_t st)
+{
+    const int ntx = (tile.w + kBinTile - 1) / kBinTile, nty = (tile.h + kBinTile - 1) / kBinTile;
+    cudaMemsetAsync(huge_count, 0, sizeof(unsigned int), st);
+    if (n_leaf_tris) k_bin<<<(n_leaf_tris + kBinBlock - 1) / kBinBlock, kBinBlock, 0, st>>>(s, cam, tile, n_leaf_tris, ntx, bin_count, bin_lists, huge_count, (HugeTri*)huge);
+    k_gbuffer_binned<<<dim3(ntx, nty), kBlock, 0, st>>>(s, cam, L, tile, out, DD0, dirs0, DD0 <= 16 ? pixmask : nullptr, ntx, bin_count, bin_lists,
+                                                        huge_count, (const HugeTri*)huge);
 }
 
 void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, const float* depth, const uint32_t* prim,

@@ -35,6 +35,15 @@ struct EntryPlan { unsigned group_offset[RC_MAX_LEVELS + 1]; int g[RC_MAX_LEVELS
 // the gather will weight with cs_d > 0
 void launch_gbuffer(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, int DD0,
                     const float* dirs0, uint16_t* pixmask, cudaStream_t st);
+// Primary visibility by triangle binning (k_bin + k_gbuffer_binned): same outputs as launch_gbuffer, bit for bit.
+// bin_count: bin_tiles(tile) counters, all zero when the frame starts (the raster kernel zeroes what it consumes);
+// bin_lists: bin_list_entries(tile) triangle slots; n_leaf_tris: entries of DScene::tri_geom / 3
+size_t bin_tiles(TileRect tile);
+size_t bin_list_entries(TileRect tile);
+size_t bin_huge_bytes(uint32_t n_leaf_tris);     // the frame's list of triangles too large to bin (tested by every tile)
+void launch_gbuffer_binned(const DScene& s, const DCamera& cam, const DLights& L, TileRect tile, GBufferOut out, int DD0,
+                           const float* dirs0, uint16_t* pixmask, uint32_t n_leaf_tris, unsigned int* bin_count, uint32_t* bin_lists,
+                           unsigned int* huge_count, void* huge, cudaStream_t st);
 // direction culling, level lv (bottom-up): appends the requests of `need` (bits at resolution Dr, probes of lv) to
 // `list` / `count` and pushes them to the upper level's masks `need_up` (has_upper: 0 none, 1 same resolution
 // [level 0 -> 1], 2 expanded 2x; up_words = mask words per upper probe) through k_link's tables; clear: zero the

@@ -49,6 +49,8 @@ struct DCamera {                // rc_spec.h S4
     // S4b (RC_CFG_RASTER_CLIP): rows 2 and 3 of view_proj, .w = the row applied to (eye, 1); clip == 0: rays see [0, FLT_MAX)
     float4 clip_z, clip_w;
     int clip;
+    // rows 0, 1, 3 of view_proj (x_clip, y_clip, w_clip of a world point): the triangle binning of the primary-visibility pass
+    float4 row_x, row_y, row_w;
 };
 
 struct DLevel {
@@ -117,6 +119,36 @@ __device__ __forceinline__ float safe_inv(float d)
 {
     // |d| below 1e-20 would make 1/d overflow; a slab this parallel can only be crossed beyond any tmax
     return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d));
+}
+
+// S5 on a triangle already in registers / shared memory: a = (v0, id bits), b = (e1, -), c = (e2, -).
+// Bit-identical to tri_test; rejects the two common miss cases before the IEEE division:
+//   u < 0:  u = fl(a * fl(1/det)) with a = dot(s, p).  Opposite signs of a and det make the exact product negative, and with
+//           |a| > 1e-30 and |det| < 1e30 its magnitude is far above the underflow threshold, so fl() cannot return -0 (which
+//           S5's `u >= 0` would accept).
+//   u > 1:  |a| > 1.0001 |det| puts the exact quotient above 1 by 1e-4, a thousand ulps beyond what the two roundings move.
+__device__ __forceinline__ void tri_test_v(float4 a, float4 b, float4 c, float3 o, float3 d, float tmin, float tmax, Hit& h)
+{
+    const float3 e1 = xyz(b), e2 = xyz(c);
+    const float3 p = vcross(d, e2);
+    const float det = vdot(e1, p);
+    if (!(det != 0.0f)) return;
+    const float3 s = vsub(o, xyz(a));
+    const float un = vdot(s, p);
+    const float ad = fabsf(det), au = fabsf(un);
+    if (ad < 1e30f && ad > 1e-30f) {
+        if (((un < 0.0f) != (det < 0.0f)) && au > 1e-30f) return;
+        if (au > 1.0001f * ad && au < 1e30f) return;
+    }
+    const float inv = 1.0f / det;
+    const float u = un * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return;
+    const float3 q = vcross(s, e1);
+    const float v = vdot(d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return;
+    const float t = vdot(e2, q) * inv;
+    const uint32_t id = __float_as_uint(a.w);
+    if (t >= tmin && t < tmax && (t < h.t || (t == h.t && id < h.prim))) { h.t = t; h.u = u; h.v = v; h.prim = id; }
 }
 
 __device__ __forceinline__ void tri_test(const float4* __restrict__ g, float3 o, float3 d, float tmin, float tmax, Hit& h)

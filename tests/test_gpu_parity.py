@@ -506,6 +506,37 @@ def test_raster_clip_matches_oracle_and_raster_restatement(name, W, H, near, far
         assert psnr(E[..., :3], Eo[..., :3], peak) >= 50.0
 
 
+@pytest.mark.culled
+@pytest.mark.parametrize("name,W,H,tile", [("living_room", 640, 360, None), ("teapot", 480, 270, None), ("sonic", 300, 400, None),
+                                           ("cube", 256, 256, None), ("test_room", 333, 187, (40, 30, 200, 120)),
+                                           ("living_room", 3840, 2160, (0, 1080, 3840, 272))])
+def test_binned_primary_visibility_equals_bvh_traversal(name, W, H, tile):
+    """k_bin + k_gbuffer_binned (optional path, rc_set_tuning "gbuffer_binned": triangles projected with view_proj and binned
+    into 16x16-pixel tiles, S5 over each tile's candidates) against the per-pixel BVH traversal: triangle id, depth, normal and irradiance bit for bit, for orbit
+    cameras, for cameras INSIDE the scene (triangles crossing the eye plane), with the raster clip, and in a tile context."""
+    osc = oracle_scene(name)
+    cams = [frame_setup(name, W, H, frame=f)[0] for f in (0, 9)]
+    # a camera in the middle of the scene looking along +x: walls / floor cross the eye plane
+    c = 0.5 * (osc.bbox_min + osc.bbox_max)
+    st_in = rc.AppState()
+    st_in.uniform_camera = rc.UniformCamera.look_at(c, c + np.array([1.0, -0.2, 0.3], np.float32), rc.Projection.new(W, H, 60.0, 0.05, 1000.0))
+    st_in.light_position = rc.scenes.bench_light(osc.bbox_min, osc.bbox_max)
+    cams.append(st_in)
+    for flags in (0, _ffi.RC_CFG_RASTER_CLIP):
+        r = rc.DefaultRenderer.new(0, (W, H), cams[0], rc.scenes.scene_path(name), rc.CascadeConfig(tile=tile, flags=flags))
+        for st in cams:
+            got = []
+            for binned in (0, 1):
+                r.set_tuning("gbuffer_binned", binned)
+                r.update(st)
+                r.render()
+                got.append([r.read_target(t).copy() for t in (_ffi.RC_TARGET_PRIM, _ffi.RC_TARGET_DEPTH, _ffi.RC_TARGET_NORMAL)] +
+                           [r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16).copy()])
+            for a, b in zip(*got):
+                assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+        assert (got[1][0] != 0xFFFFFFFF).any()
+
+
 def test_resize_matches_fresh_context():
     st, _, _ = frame_setup("cube", 96, 64)
     a = render_product("cube", 96, 64, st)
