@@ -43,7 +43,13 @@ enum {
 /* rc_config.flags */
 #define RC_CFG_SEPARATE_MERGE 0x1u /* run march and merge as separate kernels (debug / A-B) instead of the fused path */
 #define RC_CFG_NO_TEXTURES    0x2u /* ignore map_Kd / map_Bump (as if the files were missing, src/primitives.rs:390-404) */
-#define RC_CFG_HALO_EXCHANGE  0x4u /* reserved: tile mode with exchanged (not recomputed) halos; today halos are always recomputed */
+/* Tiled context with EXCHANGED instead of recomputed halos: cascade levels >= 1 are marched only for the probes
+ * whose anchor pixel lies in this context's tile ("owned"); the caller moves two things between the ranks with any transport
+ * (NCCL send/recv in radiancecascade_b200/distributed.py): the request masks of the probes a rank needs but does not own, to
+ * their owners, between rc_render_begin and rc_render_lists; and each finished level's child averages of owned probes to the
+ * ranks whose sub-grid holds them, after every rc_render_level.  Level 0 and an unmaterialised top level are never exchanged.
+ * rc_render on such a context returns RC_ERR_STATE. */
+#define RC_CFG_HALO_EXCHANGE  0x4u
 /* The reference's clip volume and depth test for primary visibility (rc_spec.h S4b): pixels and probe anchors see the closest
  * fragment between the near and far planes of the projection inside view_proj (src/camera.rs:77-79; src/app.rs:26 near 0.1,
  * far 100), exactly what the render pass keeps (Depth32Float, Less, clear 1.0: src/renderer.rs:354-360, 585-592).
@@ -242,8 +248,26 @@ rc_status rc_trace_rays(rc_ctx* ctx, const float* rays, uint32_t n, float* hits)
  * hit points.  in: float[n][8] = prim id bits, u, v, pad, view-origin xyz, pad. out: float[n][4]. */
 rc_status rc_shade_points(rc_ctx* ctx, const float* in, uint32_t n, float* out);
 
-/* Multi-GPU halo exchange (RC_CFG_HALO_EXCHANGE): device pointer + geometry of the
- * merged level so a peer (NCCL send/recv or P2P) can fill the halo ring. */
+/* Halo exchange: what the caller needs to move level `level`'s request masks and child averages.  Both buffers are row-major over
+ * the context's probe sub-grid [sub_h][sub_w]: need = need_words_per_probe uint32 per probe (requests this rank's pixels make of
+ * the probe), avg = avg_float4_per_probe float4 per probe (the averages the level below merges from, written for the owned
+ * probes by rc_render_level).  own_* = the owned probes (inclusive sub-grid coordinates; own_x1 < own_x0: none).
+ * exchanged = 0 for level 0 and for a top level that is never materialised. */
+typedef struct rc_exchange_info {
+    void*    need_ptr;
+    void*    avg_ptr;
+    uint32_t need_words_per_probe, avg_float4_per_probe;
+    int32_t  px0, py0;
+    uint32_t sub_w, sub_h;
+    int32_t  own_x0, own_y0, own_x1, own_y1;
+    uint32_t exchanged, pad;
+} rc_exchange_info;
+rc_status rc_exchange_level_info(rc_ctx* ctx, uint32_t level, rc_exchange_info* out);
+/* Halo exchange, between rc_render_begin and the first rc_render_level: builds the ray lists from the request masks (which the
+ * caller has completed with the other ranks' requests) for the probes this context owns. */
+rc_status rc_render_lists(rc_ctx* ctx, void* stream);
+
+/* Device pointer + size of the merged level (debug / custom transports). */
 rc_status rc_cascade_device_ptr(rc_ctx* ctx, uint32_t level, void** dev_ptr, size_t* bytes);
 rc_status rc_irradiance_device_ptr(rc_ctx* ctx, void** dev_ptr, size_t* bytes);
 /* Split rc_render for halo exchange: levels are processed top-down; after

@@ -53,6 +53,13 @@ class rc_level_info(C.Structure):
                 ("texel_offset", C.c_uint64), ("texel_count", C.c_uint64), ("t_begin", C.c_float), ("t_end", C.c_float)]
 
 
+class rc_exchange_info(C.Structure):
+    _fields_ = [("need_ptr", C.c_void_p), ("avg_ptr", C.c_void_p), ("need_words_per_probe", C.c_uint32), ("avg_float4_per_probe", C.c_uint32),
+                ("px0", C.c_int32), ("py0", C.c_int32), ("sub_w", C.c_uint32), ("sub_h", C.c_uint32),
+                ("own_x0", C.c_int32), ("own_y0", C.c_int32), ("own_x1", C.c_int32), ("own_y1", C.c_int32),
+                ("exchanged", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class rc_scene_info(C.Structure):
     _fields_ = [("num_models", C.c_uint32), ("num_vertices", C.c_uint32), ("num_triangles", C.c_uint32),
                 ("num_materials", C.c_uint32), ("num_textures", C.c_uint32), ("bvh_nodes", C.c_uint32),
@@ -70,6 +77,8 @@ SYMBOLS = {
     "rc_update": (C.c_int32, [_P, C.POINTER(rc_camera), C.POINTER(rc_light), C.c_uint32, C.c_uint32]),
     "rc_resize": (C.c_int32, [_P, C.c_uint32, C.c_uint32]),
     "rc_set_tile": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "rc_render_lists": (C.c_int32, [_P, _P]),
+    "rc_exchange_level_info": (C.c_int32, [_P, C.c_uint32, C.POINTER(rc_exchange_info)]),
     "rc_render": (C.c_int32, [_P, _P]),
     "rc_render_begin": (C.c_int32, [_P, _P]),
     "rc_render_level": (C.c_int32, [_P, C.c_uint32, _P]),

@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
                                                  const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
                                                  uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
                                                  uint32_t* __restrict__ list, unsigned int* __restrict__ count, int clear, int trigger, int dir_major,
-                                                 int tile_order)
+                                                 int tile_order, int append, int4 own)
 {
     // The per-level launches form a chain of short, latency-bound waves.  Launched with programmatic stream
     // serialization (launch_need pdl) level i+1 is set up while level i still runs: it may read what kernels before
@@ -681,6 +681,12 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
         cudaGridDependencySynchronize();
         r = need[gi];
         if (valid == 0.0f) r = 0u;
+        if (append && own.z >= 0) {
+            // halo exchange: this rank marches only the probes it OWNS (own = x0, y0, x1, y1 inclusive, sub-grid coordinates);
+            // the requests of the others were sent to their owners before this launch and are dropped here
+            const int ppx = (int)(probe % (uint32_t)lv.sw), ppy = (int)(probe / (uint32_t)lv.sw);
+            if (ppx < own.x || ppx > own.z || ppy < own.y || ppy > own.w) r = 0u;
+        }
         if (w == words - 1 && (bits & 31)) r &= (1u << (bits & 31)) - 1u;
         // consume and clear: the masks of levels >= 1 are accumulated by atomicOr, so they must be empty when the next
         // frame starts (level 0 is overwritten by k_probes).  A stale bit could only ever add a ray, never lose one.
@@ -714,7 +720,8 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
             tiled = 2;
         }
     }
-    const int n = tiled == 2 ? __popcll(pm64) : __popc(r);
+    int n = tiled == 2 ? __popcll(pm64) : __popc(r);
+    if (!append) { n = 0; pm = 0u; pm64 = 0ull; }      // masks only (halo exchange, first pass): nothing is listed yet
     int pre = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if ((int)lane >= o) pre += t; }
@@ -726,7 +733,7 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
         s_base = tot ? atomicAdd(count, tot) : 0u;
     }
     __syncthreads();
-    if (dir_major) {
+    if (dir_major && append) {
         // Direction-major order inside the warp's share of the list: the warp's threads are 32 / words neighbouring
         // probes of a row; their requests are appended request by request (same direction across the probes) instead
         // of probe by probe.  A warp of k_march then marches (nearly) parallel rays from adjacent origins — same
@@ -764,7 +771,7 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
             else { const int np = p >> 2; ob = ((np & 4) | ((np & 1) << 1) | ((np >> 1) & 1)) * 4 + (p & 3); }   // Dr == 8
             list[base++] = probe * (uint32_t)bits + (uint32_t)(32 * w + ob);
         }
-    } else {
+    } else if (append) {
         unsigned base = s_base + s_warp[wid] + (unsigned)(pre - n);
         for (uint32_t m = r; m; m &= m - 1u) list[base++] = probe * (uint32_t)bits + (uint32_t)(32 * w + __ffs((int)m) - 1);
     }
@@ -2035,7 +2042,7 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
 
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
                  const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, bool pdl,
-                 bool trigger, bool dir_major, int tile_order, cudaStream_t st)
+                 bool trigger, bool dir_major, int tile_order, bool append, int4 own, cudaStream_t st)
 {
     const size_t total = (size_t)lv.sw * lv.sh * ((Dr * Dr + 31) / 32);
     if (!total) return;
@@ -2050,7 +2057,8 @@ void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const fl
     cfg.numAttrs = pdl ? 1 : 0;
     // tile order needs whole (probe, row-pair) groups per warp: 256-thread blocks and 32 words per probe at Dr = 32 guarantee it
     cudaLaunchKernelEx(&cfg, k_need, lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count, clear ? 1 : 0,
-                       trigger ? 1 : 0, dir_major ? 1 : 0, (tile_order && has_upper != 1 && (Dr == 32 || (tile_order > 1 && (Dr == 8 || Dr == 16)))) ? 1 : 0);
+                       trigger ? 1 : 0, dir_major ? 1 : 0, (tile_order && has_upper != 1 && (Dr == 32 || (tile_order > 1 && (Dr == 8 || Dr == 16)))) ? 1 : 0,
+                       append ? 1 : 0, own);
 }
 
 void launch_march_all(const DScene& s, const DLights& L, const DLevelSet& ls, const int* levels, int n, const int* map,

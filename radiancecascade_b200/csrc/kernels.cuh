@@ -50,7 +50,9 @@ void launch_gbuffer_binned(const DScene& s, const DCamera& cam, const DLights& L
 // consumed words (levels >= 1, whose masks are accumulated with atomicOr and must be empty for the next frame)
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
                  const float4* link_w, uint32_t* need, uint32_t* need_up, uint32_t* list, unsigned int* count, bool clear, bool pdl,
-                 bool trigger, bool dir_major, int tile_order, cudaStream_t st);
+                 bool trigger, bool dir_major, int tile_order, bool append, int4 own, cudaStream_t st);
+// append = false: only propagate the masks (halo exchange, first pass); append = true with own.z >= 0: list only the requests of
+// the probes inside own = (x0, y0, x1, y1), inclusive sub-grid coordinates (the probes this rank owns)
 // pdl: programmatic dependent launch on the previous level's k_need (the origins / link tables must be older);
 // trigger: the next launch in the stream is a pdl k_need, so this one may release it early;
 // dir_major: order each warp's list entries by request (direction) first, probe second;

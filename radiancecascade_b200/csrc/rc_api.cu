@@ -153,6 +153,10 @@ struct rc_ctx {
     // 0 (default): the finished tiles are gathered on rank 0 (final image gather); 1: every rank receives every tile
     // (all-gather: N times the NVLink traffic — at 8 ranks the stores cost more than the gather itself).  Same value on all ranks.
     int peer_broadcast = 0;
+    // Halo exchange (RC_CFG_HALO_EXCHANGE on a tiled context): levels >= 1 are marched only for the probes this rank owns; the
+    // caller moves request masks (before rc_render_lists) and child averages (after every rc_render_level) between the ranks
+    bool exchange_active() const { return (cfg.flags & RC_CFG_HALO_EXCHANGE) && cfg.tile_w && cfg.tile_h && cull_possible(); }
+    bool lists_pending = false;
     int gather_mma = 1;
     bool gather_sym = false;                        // the level-0 direction table is point-symmetric (gather_dirs_symmetric)
     DevBuf<float> d_axis;                           // S4: nx(x) for x < W, then ny(y) for y < H
@@ -839,6 +843,45 @@ rc_status rc_set_tile(rc_ctx* c, uint32_t x0, uint32_t y0, uint32_t w, uint32_t 
     return setup_frame(c, c->W, c->H, true);      // camera, lights, peers and tuning are untouched
 }
 
+// The k_need launches of one frame.  append = true: masks are consumed into the ray lists (and pushed up) level by level —
+// the single-pass form.  append = false: masks only (first pass of the halo exchange).
+static rc_status launch_need_chain(rc_ctx* c, cudaStream_t st, bool append)
+{
+    const uint32_t n_lists = c->top_fillable() ? c->N - 1 : c->N;
+    for (uint32_t i = 0; i < n_lists; i++) {
+        const DLevel& L = c->levels[i];
+        const int has_upper = i + 1 < n_lists ? (i == 0 ? 1 : 2) : 0;
+        const int up_res = i + 1 < c->N ? c->need_res[i + 1] : 0;
+        launch_need(L, c->need_res[i], has_upper, (up_res * up_res + 31) / 32, c->d_origin.p + L.probe_offset,
+                    c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, c->d_need.p + c->need_offset[i],
+                    has_upper ? c->d_need.p + c->need_offset[i + 1] : nullptr, c->d_list.p + c->list_offset[i],
+                    c->d_ray_count.p + i, append && i >= 1, c->need_pdl && i >= 1, c->need_pdl && i + 1 < n_lists,
+                    ((c->list_dir_major >> i) & 1) != 0, i >= 1 ? c->list_tiled : 0, append, make_int4(0, 0, -1, -1), st);
+        c->launches++;
+    }
+    return RC_OK;
+}
+
+// probes of level i this context OWNS: those whose anchor pixel (S1) lies inside the tile; inclusive sub-grid coordinates,
+// z < x when none
+static int4 owned_rect(const rc_ctx* c, uint32_t i)
+{
+    const DLevel& L = c->levels[i];
+    auto range = [](int t0, int tn, int P, int full, int sub0, int subn, int& lo, int& hi) {
+        // anchor(p) = min(p*P + P/2, full - 1) in [t0, t0 + tn)
+        lo = 1; hi = 0;
+        for (int p = sub0; p < sub0 + subn; p++) {
+            const int a = std::min(p * P + P / 2, full - 1);
+            if (a >= t0 && a < t0 + tn) { if (hi < lo) lo = p - sub0; hi = p - sub0; }
+        }
+    };
+    int x0, x1, y0, y1;
+    range(c->tile.x0, c->tile.w, L.P, (int)c->W, L.px0, L.sw, x0, x1);
+    range(c->tile.y0, c->tile.h, L.P, (int)c->H, L.py0, L.sh, y0, y1);
+    if (x1 < x0 || y1 < y0) return make_int4(1, 1, 0, 0);
+    return make_int4(x0, y0, x1, y1);
+}
+
 // stage-timing events: inside a stream capture they must become EXTERNAL event-record nodes, otherwise the host
 // cannot synchronise on / time them (cudaErrorInvalidValue)
 static cudaError_t record_event(rc_ctx* c, cudaEvent_t ev, cudaStream_t st)
@@ -893,28 +936,60 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
         }
     }
     if (c->frame_culled) {
-        // request masks bottom-up + one ray list per level; a top level that is filled needs neither
-        const uint32_t n_lists = c->top_fillable() ? c->N - 1 : c->N;
-        for (uint32_t i = 0; i < n_lists; i++) {
-            const DLevel& L = c->levels[i];
-            const int has_upper = i + 1 < n_lists ? (i == 0 ? 1 : 2) : 0;
-            const int up_res = i + 1 < c->N ? c->need_res[i + 1] : 0;
-            launch_need(L, c->need_res[i], has_upper, (up_res * up_res + 31) / 32, c->d_origin.p + L.probe_offset,
-                        c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, c->d_need.p + c->need_offset[i],
-                        has_upper ? c->d_need.p + c->need_offset[i + 1] : nullptr, c->d_list.p + c->list_offset[i],
-                        c->d_ray_count.p + i, i >= 1, c->need_pdl && i >= 1, c->need_pdl && i + 1 < n_lists,
-                        ((c->list_dir_major >> i) & 1) != 0, i >= 1 ? c->list_tiled : 0, st);
-            c->launches++;
-        }
+        // request masks bottom-up + one ray list per level; a top level that is filled needs neither.
+        // Halo exchange (RC_CFG_HALO_EXCHANGE): this pass only propagates the masks — the lists are built by rc_render_lists
+        // after the caller has sent the requests of the probes this rank does not own to their owners
+        rc_status s = launch_need_chain(c, st, !c->exchange_active());
+        if (s != RC_OK) return s;
+        c->lists_pending = c->exchange_active();
     }
     CU_OK(c, record_event(c, c->ev[EV_PROBES], st));
     CU_OK(c, cudaGetLastError());
     return RC_OK;
 }
 
+rc_status rc_render_lists(rc_ctx* c, void* stream)
+{
+    if (!c) return RC_ERR_INVALID_ARG;
+    if (!c->frame_open || !c->lists_pending) { c->error = "rc_render_lists: only after rc_render_begin of a halo-exchange context"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    // second pass over the (now complete) masks: list the requests of the probes this rank owns, clear everything.
+    // Level 0 is never exchanged: every level-0 probe of the sub-grid (the tile's probes and their one-probe ring) is marched here.
+    const uint32_t n_lists = c->top_fillable() ? c->N - 1 : c->N;
+    for (uint32_t i = 0; i < n_lists; i++) {
+        const DLevel& L = c->levels[i];
+        launch_need(L, c->need_res[i], 0, 0, c->d_origin.p + L.probe_offset, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset,
+                    c->d_need.p + c->need_offset[i], nullptr, c->d_list.p + c->list_offset[i], c->d_ray_count.p + i, i >= 1, false, false,
+                    ((c->list_dir_major >> i) & 1) != 0, i >= 1 ? c->list_tiled : 0, true, i == 0 ? make_int4(0, 0, -1, -1) : owned_rect(c, i), st);
+        c->launches++;
+    }
+    c->lists_pending = false;
+    CU_OK(c, cudaGetLastError());
+    return RC_OK;
+}
+
+rc_status rc_exchange_level_info(rc_ctx* c, uint32_t level, rc_exchange_info* out)
+{
+    if (!c || !out || level >= c->N) return RC_ERR_INVALID_ARG;
+    const DLevel& L = c->levels[level];
+    memset(out, 0, sizeof(*out));
+    const int Dr = c->need_res[level];
+    out->need_ptr = c->d_need.p + c->need_offset[level];
+    out->need_words_per_probe = (uint32_t)((Dr * Dr + 31) / 32);
+    out->avg_ptr = c->avg_of(level);
+    out->avg_float4_per_probe = level >= 1 ? (uint32_t)((L.D * L.D) / 4) : 0u;
+    out->px0 = L.px0; out->py0 = L.py0; out->sub_w = (uint32_t)L.sw; out->sub_h = (uint32_t)L.sh;
+    const int4 o = owned_rect(c, level);
+    out->own_x0 = o.x; out->own_y0 = o.y; out->own_x1 = o.z; out->own_y1 = o.w;
+    out->exchanged = (c->exchange_active() && level >= 1 && !(level + 1 == c->N && c->top_fillable())) ? 1u : 0u;
+    return RC_OK;
+}
+
 rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
 {
     if (!c || level >= c->N) return RC_ERR_INVALID_ARG;
+    if (c->lists_pending) { c->error = "rc_render_level: halo-exchange context — call rc_render_lists after exchanging the request masks"; return RC_ERR_STATE; }
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const bool fused = !(c->cfg.flags & RC_CFG_SEPARATE_MERGE);
     const bool top = (level == c->N - 1);
@@ -1106,6 +1181,11 @@ static rc_status render_enqueue(rc_ctx* c, void* stream);
 rc_status rc_render(rc_ctx* c, void* stream)
 {
     if (!c) return RC_ERR_INVALID_ARG;
+    if (c->exchange_active()) {
+        c->error = "rc_render: a halo-exchange context renders through rc_render_begin / rc_render_lists / rc_render_level / rc_render_end "
+                   "with the caller's exchanges in between (include/rc_b200.h)";
+        return RC_ERR_STATE;
+    }
     if (!c->use_graph || c->level_timing || !c->have_camera) return render_enqueue(c, stream);
     cudaSetDevice(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;

@@ -204,12 +204,103 @@ def all_gather_tiles(local, tiles: Sequence[Tile], width: int, height: int, grou
     return full
 
 
+def _device_view(ptr: int, shape, typestr: str):
+    import torch
+    return torch.as_tensor(_DevicePtr(ptr, shape, typestr), device="cuda")
+
+
+class HaloExchanger:
+    """The transport of RC_CFG_HALO_EXCHANGE for full-width strips: NCCL send / recv (torch.distributed P2P, grouped) of
+    (a) request masks — every rank's requests of probes it does not own, to their owners, once per frame — and
+    (b) child averages — each finished level's owned probe rows, to every rank whose sub-grid holds them, once per level.
+    Strips make both contiguous row ranges of the library's row-major sub-grid buffers (rc_exchange_level_info), so the
+    sends and receives work on zero-copy views of librc_b200's own device memory.  Every rank derives the same plan from the
+    all-gathered level geometry; call refresh() (collectively) after the tiles moved."""
+
+    def __init__(self, renderer, rank: int, world: int, group=None):
+        self.r, self.rank, self.world, self.group = renderer, rank, world, group
+        self.refresh()
+
+    def refresh(self) -> None:
+        import torch.distributed as dist
+        n = len(self.r.levels())
+        mine = []
+        for L in range(n):
+            e = self.r.exchange_level_info(L)
+            mine.append(dict(exchanged=int(e.exchanged), px0=e.px0, py0=e.py0, sw=e.sub_w, sh=e.sub_h, oy0=e.own_y0, oy1=e.own_y1,
+                             ox0=e.own_x0, ox1=e.own_x1, words=e.need_words_per_probe, f4=e.avg_float4_per_probe))
+        allinfo = [None] * self.world
+        dist.all_gather_object(allinfo, mine, group=self.group)
+        self.levels, self.views = [], []
+        for L in range(n):
+            me = allinfo[self.rank][L]
+            plan = dict(exchanged=bool(me["exchanged"]), recv_avg=[], send_avg=[])
+            if me["exchanged"]:
+                assert me["px0"] == 0 and me["ox0"] == 0 and me["ox1"] == me["sw"] - 1, "halo exchange transports full-width strips only"
+                e = self.r.exchange_level_info(L)
+                need = _device_view(e.need_ptr, (me["sh"], me["sw"] * me["words"]), "<i4")
+                avg = _device_view(e.avg_ptr, (me["sh"], me["sw"] * me["f4"] * 4), "<f4")
+                my_sub = (me["py0"], me["py0"] + me["sh"])                                # global probe rows [a, b)
+                my_own = (me["py0"] + me["oy0"], me["py0"] + me["oy1"] + 1) if me["oy1"] >= me["oy0"] else (0, 0)
+                for q in range(self.world):
+                    if q == self.rank:
+                        continue
+                    o = allinfo[q][L]
+                    q_sub = (o["py0"], o["py0"] + o["sh"])
+                    q_own = (o["py0"] + o["oy0"], o["py0"] + o["oy1"] + 1) if o["oy1"] >= o["oy0"] else (0, 0)
+                    a, b = max(q_own[0], my_sub[0]), min(q_own[1], my_sub[1])        # rows q owns that I hold: I receive their averages
+                    if b > a:
+                        plan["recv_avg"].append((q, a - me["py0"], b - me["py0"]))
+                    a, b = max(my_own[0], q_sub[0]), min(my_own[1], q_sub[1])        # rows I own that q holds: I send their averages
+                    if b > a:
+                        plan["send_avg"].append((q, a - me["py0"], b - me["py0"]))
+                self.views.append((need, avg))
+            else:
+                self.views.append((None, None))
+            self.levels.append(plan)
+
+    def exchange_masks(self) -> None:
+        """My requests of probes owned by q go to q; q's requests of my probes are OR-ed into my masks (all levels, one batch)."""
+        import torch
+        import torch.distributed as dist
+        ops, pending = [], []
+        for L, plan in enumerate(self.levels):
+            if not plan["exchanged"]:
+                continue
+            need = self.views[L][0]
+            for q, a, b in plan["recv_avg"]:          # rows q owns -> q wants my requests of them
+                ops.append(dist.P2POp(dist.isend, need[a:b], q, group=self.group))
+            for q, a, b in plan["send_avg"]:          # rows I own -> I want q's requests of them
+                tmp = torch.empty_like(need[a:b])
+                ops.append(dist.P2POp(dist.irecv, tmp, q, group=self.group))
+                pending.append((need[a:b], tmp))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for dst, tmp in pending:
+            dst.bitwise_or_(tmp)
+
+    def exchange_avg(self, L: int) -> None:
+        """Level L has just been finalised for the probes each rank owns: fill everybody's halo rows."""
+        import torch.distributed as dist
+        plan = self.levels[L]
+        if not plan["exchanged"]:
+            return
+        avg = self.views[L][1]
+        ops = [dist.P2POp(dist.isend, avg[a:b], q, group=self.group) for q, a, b in plan["send_avg"]]
+        ops += [dist.P2POp(dist.irecv, avg[a:b], q, group=self.group) for q, a, b in plan["recv_avg"]]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
 class TiledRenderer:
     """One rank's share of a tiled frame: a DefaultRenderer restricted to this rank's tile plus the
     final all-gather.  Needs a CUDA device (no CPU fallback)."""
 
     def __init__(self, rank: int, world: int, device: int, size: Tuple[int, int], state, path: str,
-                 cascade=None, grid: Optional[Tuple[int, int]] = None, balance: bool = False):
+                 cascade=None, grid: Optional[Tuple[int, int]] = None, balance: bool = False, halo_exchange: bool = False):
+        from . import _ffi
         from .renderer import CascadeConfig, DefaultRenderer
         W, H = size
         self.balancer = StripBalancer(W, H, world) if (balance and not grid) else None
@@ -217,6 +308,10 @@ class TiledRenderer:
         self.rank, self.world, self.size = rank, world, (W, H)
         cc = cascade or CascadeConfig()
         cc.tile = self.tiles[rank]
+        self.halo_exchange = bool(halo_exchange) and not grid and world > 1
+        if self.halo_exchange:
+            cc.flags |= _ffi.RC_CFG_HALO_EXCHANGE
+        self.exchanger = None
         if self.balancer is not None and world > 1:
             # the cuts will move: size the (grow-only) device buffers once for a strip of twice the average height, so that
             # re-tiling never reaches the allocator (a cudaFree + cudaMalloc of the cascade stalls the rank for ~0.1 s)
@@ -229,7 +324,29 @@ class TiledRenderer:
 
     def render(self, state, stream: Optional[int] = None):
         self.renderer.update(state)
+        if self.halo_exchange:
+            return self._render_exchange(stream)
         self.renderer.render(stream)
+
+    def _render_exchange(self, stream: Optional[int]):
+        """RC_CFG_HALO_EXCHANGE frame: G-buffer / probes / request masks, mask exchange, ray lists of the owned probes, then the
+        levels top-down with the child averages of each finished level sent to the neighbours before the level below merges.
+        `stream` must be the handle of torch's CURRENT stream: the NCCL transfers are ordered on it."""
+        import torch
+        r = self.renderer
+        cur = torch.cuda.current_stream().cuda_stream
+        if stream is None:
+            stream = cur
+        assert stream == cur, "render the halo-exchange frame inside `with torch.cuda.stream(s)` and pass s.cuda_stream"
+        if self.exchanger is None:
+            self.exchanger = HaloExchanger(r, self.rank, self.world)
+        r.render_begin(stream)
+        self.exchanger.exchange_masks()
+        r.render_lists(stream)
+        for L in range(len(self.exchanger.levels) - 1, -1, -1):
+            r.render_level(L, stream)
+            self.exchanger.exchange_avg(L)
+        r.render_end(stream)
 
     def rebalance(self, times_ms: Sequence[float]) -> bool:
         """Move the strip cuts from every rank's last frame time (identical input on every rank -> identical tiles);
@@ -238,6 +355,8 @@ class TiledRenderer:
             return False
         self.tiles = list(self.balancer.tiles)
         self.renderer.set_tile(self.tiles[self.rank])
+        if self.exchanger is not None:
+            self.exchanger.refresh()          # collective: every rank re-tiles in the same call
         return True
 
     def all_gather_times(self, my_ms: float, group=None) -> List[float]:

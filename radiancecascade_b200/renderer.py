@@ -224,6 +224,15 @@ class DefaultRenderer:
     def render_begin(self, stream=None) -> None:
         self._check(self._lib.rc_render_begin(self._h, C.c_void_p(stream) if stream else None))
 
+    def render_lists(self, stream=None) -> None:
+        """Halo exchange: build the ray lists of the owned probes from the (completed) request masks."""
+        self._check(self._lib.rc_render_lists(self._h, C.c_void_p(stream) if stream else None))
+
+    def exchange_level_info(self, level: int) -> "_ffi.rc_exchange_info":
+        out = _ffi.rc_exchange_info()
+        self._check(self._lib.rc_exchange_level_info(self._h, level, C.byref(out)))
+        return out
+
     def render_level(self, level: int, stream=None) -> None:
         self._check(self._lib.rc_render_level(self._h, level, C.c_void_p(stream) if stream else None))
 

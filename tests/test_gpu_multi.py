@@ -60,6 +60,31 @@ def _worker(rank, world, port, W, H, q):
             if not moved:
                 ok, why = False, "the balancer did not move the cuts"
     torch.cuda.synchronize()
+    # (3) halo EXCHANGE (RC_CFG_HALO_EXCHANGE): levels >= 1 marched only by the owners, request masks and child averages moved
+    # with NCCL send / recv — the assembled frame is still the single-GPU frame bit for bit, fewer rays are marched than with
+    # recomputed halos, and it survives moving the cuts
+    trx = rd.TiledRenderer(rank, world, rank, (W, H), st, rc.scenes.scene_path(name), balance=True, halo_exchange=True)
+    marched_x = marched_r = 0
+    for f in range(4):
+        stf, _, _ = frame_setup(name, W, H, frame=2 + 7 * f)
+        with torch.cuda.stream(stream):
+            trx.render(stf, stream.cuda_stream)
+            tr.render(stf, stream.cuda_stream)
+        stream.synchronize()
+        marched_x += sum(m for m in trx.renderer.rays_marched() if m)
+        marched_r += sum(m for m in tr.renderer.rays_marched() if m)
+        fullx = rd.all_gather_tiles(rd.irradiance_tensor(trx.renderer), trx.tiles, W, H)
+        if rank == 0 and not np.array_equal(fullx.cpu().numpy().view(np.uint16), want_frame(stf)):
+            ok, why = False, f"halo-exchange frame {f} differs"
+        if f == 1:
+            times = [1.0 + 0.7 * r for r in range(world)]
+            if not trx.rebalance(trx.all_gather_times(times[rank])):
+                ok, why = False, "the balancer did not move the cuts (exchange)"
+    tot = torch.tensor([float(marched_x), float(marched_r)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tot)
+    if rank == 0 and not (tot[0] < tot[1]):
+        ok, why = False, f"exchange marched {tot[0].item()} rays, recompute {tot[1].item()}"
+    torch.cuda.synchronize()
     _, _, timeouts = tr.renderer.peer_frame(check=True)
     if rank == 0:
         if timeouts != 0:
