@@ -512,7 +512,8 @@ def run_tiled(args):
         assert nx * ny == world, "--grid must multiply to the world size"
         grid = (nx, ny)
     state = rc.AppState()
-    tr = rd.TiledRenderer(rank, world, local, (W, H), state, rc.scenes.scene_path(name), grid=grid, balance=not args.no_balance)
+    tr = rd.TiledRenderer(rank, world, local, (W, H), state, rc.scenes.scene_path(name), grid=grid, balance=not args.no_balance,
+                          halo_exchange=args.halo == "exchange")
     r = tr.renderer
     info = r.scene_info()
     stream = torch.cuda.Stream()
@@ -604,6 +605,7 @@ def run_tiled(args):
     st_all = [None] * world
     dist.all_gather_object(st_all, st_mean, group=ctl)
 
+    tr_halo = tr.halo_exchange
     launches = torch.tensor([float(r.launch_count())], device="cuda", dtype=torch.float64)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)            # kernels per frame, all ranks
 
@@ -635,7 +637,11 @@ def run_tiled(args):
         tickets = [None, None]
         for i in range(n):
             r.update_packed(inputs[i])
-            r.render(sh)
+            if tr.halo_exchange:
+                with torch.cuda.stream(stream):
+                    tr._render_exchange(sh)
+            else:
+                r.render(sh)
             if tickets[i & 1] is not None:
                 r.read_wait(tickets[i & 1])
             x0, y0, w, h = tr.tiles[rank]
@@ -728,9 +734,13 @@ def run_tiled(args):
                        "balancing": ("off" if (args.no_balance or grid) else
                                      f"strip cuts from measured frame times: {rebalances} re-tilings (calibration + every {args.rebalance_every} steps, "
                                      "outside the timed brackets)"),
-                       "halo": "upper-cascade halo recomputed locally (no data-path exchange between cascade levels)",
-                       "collective": ("none (NCCL only as plumbing): k_gather_mma stores each finished strip into every rank's frame over NVLink peer "
-                                      "memory, flags instead of a collective" if peer else "NCCL all_gather_into_tensor of the RGBA16F strips"),
+                       "halo": ("EXCHANGED (RC_CFG_HALO_EXCHANGE): levels >= 1 marched by the owning rank only; request masks once per frame and "
+                                "child averages once per level moved between strip neighbours with NCCL send/recv" if tr_halo else
+                                "upper-cascade halo recomputed locally (no data-path exchange between cascade levels)"),
+                       "collective": (("NCCL send/recv (halo: request masks + child averages of border probe rows); final image: " if tr_halo else
+                                       "none between cascade levels; final image: ") +
+                                      ("k_gather_mma stores each finished strip into rank 0's frame over NVLink peer memory, flags instead of a collective"
+                                       if peer else "NCCL all_gather_into_tensor of the RGBA16F strips")),
                        "rays_marched_single_gpu_per_frame": useful_total / args.steps,
                        "redundant_rays": float(rl.item()) / useful_total - 1.0, "l2": "flushed between timed steps (256 MiB memset)",
                        "value_definition": "ray samples a single GPU marches for the frame (redundant halo rays not counted) per second",
@@ -765,6 +775,8 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="tiled mode: peer-memory stores fused into the gather kernel (default) or an NCCL all-gather")
     ap.add_argument("--no-balance", action="store_true", help="tiled mode: equal-height strips")
+    ap.add_argument("--halo", default="recompute", choices=["recompute", "exchange"],
+                    help="tiled mode: upper-cascade halos recomputed by every rank (default) or exchanged between the ranks (NCCL send/recv)")
     ap.add_argument("--calibrate", type=int, default=10, help="tiled mode: at most this many balancing frames before the warm-up")
     ap.add_argument("--rebalance-every", type=int, default=4, help="tiled mode: re-balance every n timed steps (0: never)")
     ap.add_argument("--no-batch-extra", action="store_true", help="tiled mode: skip the sonic 8K batch record")
