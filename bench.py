@@ -358,6 +358,8 @@ def run_product(args):
 
     host_out2 = torch.empty((H, W, 4), dtype=torch.float16, pin_memory=True)
     host_ptrs = (host_ptr, host_out2.data_ptr())
+    rgb48_bytes = W * H * 6
+    e2e_fmt = {"rgb48": False}
 
     def e2e_pipelined_loop(n):
         # frame i is enqueued BEFORE the host waits for frame i-2 (the previous user of host buffer i & 1): the GPU always
@@ -369,7 +371,10 @@ def run_product(args):
             r.render(sh)
             if tickets[i & 1] is not None:
                 r.read_wait(tickets[i & 1])
-            tickets[i & 1] = r.read_irradiance_async(host_ptrs[i & 1], host_bytes)
+            if e2e_fmt["rgb48"]:
+                tickets[i & 1] = r.read_irradiance_async(host_ptrs[i & 1], rgb48_bytes, rgb48=True)
+            else:
+                tickets[i & 1] = r.read_irradiance_async(host_ptrs[i & 1], host_bytes)
         for k in (n, n + 1):
             if tickets[k & 1] is not None:
                 r.read_wait(tickets[k & 1])
@@ -388,6 +393,8 @@ def run_product(args):
         return ms
 
     e2e_sync_ms = timed(e2e_loop)
+    e2e_rgba_ms = timed(e2e_pipelined_loop)
+    e2e_fmt["rgb48"] = True          # the 6-byte target: r, g, b bit-exact, coverage in the sign bit of r
     e2e_ms = timed(e2e_pipelined_loop)
     launches_per_frame = r.launch_count()
     clocks = sampler.stop() if rank == 0 else None
@@ -448,9 +455,11 @@ def run_product(args):
                        "gather": "k_gather_mma: per-cell contraction on mma.sync, probes staged by TMA bulk copies",
                        "submission": "one CUDA graph per frame (stream capture + cudaGraphExecUpdate)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": 80 + 16 * n_lights, "d2h_bytes_per_step": host_bytes,
-                    "readback": "rc_read_target_async: double-buffered; frame i is submitted before the host waits for the read-back of "
-                                "frame i-2; every frame is received in pinned host memory inside the timed region",
+                    "h2d_bytes_per_step": 80 + 16 * n_lights, "d2h_bytes_per_step": rgb48_bytes,
+                    "readback": "rc_read_target_async(RC_TARGET_IRRADIANCE_RGB48): the irradiance as 3 x float16 per pixel (r, g, b bit-exact, "
+                                "coverage in the sign bit of r) — alpha carries no other information; double-buffered, frame i is submitted before "
+                                "the host waits for the read-back of frame i-2; every frame is received in pinned host memory inside the timed region",
+                    "rgba16f_ms_per_step": e2e_rgba_ms / args.steps, "rgba16f_d2h_bytes_per_step": host_bytes,
                     "blocking_value": traced_per_step / (e2e_sync_ms / args.steps * 1e-3) / 1e9,
                     "blocking_ms_per_step": e2e_sync_ms / args.steps},
             "gpu_launches": launches_per_frame * args.steps,
@@ -612,7 +621,13 @@ def run_tiled(args):
     # ---- end to end: host camera in, the whole frame out in (shared, pinned) host memory, every rank reading back its strip
     from multiprocessing import shared_memory
     shm_name = f"rcb200_frame_{os.environ.get('MASTER_PORT', '0')}"
-    nbytes = W * H * 8
+    nbytes = W * H * 6                               # RC_TARGET_IRRADIANCE_RGB48: 3 x float16 per pixel
+    if rank == 0:
+        try:      # a crashed earlier run on the same port may have left the segment behind
+            stale = shared_memory.SharedMemory(name=shm_name)
+            stale.close(); stale.unlink()
+        except FileNotFoundError:
+            pass
     shm = shared_memory.SharedMemory(name=shm_name, create=True, size=2 * nbytes) if rank == 0 else None
     dist.barrier()
     if rank != 0:
@@ -622,7 +637,7 @@ def run_tiled(args):
             resource_tracker.unregister(shm._name, "shared_memory")
         except Exception:       # noqa: BLE001
             pass
-    host = np.ndarray((2, H, W, 4), dtype=np.float16, buffer=shm.buf)
+    host = np.ndarray((2, H, W, 3), dtype=np.uint16, buffer=shm.buf)
     base_ptr = host.ctypes.data
     cudart = torch.cuda.cudart()
     reg = cudart.cudaHostRegister(base_ptr, 2 * nbytes, 0)
@@ -645,7 +660,7 @@ def run_tiled(args):
             if tickets[i & 1] is not None:
                 r.read_wait(tickets[i & 1])
             x0, y0, w, h = tr.tiles[rank]
-            tickets[i & 1] = r.read_irradiance_async(base_ptr + (i & 1) * nbytes + y0 * W * 8, w * h * 8)   # my rows of the shared frame
+            tickets[i & 1] = r.read_irradiance_async(base_ptr + (i & 1) * nbytes + y0 * W * 6, w * h * 6, rgb48=True)   # my rows of the shared frame
         for k in (n, n + 1):
             if tickets[k & 1] is not None:
                 r.read_wait(tickets[k & 1])
@@ -747,8 +762,9 @@ def run_tiled(args):
                        "cpu_binding": binding},
             "e2e": ({"value": useful_total / args.steps / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                      "h2d_bytes_per_step": 96 * world, "d2h_bytes_per_step": nbytes,
-                     "readback": "every rank reads its strip back into its rows of ONE process-shared pinned host frame (double-buffered, "
-                                 "rc_read_target_async): the whole frame is in host memory when the step ends; N PCIe links in parallel",
+                     "readback": "every rank reads its strip back (RC_TARGET_IRRADIANCE_RGB48: 3 x float16 per pixel, r g b bit-exact) into its rows of "
+                                 "ONE process-shared pinned host frame (double-buffered, rc_read_target_async): the whole frame is in host memory "
+                                 "when the step ends; N PCIe links in parallel",
                      "host_registered": registered} if e2e_ms else None),
             "gpu_launches": int(launches.item()) * args.steps,
             "clocks": clocks,

@@ -105,6 +105,9 @@ typedef enum rc_target {
     RC_TARGET_PRIM       = 5, /* uint32        [tile_h][tile_w]     global triangle id, 0xffffffff where no geometry */
     RC_TARGET_COMPOSITE  = 6, /* uint8 BGRA    [tile_h][tile_w][4]  sRGB-encoded albedo*E/pi + direct (Bgra8UnormSrgb, src/window/app.rs:59-75) */
     RC_TARGET_DIRECT_SRGB8 = 7, /* uint8 BGRA  [tile_h][tile_w][4]  what the reference presents: sRGB_encode(fs_main) */
+    RC_TARGET_IRRADIANCE_RGB48 = 8, /* float16 RGB [tile_h][tile_w][3]  the irradiance without its alpha channel, bit-exact: the sign bit of r is
+                                     * set where the pixel has no geometry (E >= 0 everywhere else).  6 instead of 8 bytes per pixel over
+                                     * PCIe; also accepted by rc_read_target_async */
     RC_TARGET_CASCADE0   = 16 /* + level i: float16 RGBA, merged cascade level i, layout in rc_spec.h */
 } rc_target;
 

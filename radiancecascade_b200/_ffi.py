@@ -25,6 +25,7 @@ RC_UPD_ENABLE_NORMAL_MAP = 0x1
 
 (RC_TARGET_IRRADIANCE, RC_TARGET_DIRECT, RC_TARGET_DEPTH, RC_TARGET_NORMAL, RC_TARGET_ALBEDO, RC_TARGET_PRIM,
  RC_TARGET_COMPOSITE, RC_TARGET_DIRECT_SRGB8) = range(8)
+RC_TARGET_IRRADIANCE_RGB48 = 8
 RC_TARGET_CASCADE0 = 16
 
 STAGES = ("gbuffer", "probes", "march", "merge", "gather", "frame")

@@ -1043,6 +1043,87 @@ __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel
     }
 }
 
+// ------------------------------------------------------------------ march, one 2x2 quad of texels per thread (culled levels >= 1)
+// The ray lists of levels >= 1 hold quads (the four children of one direction of the level below).  k_march gives each
+// ray its own thread, so every ray pays the list decode, the probe / link fetches, the merge set-up and three shuffles for
+// the child average — ncu (r2e, level 3 of the 4K frame): ~310 of the ~550 thread-instructions a ray costs are such
+// per-ray overhead, only ~240 are traversal.  Here a thread owns the whole quad: it decodes once, fetches the probe and
+// its link record once, marches the four rays one after the other (same origin, neighbouring directions), stores the
+// four texels as two 16-byte vectors and forms the child average in registers.  Same rays, same arithmetic per ray:
+// bit-identical texels and averages.
+template <bool FUSED, int MINB>
+__global__ void __launch_bounds__(64, MINB) k_march_quad(DScene s, DLights L, DLevel lv, int UD, float3 sky, const float4* __restrict__ origin,
+                                                        const float4* __restrict__ dirq, uint2* __restrict__ texels, const float4* __restrict__ up_avg,
+                                                        const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
+                                                        float4* __restrict__ avg_out, const uint32_t* __restrict__ list,
+                                                        const unsigned int* __restrict__ count)
+{
+    cudaTriggerProgrammaticLaunchCompletion();   // the next level's kernel may begin once every block got here
+    const unsigned total = __ldg(count);
+    const int ld = 31 - __clz(lv.D);             // culled mode requires power-of-two D
+    const uint32_t DD = (uint32_t)lv.D * (uint32_t)lv.D, HD = (uint32_t)lv.D >> 1;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+        const uint32_t e = __ldg(list + j);
+        const uint32_t q = e & ((DD >> 2) - 1u), probe = e >> (2 * ld - 2);
+        const uint32_t x = q & (HD - 1u), y = q >> (ld - 1);
+        const float4 og = __ldg(origin + probe);
+        uint2 t[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) t[c] = pack_half4(0.f, 0.f, 0.f, 1.f);   // invalid probe (S7)
+        if (og.w != 0.0f) {
+            const float3 o = xyz(og);
+            Hit h[4];
+            float3 w[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t d = ((2u * y + (uint32_t)(c >> 1)) << ld) + 2u * x + (uint32_t)(c & 1);
+                const float4 qa = __ldg(dirq + 2 * (size_t)d), qb = __ldg(dirq + 2 * (size_t)d + 1);
+                w[c] = xyz(qa);
+                h[c] = trace_inv(s, o, w[c], f3(qa.w, qb.x, qb.y), lv.t0, lv.t1);
+            }
+            // S7: radiance of the hits (the float16-rounded raw texel is what S8 reads)
+            float4 raw[4];
+            bool any_miss = false;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float4 v;
+                if (h[c].prim != 0xffffffffu) {
+                    const Shade sh = shade_hit(s, L, h[c].prim, h[c].u, h[c].v, vfma(h[c].t, w[c], o), vneg(w[c]));
+                    v = make_float4(sh.rad.x, sh.rad.y, sh.rad.z, 0.0f);
+                } else {
+                    v = make_float4(0.f, 0.f, 0.f, 1.0f);
+                    any_miss = true;
+                }
+                t[c] = pack_half4(v.x, v.y, v.z, v.w);
+                raw[c] = unpack_half4(t[c]);
+            }
+            if (FUSED && any_miss) {
+                // S8, once per quad: the link record, then per missed ray the four upper averages of its own direction
+                cudaGridDependencySynchronize();
+                const uint4 li = __ldg(link_idx + probe);
+                const float4 lw = __ldg(link_w + probe);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (raw[c].w == 0.0f) continue;     // a = 0: fma(0, far, raw) = raw exactly
+                    const float4 far = far_field(up_avg, lv.D, li, lw, (int)(2u * x) + (c & 1), (int)(2u * y) + (c >> 1), sky, UD < 0);
+                    float4 m = make_float4(fmaf(raw[c].w, far.x, raw[c].x), fmaf(raw[c].w, far.y, raw[c].y), fmaf(raw[c].w, far.z, raw[c].z), raw[c].w * far.w);
+                    t[c] = pack_half4(fminf(m.x, 65504.0f), fminf(m.y, 65504.0f), fminf(m.z, 65504.0f), m.w);
+                }
+            }
+        }
+        uint2* base = texels + (size_t)probe * DD + ((size_t)(2u * y) << ld) + 2u * x;
+        *reinterpret_cast<uint4*>(base) = make_uint4(t[0].x, t[0].y, t[1].x, t[1].y);
+        *reinterpret_cast<uint4*>(base + lv.D) = make_uint4(t[2].x, t[2].y, t[3].x, t[3].y);
+        if (avg_out) {
+            const float4 c0 = unpack_half4(t[0]), c1 = unpack_half4(t[1]), c2 = unpack_half4(t[2]), c3 = unpack_half4(t[3]);
+            avg_out[(size_t)probe * (DD >> 2) + (size_t)y * HD + x] =
+                make_float4(0.25f * (((c0.x + c1.x) + c2.x) + c3.x), 0.25f * (((c0.y + c1.y) + c2.y) + c3.y),
+                            0.25f * (((c0.z + c1.z) + c2.z) + c3.z), 0.25f * (((c0.w + c1.w) + c2.w) + c3.w));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ all levels in ONE launch (small frames)
 // The ray marches of the N levels are independent of each other — only the merge runs top-down.  On a small
 // frame (1080p, open scene: ~0.5 M real rays per level = 2-3 waves of blocks) each per-level kernel spends
@@ -1886,6 +1967,44 @@ __global__ void __launch_bounds__(kBlock) k_copy_to_host(const uint4* __restrict
     for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n16; i += (size_t)gridDim.x * kBlock) dst[i] = ld_u4(src + i);
 }
 
+// ------------------------------------------------------------------ 6-byte read-back format of the irradiance
+// RGBA16F spends a quarter of the frame's PCIe bytes on alpha, which is only the coverage flag (1 where geometry, else 0) —
+// and at 4K the 66 MB read-back (1.3 ms) is what bounds the end-to-end frame rate, not the 1.3 ms of rendering.  RGB48:
+// three float16 per pixel, bit-exact r, g, b (E >= 0, so the sign bit of r is free) with the sign bit of r SET where the
+// pixel has no geometry.  Eight pixels (64 bytes in, 48 bytes out) per thread, 16-byte vectors both ways.
+__global__ void __launch_bounds__(kBlock) k_pack_rgb48(size_t n8, size_t n, const uint4* irr2, uint4* out3, const uint2* irr, uint16_t* out16)
+{
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < n8) {
+        uint32_t h[16];                       // 8 pixels x (rg, ba)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 v = ld_u4(irr2 + 4 * i + k);
+            h[4 * k] = v.x; h[4 * k + 1] = v.y; h[4 * k + 2] = v.z; h[4 * k + 3] = v.w;
+        }
+        uint16_t o[24];
+#pragma unroll
+        for (int px = 0; px < 8; px++) {
+            const uint32_t rg = h[2 * px], ba = h[2 * px + 1];
+            const bool covered = (ba >> 16) != 0u;          // alpha is 1.0 or 0.0
+            o[3 * px] = (uint16_t)((rg & 0x7fffu) | (covered ? 0u : 0x8000u));
+            o[3 * px + 1] = (uint16_t)(rg >> 16);
+            o[3 * px + 2] = (uint16_t)(ba & 0xffffu);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            out3[3 * i + k] = make_uint4((uint32_t)o[8 * k] | ((uint32_t)o[8 * k + 1] << 16), (uint32_t)o[8 * k + 2] | ((uint32_t)o[8 * k + 3] << 16),
+                                         (uint32_t)o[8 * k + 4] | ((uint32_t)o[8 * k + 5] << 16), (uint32_t)o[8 * k + 6] | ((uint32_t)o[8 * k + 7] << 16));
+    } else if (i == n8) {                     // the last n % 8 pixels
+        for (size_t p = 8 * n8; p < n; p++) {
+            const uint2 v = irr[p];
+            out16[3 * p] = (uint16_t)((v.x & 0x7fffu) | ((v.y >> 16) ? 0u : 0x8000u));
+            out16[3 * p + 1] = (uint16_t)(v.x >> 16);
+            out16[3 * p + 2] = (uint16_t)(v.y & 0xffffu);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ display composite (outside the hot path)
 __device__ __forceinline__ unsigned char srgb8(float x)
 {
@@ -2038,6 +2157,32 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     else if (occ >= 10) { if (f) RC_LAUNCH_MARCH(true, 10, t); else RC_LAUNCH_MARCH(false, 10, t); }
     else { if (f) RC_LAUNCH_MARCH(true, 8, t); else RC_LAUNCH_MARCH(false, 8, t); }
 #undef RC_LAUNCH_MARCH
+}
+
+void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,
+                       const float4* up_avg, const uint4* link_idx, const float4* link_w, float4* avg_out, bool fused, int occ, bool pdl, int max_blocks,
+                       const uint32_t* list, const unsigned int* count, bool up_const, cudaStream_t st)
+{
+    const int UD = up_const ? -1 : 0;
+    cudaLaunchConfig_t cfg{};
+    const size_t nq = (size_t)lv.sw * lv.sh * lv.D * lv.D / 4;
+    size_t blocks = (nq + 63) / 64;
+    if (max_blocks > 0 && blocks > (size_t)max_blocks) blocks = (size_t)max_blocks;
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(64);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && fused) ? 1 : 0;
+    if (fused) {
+        if (occ >= 16) cudaLaunchKernelEx(&cfg, k_march_quad<true, 16>, s, L, lv, UD, sky, origin, dirq, texels, up_avg, link_idx, link_w, avg_out, list, count);
+        else if (occ >= 12) cudaLaunchKernelEx(&cfg, k_march_quad<true, 12>, s, L, lv, UD, sky, origin, dirq, texels, up_avg, link_idx, link_w, avg_out, list, count);
+        else cudaLaunchKernelEx(&cfg, k_march_quad<true, 8>, s, L, lv, UD, sky, origin, dirq, texels, up_avg, link_idx, link_w, avg_out, list, count);
+    } else {
+        cudaLaunchKernelEx(&cfg, k_march_quad<false, 12>, s, L, lv, UD, sky, origin, dirq, texels, up_avg, link_idx, link_w, avg_out, list, count);
+    }
 }
 
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,
@@ -2212,6 +2357,13 @@ void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t s
 void launch_copy_to_host(const void* src, void* dst_host_mapped, size_t bytes, int blocks, cudaStream_t st)
 {
     k_copy_to_host<<<blocks, kBlock, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst_host_mapped), bytes / 16);
+}
+
+void launch_pack_rgb48(size_t n_pixels, const uint2* irradiance, void* out, cudaStream_t st)
+{
+    const size_t n8 = n_pixels / 8;
+    k_pack_rgb48<<<blocks_for(n8 + 1), kBlock, 0, st>>>(n8, n_pixels, reinterpret_cast<const uint4*>(irradiance), reinterpret_cast<uint4*>(out),
+                                                       irradiance, reinterpret_cast<uint16_t*>(out));
 }
 
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,

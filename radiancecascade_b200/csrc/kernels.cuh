@@ -87,6 +87,11 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ,
                   bool pdl, bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const,
                   cudaStream_t st);
+// culled levels >= 1, one 2x2 quad of texels per thread (k_march_quad): list = the level's quad list, count = its length;
+// occ = resident 64-thread blocks per SM the register allocation must allow (8 -> 128 regs, 12 -> 80, 16 -> 64)
+void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,
+                       const float4* up_avg, const uint4* link_idx, const float4* link_w, float4* avg_out, bool fused, int occ, bool pdl, int max_blocks,
+                       const uint32_t* list, const unsigned int* count, bool up_const, cudaStream_t st);
 int march_avg_ystep(int D, int map);
 // child averages of a finalised level from its texels (paths whose march kernel does not write them itself)
 void launch_child_avg(const DLevel& lv, const uint2* texels, float4* avg_out, cudaStream_t st);
@@ -119,6 +124,8 @@ void launch_peer_publish(const PeerOut& peer, cudaStream_t st);
 void launch_peer_wait(int world, uint32_t seq, uint32_t* my_ctrl, cudaStream_t st);
 // SM-driven device -> pinned-host copy (bytes % 16 == 0, dst = device-visible address of page-locked host memory)
 void launch_copy_to_host(const void* src, void* dst_host_mapped, size_t bytes, int blocks, cudaStream_t st);
+// RGBA16F irradiance -> RGB48 (3 x float16 per pixel, sign bit of r = "no geometry"): the 6-byte read-back format
+void launch_pack_rgb48(size_t n_pixels, const uint2* irradiance, void* out, cudaStream_t st);
 void launch_composite(TileRect tile, const uint2* irradiance, const uint2* albedo, const uint2* direct,
                       uchar4* composite, uchar4* direct_srgb, cudaStream_t st);
 void launch_trace_rays(const DScene& s, const float* rays, uint32_t n, float* hits, cudaStream_t st);

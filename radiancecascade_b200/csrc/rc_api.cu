@@ -209,6 +209,7 @@ struct rc_ctx {
     bool copy_pending[2] = {false, false};
     uint2* irr() { return irr_slot ? d_irr2.p : d_irr.p; }
     DevBuf<uchar4> d_composite, d_direct_srgb;
+    DevBuf<uint16_t> d_irr_pack;         // RC_TARGET_IRRADIANCE_RGB48 staging (3 x float16 per pixel)
     DevBuf<float> d_dbg_in, d_dbg_out;
     DevBuf<unsigned int> d_counters;     // per-level ray-fetch counters of the persistent march
 
@@ -245,6 +246,11 @@ struct rc_ctx {
     // per level, PDL-chained.  Measured: the single launch saves nothing over the PDL chain and the
     // separate merges cost more than the fused ones.
     int march_batch = 0;
+    // culled levels >= 1: one 2x2 quad of texels per thread (k_march_quad) instead of one ray per thread; march_quad_occ = resident
+    // 64-thread blocks per SM the register allocation must allow
+    // Measured SLOWER (4K march 1.02-1.18 vs 0.685 ms, teapot 0.39-0.51 vs 0.30): 32 different quads per warp, four rounds of
+    // traversal each waiting for its slowest lane — the per-ray overhead it saves is smaller than the divergence it adds.  Off.
+    int march_quad = 0, march_quad_occ = 16;
     size_t texels_per_level() const { return levels.empty() ? 0 : (size_t)levels[0].sw * levels[0].sh * levels[0].D * levels[0].D; }
     bool batched() const
     {
@@ -701,7 +707,7 @@ void destroy_ctx(rc_ctx* c)
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_frame_done) cudaEventDestroy(c->ev_frame_done);
     for (auto& e : c->ev_copy_done) if (e) cudaEventDestroy(e);
-    c->d_composite.release(); c->d_direct_srgb.release();
+    c->d_composite.release(); c->d_direct_srgb.release(); c->d_irr_pack.release();
     c->d_dbg_in.release(); c->d_dbg_out.release(); c->d_counters.release();
     delete c;
 }
@@ -775,6 +781,8 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_MARCH_PDL")) c->march_pdl = atoi(e);
         if (const char* e = getenv("RC_MARCH_ENTRY")) c->march_entry = atoi(e) < -1 ? -1 : atoi(e);
         if (const char* e = getenv("RC_MARCH_BATCH")) c->march_batch = atoi(e) > 0 ? 1 : 0;
+        if (const char* e = getenv("RC_MARCH_QUAD")) c->march_quad = atoi(e) != 0;
+        if (const char* e = getenv("RC_MARCH_QUAD_OCC")) c->march_quad_occ = atoi(e);
         if (const char* e = getenv("RC_CULL")) c->cull = atoi(e) != 0;
         if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
         if (const char* e = getenv("RC_COPY_BLOCKS")) c->copy_blocks = atoi(e) < 0 ? 0 : (atoi(e) > 1024 ? 1024 : atoi(e));
@@ -1029,7 +1037,17 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
         }
     }
     const bool avg_in_kernel = my_avg && (fused || top) && !c->march_persist && !compact && (culled || march_avg_ystep(L.D, eff_map) != 0);
-    if (c->march_persist)
+    const bool quad_kernel = culled && level >= 1 && !top && c->march_quad;
+    if (quad_kernel) {
+        int qblocks = 0;
+        if (c->h_ray_count) {
+            const unsigned int prev = *(volatile unsigned int*)(c->h_ray_count + level);
+            if (prev != 0xffffffffu) qblocks = (int)std::min((double)prev * 1.25 / 64.0 + 64.0, 2.0e9);
+        }
+        launch_march_quad(c->scene, c->lights, L, sky, c->d_origin.p + L.probe_offset, c->d_dirq.p + 2 * (c->dir_offset[level] / 3), tex, up,
+                          c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, my_avg, fused, c->march_quad_occ, c->march_pdl != 0,
+                          qblocks, c->d_list.p + c->list_offset[level], c->d_ray_count.p + level, up_const, st);
+    } else if (c->march_persist)
         launch_march_persist(c->scene, c->lights, L, U, top, sky, c->d_origin.p + L.probe_offset, c->d_dirs.p + c->dir_offset[level], tex, up,
                              c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, fused, c->march_map[level], c->march_thresh,
                              c->march_grid, c->d_counters.p + level, c->march_pdl && fused && !top, st);
@@ -1070,6 +1088,8 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "fill_top") c->fill_top = value != 0;
     else if (k == "march_entry" && value >= -1) c->march_entry = value;
     else if (k == "march_batch" && value >= 0 && value <= 1) c->march_batch = value;
+    else if (k == "march_quad" && value >= 0 && value <= 1) c->march_quad = value;
+    else if (k == "march_quad_occ" && value >= 8 && value <= 16) c->march_quad_occ = value;
     else if (k == "cull" && value >= 0 && value <= 1) c->cull = value;
     else if (k == "gather_tiles" && value >= 0 && value <= 64) c->gather_tiles = value;
     else if (k == "gather_mma" && value >= 0 && value <= 1) c->gather_mma = value;
@@ -1263,6 +1283,7 @@ rc_status rc_target_bytes(rc_ctx* c, rc_target which, size_t* bytes)
     const size_t npx = (size_t)c->tile.w * c->tile.h;
     switch ((int)which) {
     case RC_TARGET_IRRADIANCE: case RC_TARGET_DIRECT: case RC_TARGET_ALBEDO: *bytes = npx * 8; return RC_OK;
+    case RC_TARGET_IRRADIANCE_RGB48: *bytes = npx * 6; return RC_OK;
     case RC_TARGET_DEPTH: case RC_TARGET_NORMAL: case RC_TARGET_PRIM: case RC_TARGET_COMPOSITE: case RC_TARGET_DIRECT_SRGB8:
         *bytes = npx * 4; return RC_OK;
     default: break;
@@ -1296,6 +1317,11 @@ rc_status rc_read_target(rc_ctx* c, rc_target which, void* host_dst, size_t byte
     }
     switch ((int)which) {
     case RC_TARGET_IRRADIANCE: src = c->irr(); break;
+    case RC_TARGET_IRRADIANCE_RGB48:
+        CU_OK(c, c->d_irr_pack.alloc(((size_t)c->tile.w * c->tile.h * 6 + 15) / 16 * 16 / 2));
+        launch_pack_rgb48((size_t)c->tile.w * c->tile.h, c->irr(), c->d_irr_pack.p, st);
+        src = c->d_irr_pack.p;
+        break;
     case RC_TARGET_DIRECT: src = c->d_direct.p; break;
     case RC_TARGET_ALBEDO: src = c->d_albedo.p; break;
     case RC_TARGET_DEPTH: src = c->d_depth.p; break;
@@ -1318,27 +1344,37 @@ rc_status rc_read_target(rc_ctx* c, rc_target which, void* host_dst, size_t byte
 rc_status rc_read_target_async(rc_ctx* c, rc_target which, void* host_dst, size_t bytes, uint32_t* ticket)
 {
     if (!c || !host_dst || !ticket) return RC_ERR_INVALID_ARG;
-    if (which != RC_TARGET_IRRADIANCE) { c->error = "rc_read_target_async: only RC_TARGET_IRRADIANCE is double-buffered"; return RC_ERR_INVALID_ARG; }
-    const size_t need = (size_t)c->tile.w * c->tile.h * 8;
+    if (which != RC_TARGET_IRRADIANCE && which != RC_TARGET_IRRADIANCE_RGB48) {
+        c->error = "rc_read_target_async: only the irradiance targets are double-buffered";
+        return RC_ERR_INVALID_ARG;
+    }
+    const bool rgb48 = which == RC_TARGET_IRRADIANCE_RGB48;
+    const size_t need = (size_t)c->tile.w * c->tile.h * (rgb48 ? 6 : 8);
     if (bytes < need) { c->error = "rc_read_target_async: buffer too small"; return RC_ERR_BUFFER_SIZE; }
     cudaSetDevice(c->device);
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     const int slot = c->irr_slot;
     CU_OK(c, cudaEventRecord(c->ev_frame_done, st));
     CU_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_frame_done, 0));
+    const void* src = c->irr();
+    if (rgb48) {   // packed on the copy stream (which is ordered: pack i, copy i, pack i+1, ...), so one staging buffer serves
+        CU_OK(c, c->d_irr_pack.alloc(((size_t)c->tile.w * c->tile.h * 6 + 15) / 16 * 16 / 2));
+        launch_pack_rgb48((size_t)c->tile.w * c->tile.h, c->irr(), c->d_irr_pack.p, c->copy_stream);
+        src = c->d_irr_pack.p;
+    }
     bool by_sm = false;
     if (c->copy_blocks > 0 && need % 16 == 0) {   // SM-driven copy: only into page-locked memory the device can address
         cudaPointerAttributes pa{};
         void* dev_view = nullptr;
         if (cudaPointerGetAttributes(&pa, host_dst) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
             cudaHostGetDevicePointer(&dev_view, host_dst, 0) == cudaSuccess && dev_view) {
-            launch_copy_to_host(c->irr(), dev_view, need, c->copy_blocks, c->copy_stream);
+            launch_copy_to_host(src, dev_view, need, c->copy_blocks, c->copy_stream);
             by_sm = true;
         } else {
             cudaGetLastError();
         }
     }
-    if (!by_sm) CU_OK(c, cudaMemcpyAsync(host_dst, c->irr(), need, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (!by_sm) CU_OK(c, cudaMemcpyAsync(host_dst, src, need, cudaMemcpyDeviceToHost, c->copy_stream));
     CU_OK(c, cudaEventRecord(c->ev_copy_done[slot], c->copy_stream));
     c->copy_pending[slot] = true;
     *ticket = (uint32_t)slot;

@@ -246,7 +246,8 @@ class DefaultRenderer:
     _DTYPES = {_ffi.RC_TARGET_IRRADIANCE: (np.float16, 4), _ffi.RC_TARGET_DIRECT: (np.float16, 4),
                _ffi.RC_TARGET_ALBEDO: (np.float16, 4), _ffi.RC_TARGET_DEPTH: (np.float32, 1),
                _ffi.RC_TARGET_NORMAL: (np.uint32, 1), _ffi.RC_TARGET_PRIM: (np.uint32, 1),
-               _ffi.RC_TARGET_COMPOSITE: (np.uint8, 4), _ffi.RC_TARGET_DIRECT_SRGB8: (np.uint8, 4)}
+               _ffi.RC_TARGET_COMPOSITE: (np.uint8, 4), _ffi.RC_TARGET_DIRECT_SRGB8: (np.uint8, 4),
+               _ffi.RC_TARGET_IRRADIANCE_RGB48: (np.uint16, 3)}
 
     def target_bytes(self, which: int) -> int:
         n = C.c_size_t()
@@ -268,11 +269,24 @@ class DefaultRenderer:
         self._check(self._lib.rc_read_target(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
-    def read_irradiance_async(self, host_ptr: int, nbytes: int) -> int:
-        """Pipelined read-back into page-locked memory at `host_ptr`; returns a ticket for read_wait()."""
+    def read_irradiance_async(self, host_ptr: int, nbytes: int, rgb48: bool = False) -> int:
+        """Pipelined read-back into page-locked memory at `host_ptr`; returns a ticket for read_wait().
+        rgb48: the 6-byte-per-pixel target RC_TARGET_IRRADIANCE_RGB48 instead of RGBA16F."""
         t = C.c_uint32()
-        self._check(self._lib.rc_read_target_async(self._h, _ffi.RC_TARGET_IRRADIANCE, C.c_void_p(host_ptr), nbytes, C.byref(t)))
+        which = _ffi.RC_TARGET_IRRADIANCE_RGB48 if rgb48 else _ffi.RC_TARGET_IRRADIANCE
+        self._check(self._lib.rc_read_target_async(self._h, which, C.c_void_p(host_ptr), nbytes, C.byref(t)))
         return t.value
+
+    @staticmethod
+    def unpack_rgb48(a: np.ndarray) -> np.ndarray:
+        """RC_TARGET_IRRADIANCE_RGB48 (uint16 [h][w][3]) -> float16 RGBA [h][w][4], bit-exact."""
+        a = np.asarray(a, dtype=np.uint16)
+        out = np.zeros(a.shape[:-1] + (4,), dtype=np.uint16)
+        covered = (a[..., 0] & 0x8000) == 0
+        out[..., 0] = a[..., 0] & 0x7FFF
+        out[..., 1:3] = a[..., 1:3]
+        out[..., 3] = np.where(covered, np.uint16(0x3C00), np.uint16(0))
+        return out.view(np.float16)
 
     def read_wait(self, ticket: int) -> None:
         self._check(self._lib.rc_read_wait(self._h, ticket))

@@ -644,6 +644,25 @@ def test_pipelined_readback_equals_blocking_readback():
     assert not np.array_equal(want[0], want[3])      # the frames really differ
 
 
+@pytest.mark.culled
+@pytest.mark.parametrize("name,W,H", [("teapot", 203, 117), ("living_room", 320, 180), ("cube", 64, 64)])
+def test_rgb48_readback_is_the_irradiance_without_alpha_bit_exact(name, W, H):
+    """RC_TARGET_IRRADIANCE_RGB48 (6 bytes per pixel over PCIe instead of 8): r, g, b bit-exact, coverage in the sign bit of r;
+    blocking and pipelined read-back, frame sizes that are not a multiple of the kernel's 8-pixel vectors."""
+    import torch
+    st, _, _ = frame_setup(name, W, H)
+    r = render_product(name, W, H, st)
+    want = r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)
+    got = rc.DefaultRenderer.unpack_rgb48(r.read_target(_ffi.RC_TARGET_IRRADIANCE_RGB48)).view(np.uint16)
+    assert np.array_equal(got, want)
+    assert (want[..., 3] == 0).any() or name == "living_room"
+    host = torch.empty((H, W, 3), dtype=torch.uint16, pin_memory=True)
+    for _ in range(3):
+        r.render()
+        r.read_wait(r.read_irradiance_async(host.data_ptr(), host.numel() * 2, rgb48=True))
+        assert np.array_equal(rc.DefaultRenderer.unpack_rgb48(host.numpy()).view(np.uint16), want)
+
+
 def test_scene_without_geometry_renders_background(tmp_path):
     """An OBJ with no faces: every pixel is background, every probe invalid; nothing crashes, E = 0."""
     p = tmp_path / "nofaces.obj"

@@ -31,7 +31,7 @@ def main(tag):
     for wl in ("teapot_1080p", "living_room_4k"):
         pk = per_kernel(f"gpurun_out/raw_{tag}_{wl}.csv")
         march = pk.get("k_march", [])
-        gather = pk.get("k_gather_pipe", pk.get("k_gather", []))
+        gather = pk.get("k_gather_mma", pk.get("k_gather_pipe", pk.get("k_gather", [])))
         res[wl] = {"k_march_dram_bytes_per_launch": sum(march) / max(1, len(march)), "k_march_launches": len(march),
                    "k_gather_dram_bytes_per_launch": sum(gather) / max(1, len(gather)),
                    "k_gbuffer_dram_bytes_per_launch": sum(pk.get("k_gbuffer", [0])) / max(1, len(pk.get("k_gbuffer", [0])))}
