@@ -607,18 +607,32 @@ void rco_probes(const rco_scene* s, const rco_params* p, const float cam[20], in
                 int px0, int py0, int sw, int sh, float* origin, float* nrm)
 {
     rco_level L; rco_level_layout(p, level, &L);
+    rco_level FL[16];
+    for (int l = 0; l <= level && l < 16; l++) rco_level_layout(p, l, &FL[l]);
     float b[9]; rco_primary_basis(cam, b);
     v3 eye = V(cam[16], cam[17], cam[18]);
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 1)
     for (int j = 0; j < sh; j++) for (int i = 0; i < sw; i++) {
         int px = px0 + i, py = py0 + j;
         size_t o = (size_t)j * sw + i;
-        int ax = px * L.P + L.P / 2, ay = py * L.P + L.P / 2;
-        if (ax > p->W - 1) ax = p->W - 1; if (ay > p->H - 1) ay = p->H - 1;
-        v3 d = primary_dir(p, b, ax, ay);
-        float tmin, tmax;
-        primary_range(p, cam, eye, d, &tmin, &tmax);
-        rco_hit h = trace_bvh(s, eye, d, tmin, tmax);
+        /* S6: the probe's own anchor first; when it sees no geometry the probe FLOATS to the first anchor of the finer
+         * levels' probes inside its cell that does (level by level downwards, row-major within a level) */
+        rco_hit h; h.prim = 0xffffffffu; h.t = -1.0f; h.u = h.v = 0.0f;
+        v3 d = V(0, 0, 0);
+        for (int l = level; l >= 0 && h.prim == 0xffffffffu; l--) {
+            const rco_level F = FL[l];
+            const int sc = 1 << (level - l);
+            for (int qy = py * sc; qy < (py + 1) * sc && qy < F.gh && h.prim == 0xffffffffu; qy++)
+                for (int qx = px * sc; qx < (px + 1) * sc && qx < F.gw; qx++) {
+                    int ax = qx * F.P + F.P / 2, ay = qy * F.P + F.P / 2;
+                    if (ax > p->W - 1) ax = p->W - 1; if (ay > p->H - 1) ay = p->H - 1;
+                    d = primary_dir(p, b, ax, ay);
+                    float tmin, tmax;
+                    primary_range(p, cam, eye, d, &tmin, &tmax);
+                    h = trace_bvh(s, eye, d, tmin, tmax);
+                    if (h.prim != 0xffffffffu) break;
+                }
+        }
         if (h.prim == 0xffffffffu) {
             for (int k = 0; k < 4; k++) { origin[4 * o + k] = 0; nrm[4 * o + k] = 0; }
             continue;

@@ -439,12 +439,42 @@ __device__ __forceinline__ int level_of(const DLevelSet& ls, unsigned i)
     return l;
 }
 
-__global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, TileRect tile, float offset,
-                                                   const float* __restrict__ depth, const uint32_t* __restrict__ prim,
+// primary hit through the anchor pixel of probe (qx, qy) of level fl: the G-buffer's when the anchor lies in the tile (same
+// ray, same S4/S5 arithmetic -> bit-identical), traced otherwise (halo probes of a multi-GPU tile)
+__device__ __forceinline__ bool anchor_hit(const DScene& s, const DCamera& cam, const DLevel& fl, const TileRect& tile, int qx, int qy,
+                                           const float* __restrict__ depth, const uint32_t* __restrict__ prim, float3& d, float& t, uint32_t& id)
+{
+    const int ax = min(qx * fl.P + fl.P / 2, cam.W - 1), ay = min(qy * fl.P + fl.P / 2, cam.H - 1);
+    const int tx = ax - tile.x0, ty = ay - tile.y0;
+    if (tx >= 0 && tx < tile.w && ty >= 0 && ty < tile.h) {
+        const size_t o = (size_t)ty * tile.w + tx;
+        id = prim[o];
+        if (id == 0xffffffffu) return false;
+        t = depth[o];
+        d = primary_dir(cam, ax, ay);
+        return true;
+    }
+    d = primary_dir(cam, ax, ay);
+    float tmin, tmax;
+    primary_range(cam, d, tmin, tmax);
+    const Hit h = trace(s, cam.eye, d, tmin, tmax);
+    t = h.t;
+    id = h.prim;
+    return id != 0xffffffffu;
+}
+
+// S6.  Probes of the levels below `warp_level` take one thread each (their cells hold at most 1 + 4 + 16 candidate anchors);
+// from `warp_level` up a probe takes a warp, which checks 32 candidates of a floating probe at a time — an empty cell of the
+// top level has 1365 of them, and one thread walking them would outlast the whole frame.
+__global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, unsigned thread_probes, TileRect tile,
+                                                   float offset, const float* __restrict__ depth, const uint32_t* __restrict__ prim,
                                                    float4* __restrict__ origin, float4* __restrict__ normal,
                                                    const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0)
 {
-    const unsigned gi = blockIdx.x * kBlock + threadIdx.x;
+    const unsigned g = blockIdx.x * kBlock + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool warp_mode = g >= thread_probes;          // thread_probes is a multiple of 32: whole warps are in one mode
+    const unsigned gi = warp_mode ? thread_probes + ((g - thread_probes) >> 5) : g;
     if (gi >= total) return;
     const int level = level_of(ls, gi);
     const DLevel& lv = ls.lv[level];
@@ -467,21 +497,44 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
         }
         need0[i] = (m | (m >> 16)) & 0xffffu;
     }
-    const int ax = min(px * lv.P + lv.P / 2, cam.W - 1), ay = min(py * lv.P + lv.P / 2, cam.H - 1);
-    const float3 d = primary_dir(cam, ax, ay);
-    float t;
-    uint32_t id;
-    const int tx = ax - tile.x0, ty = ay - tile.y0;
-    if (tx >= 0 && tx < tile.w && ty >= 0 && ty < tile.h) {
-        const size_t o = (size_t)ty * tile.w + tx;
-        t = depth[o];
-        id = prim[o];
+    // S6: the probe's own anchor first; when it sees no geometry the probe floats to the first anchor of the finer levels'
+    // probes inside its cell that does (level by level downwards, row-major within a level)
+    float3 d = f3(0.f, 0.f, 0.f);
+    float t = -1.0f;
+    uint32_t id = 0xffffffffu;
+    if (!warp_mode) {
+        for (int l = level; l >= 0 && id == 0xffffffffu; l--) {
+            const DLevel& fl = ls.lv[l];
+            const int sc = 1 << (level - l);
+            const int qy1 = min((py + 1) * sc, fl.gh), qx1 = min((px + 1) * sc, fl.gw);
+            for (int qy = py * sc; qy < qy1 && id == 0xffffffffu; qy++)
+                for (int qx = px * sc; qx < qx1; qx++)
+                    if (anchor_hit(s, cam, fl, tile, qx, qy, depth, prim, d, t, id)) break;
+        }
     } else {
-        float tmin, tmax;
-        primary_range(cam, d, tmin, tmax);
-        const Hit h = trace(s, cam.eye, d, tmin, tmax);
-        t = h.t;
-        id = h.prim;
+        for (int l = level; l >= 0 && id == 0xffffffffu; l--) {     // id is warp-uniform at every loop test
+            const DLevel& fl = ls.lv[l];
+            const int sc = 1 << (level - l);
+            const int qx0 = px * sc, qy0 = py * sc;
+            const int wdt = min((px + 1) * sc, fl.gw) - qx0, hgt = min((py + 1) * sc, fl.gh) - qy0;
+            const int n = wdt > 0 && hgt > 0 ? wdt * hgt : 0;
+            for (int base = 0; base < n; base += 32) {
+                const int c = base + (int)lane;
+                float3 dc = f3(0.f, 0.f, 0.f);
+                float tc = -1.0f;
+                uint32_t ic = 0xffffffffu;
+                const bool hit = c < n && anchor_hit(s, cam, fl, tile, qx0 + c % wdt, qy0 + c / wdt, depth, prim, dc, tc, ic);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {                                            // the first candidate in row-major order
+                    const int src = __ffs((int)m) - 1;
+                    id = __shfl_sync(0xffffffffu, ic, src);
+                    t = __shfl_sync(0xffffffffu, tc, src);
+                    d = f3(__shfl_sync(0xffffffffu, dc.x, src), __shfl_sync(0xffffffffu, dc.y, src), __shfl_sync(0xffffffffu, dc.z, src));
+                    break;
+                }
+            }
+        }
+        if (lane != 0) return;
     }
     if (id == 0xffffffffu) {
         origin[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -2092,7 +2145,12 @@ void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, uns
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
                    uint32_t* need0, cudaStream_t st)
 {
-    k_probes<<<blocks_for(total), kBlock, 0, st>>>(s, cam, ls, total, tile, offset, depth, prim, origin, normal, pixmask, need0);
+    // levels 0..2: a thread per probe; from level 3 up a warp per probe (k_probes).  The split is rounded down to a multiple of
+    // 32 so that a warp never mixes the two modes (the few probes of level 2 behind it simply get a warp each as well)
+    unsigned thread_probes = ls.n > 3 ? ls.lv[3].probe_offset : total;
+    thread_probes &= ~31u;
+    const size_t threads = (size_t)thread_probes + (size_t)(total - thread_probes) * 32;
+    k_probes<<<blocks_for(threads), kBlock, 0, st>>>(s, cam, ls, total, thread_probes, tile, offset, depth, prim, origin, normal, pixmask, need0);
 }
 
 // lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do

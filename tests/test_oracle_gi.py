@@ -1,6 +1,7 @@
 """The GI oracle (oracle/rc_oracle.c) against its golden fixture and against properties of the
 specification (include/rc_spec.h) that do not depend on any implementation."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -10,6 +11,7 @@ from oracle import gi_oracle as go
 from oracle import ref_ingest as ri
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "gi_cube64.npz"))
 
 
@@ -193,3 +195,40 @@ def test_clipped_ray_cast_equals_the_raster_restatement(name, W, H, near, far):
     unc = osc.gbuffer(osc.params(W, H, clip=False), cam, lights)
     if name in ("teapot", "cube", "test_room"):
         assert (unc["prim"] != gb["prim"]).mean() > 0.05     # the planes really cut something away
+
+
+def test_floating_probes_leave_no_lower_probe_without_an_upper_probe():
+    """rc_spec.h S6: a probe whose anchor pixel sees no geometry floats to the first finer-level anchor inside its cell that
+    does.  On the teapot's silhouette (78 % of the frame is background) that makes every valid probe of level i have at least
+    one valid probe among its four upper probes (S1), so S8 never falls back to "far field = sky" next to geometry; probes whose
+    whole cell is empty stay invalid, and a probe whose own anchor hits is exactly where it was before the rule existed."""
+    name, W, H = "teapot", 480, 270
+    osc = go.OracleScene(rc.scenes.scene_path(name))
+    pos, tgt, zn, zf = rc.scenes.orbit_camera(osc.bbox_min, osc.bbox_max, 5)
+    import math
+    cam = ri.uniform_camera_look_at(pos, tgt, np.float32(math.radians(45.0)), np.float32(W) / np.float32(H), zn, zf)
+    p = osc.params(W, H)
+    out = osc.render(p, cam, np.array([[0, 0, 0, 1]], np.float32))
+    lv, rects = out["levels"], out["rects"]
+    depth = out["depth"]
+    floated = 0
+    for i in range(p.N):
+        _, _, sw, sh = rects[i]
+        valid = (out["origins"][i][:, 3] != 0).reshape(sh, sw)
+        P = lv[i].P
+        ay = np.minimum(np.arange(sh) * P + P // 2, H - 1)
+        ax = np.minimum(np.arange(sw) * P + P // 2, W - 1)
+        own = depth[np.ix_(ay, ax)] >= 0
+        assert np.all(valid[own])                                  # an anchor that hits always gives a valid probe
+        floated += int((valid & ~own).sum())
+        # a cell without any geometry at its level-0 anchors stays invalid
+        if i + 1 < p.N:
+            _, _, usw, ush = rects[i + 1]
+            uvalid = (out["origins"][i + 1][:, 3] != 0).reshape(ush, usw)
+            ys, xs = np.nonzero(valid)
+            from common import _upper_pair
+            x0, x1 = _upper_pair(xs, usw)
+            y0, y1 = _upper_pair(ys, ush)
+            has = uvalid[y0, x0] | uvalid[y0, x1] | uvalid[y1, x0] | uvalid[y1, x1]
+            assert np.all(has), (i, int((~has).sum()))
+    assert floated > 20
