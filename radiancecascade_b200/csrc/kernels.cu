@@ -86,6 +86,11 @@ __device__ __forceinline__ void gbuffer_store(const DScene& s, const DCamera& ca
                                               int DD0, const float* s_dirs, uint16_t* __restrict__ pixmask, int tx, int ty, float3 d, const Hit& h)
 {
     const size_t o = (size_t)ty * tile.w + tx;
+    {   // a warp covers 8x4 pixels, i.e. lies inside one 32x8 occupancy cell: one stamp per warp that saw geometry
+        const unsigned act = __activemask();
+        const unsigned hits = __ballot_sync(act, h.prim != 0xffffffffu);
+        if (hits && (threadIdx.x & 31u) == (unsigned)(__ffs((int)hits) - 1)) out.occ[(size_t)(ty >> 3) * out.ow + (tx >> 5)] = out.frame;
+    }
     if (h.prim == 0xffffffffu) {
         out.depth[o] = -1.0f; out.prim[o] = 0xffffffffu; out.normal[o] = 0u; out.bary[o] = make_float2(0.f, 0.f);
         if (pixmask) pixmask[o] = 0;
@@ -439,6 +444,22 @@ __device__ __forceinline__ int level_of(const DLevelSet& ls, unsigned i)
     return l;
 }
 
+// S6 shortcut: true when the whole cell of probe (px, py) lies inside the tile and none of the 32x8-pixel occupancy cells it
+// touches was stamped in this frame — then no candidate anchor can hit.  The flags are dealt out to `n` cooperating lanes
+// (k-th lane takes flags k, k+n, ...); the caller combines the lanes' answers with a vote.  A cell that leaves the tile is
+// never "empty" here: its candidates are traced.
+__device__ __forceinline__ bool cell_empty(const DLevel& lv, const DCamera& cam, const TileRect& tile, int px, int py,
+                                           const uint32_t* __restrict__ occ, uint32_t frame, int ow, int k, int n)
+{
+    const int x0 = px * lv.P - tile.x0, y0 = py * lv.P - tile.y0;
+    const int x1 = min((px + 1) * lv.P, cam.W) - 1 - tile.x0, y1 = min((py + 1) * lv.P, cam.H) - 1 - tile.y0;
+    if (x0 < 0 || y0 < 0 || x1 >= tile.w || y1 >= tile.h) return false;
+    const int ox0 = x0 >> 5, oy0 = y0 >> 3, nx = (x1 >> 5) - ox0 + 1, ny = (y1 >> 3) - oy0 + 1;
+    for (int i = k; i < nx * ny; i += n)
+        if (occ[(size_t)(oy0 + i / nx) * ow + ox0 + i % nx] == frame) return false;
+    return true;
+}
+
 // primary hit through the anchor pixel of probe (qx, qy) of level fl: the G-buffer's when the anchor lies in the tile (same
 // ray, same S4/S5 arithmetic -> bit-identical), traced otherwise (halo probes of a multi-GPU tile)
 __device__ __forceinline__ bool anchor_hit(const DScene& s, const DCamera& cam, const DLevel& fl, const TileRect& tile, int qx, int qy,
@@ -469,7 +490,8 @@ __device__ __forceinline__ bool anchor_hit(const DScene& s, const DCamera& cam, 
 __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, unsigned thread_probes, TileRect tile,
                                                    float offset, const float* __restrict__ depth, const uint32_t* __restrict__ prim,
                                                    float4* __restrict__ origin, float4* __restrict__ normal,
-                                                   const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0)
+                                                   const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0,
+                                                   const uint32_t* __restrict__ occ, uint32_t frame, int ow)
 {
     const unsigned g = blockIdx.x * kBlock + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -503,16 +525,42 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
     float t = -1.0f;
     uint32_t id = 0xffffffffu;
     if (!warp_mode) {
-        for (int l = level; l >= 0 && id == 0xffffffffu; l--) {
-            const DLevel& fl = ls.lv[l];
-            const int sc = 1 << (level - l);
-            const int qy1 = min((py + 1) * sc, fl.gh), qx1 = min((px + 1) * sc, fl.gw);
-            for (int qy = py * sc; qy < qy1 && id == 0xffffffffu; qy++)
-                for (int qx = px * sc; qx < qx1; qx++)
-                    if (anchor_hit(s, cam, fl, tile, qx, qy, depth, prim, d, t, id)) break;
+        // (thread mode: at most 1 + 4 + 16 candidates.)  All candidate anchors that lie inside the tile are looked up FIRST, with
+        // independent loads — walking them one by one made every empty cell a chain of up to 21 dependent L2 round trips
+        // (k_probes 25 -> 55 us at 4K) — then the candidates are resolved in S6's order; only anchors outside the tile trace.
+        if (!anchor_hit(s, cam, lv, tile, px, py, depth, prim, d, t, id) && level >= 1 && !cell_empty(lv, cam, tile, px, py, occ, frame, ow, 0, 1)) {
+            uint32_t hitm = 0u, unkm = 0u;       // candidate k (S6 order, own anchor excluded): G-buffer says hit / not in the tile
+            int k = 0;
+            for (int l = level - 1; l >= 0; l--) {
+                const DLevel& fl = ls.lv[l];
+                const int sc = 1 << (level - l);
+                const int qy1 = min((py + 1) * sc, fl.gh), qx1 = min((px + 1) * sc, fl.gw);
+                for (int qy = py * sc; qy < qy1; qy++)
+                    for (int qx = px * sc; qx < qx1; qx++, k++) {
+                        const int tx = min(qx * fl.P + fl.P / 2, cam.W - 1) - tile.x0, ty = min(qy * fl.P + fl.P / 2, cam.H - 1) - tile.y0;
+                        if (tx >= 0 && tx < tile.w && ty >= 0 && ty < tile.h) { if (prim[(size_t)ty * tile.w + tx] != 0xffffffffu) hitm |= 1u << k; }
+                        else unkm |= 1u << k;
+                    }
+            }
+            if (hitm | unkm) {
+                k = 0;
+                for (int l = level - 1; l >= 0 && id == 0xffffffffu; l--) {
+                    const DLevel& fl = ls.lv[l];
+                    const int sc = 1 << (level - l);
+                    const int qy1 = min((py + 1) * sc, fl.gh), qx1 = min((px + 1) * sc, fl.gw);
+                    for (int qy = py * sc; qy < qy1 && id == 0xffffffffu; qy++)
+                        for (int qx = px * sc; qx < qx1; qx++, k++)
+                            if ((((hitm | unkm) >> k) & 1u) && anchor_hit(s, cam, fl, tile, qx, qy, depth, prim, d, t, id)) break;
+                }
+            }
         }
     } else {
-        for (int l = level; l >= 0 && id == 0xffffffffu; l--) {     // id is warp-uniform at every loop test
+        // own anchor by lane 0; an empty cell (all 32 lanes look at its occupancy stamps together) ends the search at once
+        bool own = false;
+        if (lane == 0) own = anchor_hit(s, cam, lv, tile, px, py, depth, prim, d, t, id);
+        own = __shfl_sync(0xffffffffu, own ? 1 : 0, 0) != 0;
+        const bool skip = own || level == 0 || __all_sync(0xffffffffu, cell_empty(lv, cam, tile, px, py, occ, frame, ow, (int)lane, 32));
+        for (int l = skip ? -1 : level - 1; l >= 0 && id == 0xffffffffu; l--) {     // id is warp-uniform at every loop test
             const DLevel& fl = ls.lv[l];
             const int sc = 1 << (level - l);
             const int qx0 = px * sc, qy0 = py * sc;
@@ -2143,14 +2191,15 @@ void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRe
 
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
-                   uint32_t* need0, cudaStream_t st)
+                   uint32_t* need0, const uint32_t* occ, uint32_t frame, int ow, cudaStream_t st)
 {
     // levels 0..2: a thread per probe; from level 3 up a warp per probe (k_probes).  The split is rounded down to a multiple of
     // 32 so that a warp never mixes the two modes (the few probes of level 2 behind it simply get a warp each as well)
     unsigned thread_probes = ls.n > 3 ? ls.lv[3].probe_offset : total;
     thread_probes &= ~31u;
     const size_t threads = (size_t)thread_probes + (size_t)(total - thread_probes) * 32;
-    k_probes<<<blocks_for(threads), kBlock, 0, st>>>(s, cam, ls, total, thread_probes, tile, offset, depth, prim, origin, normal, pixmask, need0);
+    k_probes<<<blocks_for(threads), kBlock, 0, st>>>(s, cam, ls, total, thread_probes, tile, offset, depth, prim, origin, normal, pixmask, need0,
+                                                     occ, frame, ow);
 }
 
 // lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do

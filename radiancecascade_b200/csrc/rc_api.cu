@@ -168,6 +168,8 @@ struct rc_ctx {
     // (ncu r2l: a third of the stall samples in the block prologue).  Off by default; kept as an A/B path.
     int gbuffer_binned = 0;
     uint32_t n_leaf_tris = 0;
+    DevBuf<uint32_t> d_occ;                         // 32x8-pixel occupancy stamps of the tile (GBufferOut::occ), frame_id = the stamp
+    uint32_t frame_id = 0;
     DevBuf<unsigned int> d_bin_count, d_bin_huge_count;
     DevBuf<uint32_t> d_bin_lists;
     DevBuf<uint8_t> d_bin_huge;
@@ -482,6 +484,7 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H, bool retile = false)
         }
         CU_OK(c, c->d_dirq.upload(q));
     }
+    CU_OK(c, c->d_occ.alloc_zero((size_t)((t.w + 31) / 32) * ((t.h + 7) / 8), !retile));    // stale stamps carry older frame ids
     CU_OK(c, c->d_bin_count.alloc_zero(bin_tiles(t)));          // always zeroed: a re-tiled context starts from empty candidate lists
     CU_OK(c, c->d_bin_lists.alloc(bin_list_entries(t)));
     CU_OK(c, c->d_bin_huge_count.alloc_zero(1));
@@ -702,7 +705,7 @@ void destroy_ctx(rc_ctx* c)
     if (c->h_ray_count) cudaFreeHost(c->h_ray_count);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     peer_release(c); c->d_ray_count.release();
-    c->d_dirs.release(); c->d_dirq.release(); c->d_axis.release(); c->d_bin_count.release(); c->d_bin_lists.release(); c->d_bin_huge_count.release(); c->d_bin_huge.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
+    c->d_dirs.release(); c->d_dirq.release(); c->d_axis.release(); c->d_occ.release(); c->d_bin_count.release(); c->d_bin_lists.release(); c->d_bin_huge_count.release(); c->d_bin_huge.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_frame_done) cudaEventDestroy(c->ev_frame_done);
@@ -916,7 +919,9 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     if (c->frame_open && c->frame_culled)           // the last frame never reached its gather: its list lengths are still set
         CU_OK(c, cudaMemsetAsync(c->d_ray_count.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
     c->frame_open = true;
-    GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p};
+    c->frame_id++;
+    if (c->frame_id == 0) c->frame_id = 1;
+    GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p, c->d_occ.p, c->frame_id, (c->tile.w + 31) / 32};
     if (c->gbuffer_binned) {
         launch_gbuffer_binned(c->scene, c->cam, c->lights, c->tile, gb, c->levels[0].D * c->levels[0].D, c->d_dirs.p,
                               c->frame_culled ? c->d_pixmask.p : nullptr, c->n_leaf_tris, c->d_bin_count.p, c->d_bin_lists.p,
@@ -934,7 +939,7 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     const DLevel& top = c->levels[c->N - 1];
     const unsigned n_probes = top.probe_offset + (unsigned)(top.sw * top.sh);
     launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p,
-                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, st);
+                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, c->d_occ.p, c->frame_id, (c->tile.w + 31) / 32, st);
     c->launches++;
     {
         const int ne = c->march_persist ? 0 : c->entry_levels();
