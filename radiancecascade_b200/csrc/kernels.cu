@@ -754,11 +754,12 @@ __device__ __forceinline__ uint32_t dup_spread16(uint32_t x)
     return x | (x << 1);
 }
 
-__global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_upper, int up_words, const float4* __restrict__ origin,
-                                                 const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
-                                                 uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
-                                                 uint32_t* __restrict__ list, unsigned int* __restrict__ count, int clear, int trigger, int dir_major,
-                                                 int tile_order, int append, int4 own)
+template <int BLK>
+__device__ __forceinline__ void need_body(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* __restrict__ origin,
+                                          const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
+                                          uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
+                                          uint32_t* __restrict__ list, unsigned int* __restrict__ count, int clear, int trigger, int dir_major,
+                                          int tile_order, int append, int4 own, size_t gi, unsigned* s_warp, unsigned* s_base_p, bool grid_dep)
 {
     // The per-level launches form a chain of short, latency-bound waves.  Launched with programmatic stream
     // serialization (launch_need pdl) level i+1 is set up while level i still runs: it may read what kernels before
@@ -768,7 +769,6 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
     if (trigger) cudaTriggerProgrammaticLaunchCompletion();
     const int bits = Dr * Dr, words = (bits + 31) >> 5;
     const size_t total = (size_t)lv.sw * lv.sh * words;
-    const size_t gi = (size_t)blockIdx.x * kBlock + threadIdx.x;
     uint32_t r = 0u, probe = 0u;
     int w = 0;
     float4 lw = make_float4(-1.f, 0.f, 0.f, 0.f);
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
         // independent loads first: the kernel is one short latency-bound wave
         const float valid = __ldg(origin + probe).w;
         if (has_upper) { lw = __ldg(link_w + probe); li = __ldg(link_idx + probe); }
-        cudaGridDependencySynchronize();
+        if (grid_dep) cudaGridDependencySynchronize();
         r = need[gi];
         if (valid == 0.0f) r = 0u;
         if (append && own.z >= 0) {
@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
         if (clear) need[gi] = 0u;
     }
     // (a) ray list: block-aggregated append (one atomicAdd per block; all blocks hit the same counter)
-    __shared__ unsigned s_warp[kBlock / 32], s_base;
+    unsigned& s_base = *s_base_p;
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     // tile-ordered append (tile_order != 0, levels whose requests are quads): permuted request masks
     int tiled = 0;
@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned tot = 0;
-        for (int k = 0; k < kBlock / 32; k++) { const unsigned t = s_warp[k]; s_warp[k] = tot; tot += t; }
+        for (int k = 0; k < BLK / 32; k++) { const unsigned t = s_warp[k]; s_warp[k] = tot; tot += t; }
         s_base = tot ? atomicAdd(count, tot) : 0u;
     }
     __syncthreads();
@@ -940,6 +940,47 @@ __global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_uppe
 #pragma unroll
         for (int q = 0; q < 4; q++)
             if (tw_idx[q] != 0xffffffffu) atomicOr(need_up + (size_t)up[k] * up_words + tw_idx[q], tw_val[q]);
+    }
+}
+
+
+__global__ void __launch_bounds__(kBlock) k_need(DLevel lv, int Dr, int has_upper, int up_words, const float4* __restrict__ origin,
+                                                 const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
+                                                 uint32_t* __restrict__ need, uint32_t* __restrict__ need_up,
+                                                 uint32_t* __restrict__ list, unsigned int* __restrict__ count, int clear, int trigger, int dir_major,
+                                                 int tile_order, int append, int4 own)
+{
+    __shared__ unsigned s_warp[kBlock / 32], s_base;
+    need_body<kBlock>(lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count, clear, trigger, dir_major, tile_order,
+                      append, own, (size_t)blockIdx.x * kBlock + threadIdx.x, s_warp, &s_base, true);
+}
+
+// Levels >= 1 of the request chain in ONE launch: a cluster of eight 1024-thread blocks walks the levels bottom-up with a
+// cluster barrier (release / acquire at cluster scope: the atomicOr pushes of level i are visible to every block before level
+// i+1 reads its masks) instead of a kernel boundary between them.  Each of those levels is a fraction of a wave of work; as
+// separate launches they cost 12-14 us apiece at 4K (7-10 us at 1080p and in every strip of a tiled frame) whatever their size.
+constexpr int kChainBlock = 1024, kChainCtas = 8;
+
+__global__ void __launch_bounds__(kChainBlock) k_need_chain(NeedChain c, const float4* __restrict__ origin, const uint4* __restrict__ link_idx,
+                                                            const float4* __restrict__ link_w, uint32_t* __restrict__ need_all,
+                                                            uint32_t* __restrict__ list_all, unsigned int* __restrict__ counts)
+{
+    __shared__ unsigned s_warp[kChainBlock / 32], s_base;
+    for (int i = c.first; i <= c.last; i++) {
+        const DLevel& lv = c.lv[i];
+        const int words = (c.Dr[i] * c.Dr[i] + 31) >> 5;
+        const size_t total = (size_t)lv.sw * lv.sh * words;
+        for (size_t base = 0; base < total; base += (size_t)kChainBlock * kChainCtas) {
+            need_body<kChainBlock>(lv, c.Dr[i], c.has_upper[i], c.up_words[i], origin + lv.probe_offset, link_idx + lv.probe_offset,
+                                   link_w + lv.probe_offset, need_all + c.need_off[i], need_all + c.need_up_off[i], list_all + c.list_off[i],
+                                   counts + i, c.clear[i], 0, c.dir_major[i], c.tile_order[i], c.append, c.own[i],
+                                   base + (size_t)blockIdx.x * kChainBlock + threadIdx.x, s_warp, &s_base, false);
+            __syncthreads();      // s_warp / s_base are reused by the next chunk
+        }
+        if (i < c.last) {
+            __threadfence();
+            asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
     }
 }
 
@@ -2264,6 +2305,21 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     else if (occ >= 10) { if (f) RC_LAUNCH_MARCH(true, 10, t); else RC_LAUNCH_MARCH(false, 10, t); }
     else { if (f) RC_LAUNCH_MARCH(true, 8, t); else RC_LAUNCH_MARCH(false, 8, t); }
 #undef RC_LAUNCH_MARCH
+}
+
+void launch_need_chain(const NeedChain& c, const float4* origin, const uint4* link_idx, const float4* link_w, uint32_t* need_all,
+                       uint32_t* list_all, unsigned int* counts, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kChainCtas);
+    cfg.blockDim = dim3(kChainBlock);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kChainCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_need_chain, c, origin, link_idx, link_w, need_all, list_all, counts);
 }
 
 void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,

@@ -96,6 +96,17 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
 void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,
                        const float4* up_avg, const uint4* link_idx, const float4* link_w, float4* avg_out, bool fused, int occ, bool pdl, int max_blocks,
                        const uint32_t* list, const unsigned int* count, bool up_const, cudaStream_t st);
+// levels first..last of the request chain in one launch (a thread-block cluster with a cluster barrier between the levels);
+// per level the same parameters as launch_need, offsets in words / entries from need_all / list_all; probe arrays are whole-frame
+struct NeedChain {
+    DLevel lv[RC_MAX_LEVELS];
+    int Dr[RC_MAX_LEVELS], has_upper[RC_MAX_LEVELS], up_words[RC_MAX_LEVELS], clear[RC_MAX_LEVELS], dir_major[RC_MAX_LEVELS], tile_order[RC_MAX_LEVELS];
+    unsigned long long need_off[RC_MAX_LEVELS], need_up_off[RC_MAX_LEVELS], list_off[RC_MAX_LEVELS];
+    int4 own[RC_MAX_LEVELS];
+    int first, last, append;
+};
+void launch_need_chain(const NeedChain& c, const float4* origin, const uint4* link_idx, const float4* link_w, uint32_t* need_all,
+                       uint32_t* list_all, unsigned int* counts, cudaStream_t st);
 int march_avg_ystep(int D, int map);
 // child averages of a finalised level from its texels (paths whose march kernel does not write them itself)
 void launch_child_avg(const DLevel& lv, const uint2* texels, float4* avg_out, cudaStream_t st);

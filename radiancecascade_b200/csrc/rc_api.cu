@@ -131,6 +131,10 @@ struct rc_ctx {
     std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
     int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
     int list_dir_major = 0;
+    // levels >= 1 of the request chain in one cluster launch (k_need_chain, eight 1024-thread blocks with cluster barriers between
+    // the levels).  Measured SLOWER: probes stage 0.128 -> 0.46 ms at 4K, 0.058 -> 0.11 at 1080p — level 1 alone is 130 k mask
+    // words at 4K, sixteen passes of a cluster that occupies 8 of 148 SMs.  Off; the per-level launches stay.
+    int need_fused = 0;
     int list_tiled = 1;                             // levels >= 2: ray lists in 4x2 quad-tile order (k_need tile_order)                         // bit i: level i's ray list is ordered direction-major inside each warp's share
     // rc_read_target_async: 0 = copy engine (cudaMemcpyAsync); n > 0 = n resident blocks of k_copy_to_host store the
     // target into the page-locked destination
@@ -789,6 +793,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_CULL")) c->cull = atoi(e) != 0;
         if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
         if (const char* e = getenv("RC_COPY_BLOCKS")) c->copy_blocks = atoi(e) < 0 ? 0 : (atoi(e) > 1024 ? 1024 : atoi(e));
+        if (const char* e = getenv("RC_NEED_FUSED")) c->need_fused = atoi(e) != 0;
         if (const char* e = getenv("RC_LIST_TILED")) c->list_tiled = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
         if (const char* e = getenv("RC_LIST_DIRMAJOR")) c->list_dir_major = (int)strtol(e, nullptr, 0);
         if (const char* e = getenv("RC_GATHER_MMA")) c->gather_mma = atoi(e) != 0;
@@ -856,18 +861,46 @@ rc_status rc_set_tile(rc_ctx* c, uint32_t x0, uint32_t y0, uint32_t w, uint32_t 
 
 // The k_need launches of one frame.  append = true: masks are consumed into the ray lists (and pushed up) level by level —
 // the single-pass form.  append = false: masks only (first pass of the halo exchange).
-static rc_status launch_need_chain(rc_ctx* c, cudaStream_t st, bool append)
+static int4 owned_rect(const rc_ctx* c, uint32_t i);
+
+// pass = 0: the single-pass form (masks consumed into the ray lists and pushed up, level by level);
+// pass = 1: masks only (first pass of the halo exchange);  pass = 2: lists of the owned probes from the completed masks
+static rc_status enqueue_need_chain(rc_ctx* c, cudaStream_t st, int pass)
 {
     const uint32_t n_lists = c->top_fillable() ? c->N - 1 : c->N;
-    for (uint32_t i = 0; i < n_lists; i++) {
+    const bool append = pass != 1, push = pass != 2;
+    auto has_upper_of = [&](uint32_t i) { return (push && i + 1 < n_lists) ? (i == 0 ? 1 : 2) : 0; };
+    auto own_of = [&](uint32_t i) { return (pass == 2 && i >= 1) ? owned_rect(c, i) : make_int4(0, 0, -1, -1); };
+    const uint32_t fused_from = (c->need_fused && n_lists >= 3) ? 1u : n_lists;      // levels >= fused_from go into ONE cluster launch
+    for (uint32_t i = 0; i < n_lists && i < fused_from; i++) {
         const DLevel& L = c->levels[i];
-        const int has_upper = i + 1 < n_lists ? (i == 0 ? 1 : 2) : 0;
+        const int has_upper = has_upper_of(i);
         const int up_res = i + 1 < c->N ? c->need_res[i + 1] : 0;
         launch_need(L, c->need_res[i], has_upper, (up_res * up_res + 31) / 32, c->d_origin.p + L.probe_offset,
                     c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, c->d_need.p + c->need_offset[i],
                     has_upper ? c->d_need.p + c->need_offset[i + 1] : nullptr, c->d_list.p + c->list_offset[i],
-                    c->d_ray_count.p + i, append && i >= 1, c->need_pdl && i >= 1, c->need_pdl && i + 1 < n_lists,
-                    ((c->list_dir_major >> i) & 1) != 0, i >= 1 ? c->list_tiled : 0, append, make_int4(0, 0, -1, -1), st);
+                    c->d_ray_count.p + i, append && i >= 1, c->need_pdl && i >= 1 && pass == 0, c->need_pdl && i + 1 < n_lists && pass == 0,
+                    ((c->list_dir_major >> i) & 1) != 0, i >= 1 ? c->list_tiled : 0, append, own_of(i), st);
+        c->launches++;
+    }
+    if (fused_from < n_lists) {
+        NeedChain ch{};
+        ch.first = (int)fused_from; ch.last = (int)n_lists - 1; ch.append = append ? 1 : 0;
+        for (uint32_t i = fused_from; i < n_lists; i++) {
+            const int up_res = i + 1 < c->N ? c->need_res[i + 1] : 0;
+            ch.lv[i] = c->levels[i];
+            ch.Dr[i] = c->need_res[i];
+            ch.has_upper[i] = has_upper_of(i);
+            ch.up_words[i] = (up_res * up_res + 31) / 32;
+            ch.clear[i] = append ? 1 : 0;
+            ch.dir_major[i] = (c->list_dir_major >> i) & 1;
+            ch.tile_order[i] = (c->list_tiled && ch.has_upper[i] != 1 && (ch.Dr[i] == 32 || (c->list_tiled > 1 && (ch.Dr[i] == 8 || ch.Dr[i] == 16)))) ? 1 : 0;
+            ch.need_off[i] = c->need_offset[i];
+            ch.need_up_off[i] = i + 1 < c->N ? c->need_offset[i + 1] : c->need_offset[i];
+            ch.list_off[i] = c->list_offset[i];
+            ch.own[i] = own_of(i);
+        }
+        launch_need_chain(ch, c->d_origin.p, c->d_link_idx.p, c->d_link_w.p, c->d_need.p, c->d_list.p, c->d_ray_count.p, st);
         c->launches++;
     }
     return RC_OK;
@@ -952,7 +985,7 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
         // request masks bottom-up + one ray list per level; a top level that is filled needs neither.
         // Halo exchange (RC_CFG_HALO_EXCHANGE): this pass only propagates the masks — the lists are built by rc_render_lists
         // after the caller has sent the requests of the probes this rank does not own to their owners
-        rc_status s = launch_need_chain(c, st, !c->exchange_active());
+        rc_status s = enqueue_need_chain(c, st, c->exchange_active() ? 1 : 0);
         if (s != RC_OK) return s;
         c->lists_pending = c->exchange_active();
     }
@@ -969,14 +1002,8 @@ rc_status rc_render_lists(rc_ctx* c, void* stream)
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     // second pass over the (now complete) masks: list the requests of the probes this rank owns, clear everything.
     // Level 0 is never exchanged: every level-0 probe of the sub-grid (the tile's probes and their one-probe ring) is marched here.
-    const uint32_t n_lists = c->top_fillable() ? c->N - 1 : c->N;
-    for (uint32_t i = 0; i < n_lists; i++) {
-        const DLevel& L = c->levels[i];
-        launch_need(L, c->need_res[i], 0, 0, c->d_origin.p + L.probe_offset, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset,
-                    c->d_need.p + c->need_offset[i], nullptr, c->d_list.p + c->list_offset[i], c->d_ray_count.p + i, i >= 1, false, false,
-                    ((c->list_dir_major >> i) & 1) != 0, i >= 1 ? c->list_tiled : 0, true, i == 0 ? make_int4(0, 0, -1, -1) : owned_rect(c, i), st);
-        c->launches++;
-    }
+    rc_status sl = enqueue_need_chain(c, st, 2);
+    if (sl != RC_OK) return sl;
     c->lists_pending = false;
     CU_OK(c, cudaGetLastError());
     return RC_OK;
@@ -1105,6 +1132,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "copy_blocks" && value >= 0 && value <= 1024) c->copy_blocks = value;
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
     else if (k == "list_tiled" && value >= 0 && value <= 2) c->list_tiled = value;
+    else if (k == "need_fused" && value >= 0 && value <= 1) c->need_fused = value;
     else if (k == "graph" && value >= 0 && value <= 1) c->use_graph = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
     else if (k == "march_grid" && value > 0) c->march_grid = value;
