@@ -537,6 +537,32 @@ def test_binned_primary_visibility_equals_bvh_traversal(name, W, H, tile):
         assert (got[1][0] != 0xFFFFFFFF).any()
 
 
+@pytest.mark.culled
+@pytest.mark.parametrize("name,W,H", [("living_room", 480, 270), ("teapot", 384, 216), ("cube", 130, 94)])
+def test_experimental_schedules_are_bit_identical(name, W, H):
+    """The measured-and-rejected schedules stay selectable for A/B runs and must not change a bit: one 2x2 quad
+    per thread in the march (k_march_quad), the request chain of levels >= 1 in one cluster launch (k_need_chain), 4x2-tile
+    order for every request resolution."""
+    st, _, _ = frame_setup(name, W, H)
+    res = []
+    for knobs in ({}, {"march_quad": 1}, {"march_quad": 1, "march_quad_occ": 8}, {"need_fused": 1}, {"need_fused": 1, "list_tiled": 2},
+                  {"need_fused": 1, "march_quad": 1, "gbuffer_binned": 1}):
+        r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name))
+        for k, v in knobs.items():
+            r.set_tuning(k, v)
+        r.update(st)
+        for _ in range(2):
+            r.render()
+        res.append((r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16).copy(), r.rays_marched(),
+                    [np.sort(r.ray_list(i)) for i in range(5)]))
+    for E, rays, lists in res[1:]:
+        assert np.array_equal(E, res[0][0])
+        assert rays == res[0][1]
+        for a, b in zip(lists, res[0][2]):
+            assert np.array_equal(a, b)
+    assert float(res[0][0].view(np.float16)[..., :3].astype(np.float32).max()) > 0.0
+
+
 def test_resize_matches_fresh_context():
     st, _, _ = frame_setup("cube", 96, 64)
     a = render_product("cube", 96, 64, st)
