@@ -55,6 +55,10 @@ enum {
  * far 100), exactly what the render pass keeps (Depth32Float, Less, clear 1.0: src/renderer.rs:354-360, 585-592).
  * Without the flag primary rays see [0, inf): the GI benchmark cameras use far = 4 x the scene diagonal either way. */
 #define RC_CFG_RASTER_CLIP    0x8u
+/* rc_spec.h S6, optional: a probe whose anchor pixel sees no geometry floats to the first anchor of the finer levels' probes inside
+ * its cell that does, so that no valid probe is left without a valid upper probe (the far field is then never dropped next to a
+ * silhouette).  Costs 4-8 % of a frame. */
+#define RC_CFG_FLOATING_PROBES 0x10u
 
 /* rc_update flags.  bit0 ≙ AppState::enable_normal_map (src/app.rs:18, src/renderer.rs:620-631) */
 #define RC_UPD_ENABLE_NORMAL_MAP 0x1u

@@ -87,12 +87,15 @@
  *   then model 1, ... in index-buffer order.
  *
  * ---- S6. probes -------------------------------------------------------------
- *   probe(px,py) of level i: primary ray through anchor(px,py).  On a miss the probe FLOATS: the candidates are the anchors
+ *   probe(px,py) of level i: primary ray through anchor(px,py); invalid on a miss.
+ *   Optional (RC_CFG_FLOATING_PROBES): on a miss the probe FLOATS instead: the candidates are the anchors
  *   of the probes of the finer levels l = i-1, ..., 0 that lie inside its cell — (qx,qy) with px*2^(i-l) <= qx < (px+1)*2^(i-l)
  *   (likewise y), inside the level-l grid — taken level by level downwards and row-major (qy, then qx) within a level; the
  *   first candidate whose primary ray hits places the probe (hit point, direction and triangle of THAT ray below).  Invalid
  *   only if none hits.  Consequence: a valid probe of level i always has a valid upper probe (the one whose cell contains its
- *   own cell lists its anchor and all of its candidates), so the far field of S8 is never dropped at a silhouette.
+ *   own cell lists its anchor and all of its candidates), so the far field of S8 is never dropped at a silhouette.  Without
+ *   the flag a lower probe none of whose four upper probes is valid takes the sky as its whole far field (S8).  The flag costs
+ *   4-8 % of a frame on one GPU and ~10 % per rank of a tiled frame (halo probes must trace their candidates): off by default.
  *   hit point h = fma(t, dir, eye);  ng = normalize(cross(e1,e2)), negated if dot(ng,dir) > 0
  *   origin = fma(offset, ng, h);  offset default L0/16.
  *   normalize(x) = x * (1/sqrt(dot(x,x)))   (glam 0.29 form)

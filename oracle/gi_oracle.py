@@ -42,7 +42,7 @@ class Params(C.Structure):
     _fields_ = [("W", C.c_int), ("H", C.c_int), ("P0", C.c_int), ("D0", C.c_int), ("N", C.c_int),
                 ("L0", C.c_float), ("t_far", C.c_float), ("offset", C.c_float), ("sky", C.c_float * 3),
                 ("tile_x0", C.c_int), ("tile_y0", C.c_int), ("tile_w", C.c_int), ("tile_h", C.c_int),
-                ("store_half", C.c_int), ("clip", C.c_int)]
+                ("store_half", C.c_int), ("clip", C.c_int), ("floating", C.c_int)]
 
 
 class Level(C.Structure):
@@ -174,13 +174,13 @@ class OracleScene:
         return out
 
     def params(self, W, H, P0=4, D0=4, N=6, L0=0.0, t_far=0.0, offset=0.0, sky=(0, 0, 0),
-               tile=None, store_half=True, clip=False) -> Params:
+               tile=None, store_half=True, clip=False, floating=False) -> Params:
         diag, dL0, dfar, _ = default_intervals(self.bbox_min, self.bbox_max)
         L0 = np.float32(L0) if L0 > 0 else dL0
         t_far = np.float32(t_far) if t_far > 0 else dfar
         offset = np.float32(offset) if offset > 0 else np.float32(L0 / np.float32(16.0))
         tile = tile or (0, 0, W, H)
-        return Params(W, H, P0, D0, N, L0, t_far, offset, (C.c_float * 3)(*sky), *tile, int(store_half), int(clip))
+        return Params(W, H, P0, D0, N, L0, t_far, offset, (C.c_float * 3)(*sky), *tile, int(store_half), int(clip), int(floating))
 
     @staticmethod
     def levels(p: Params) -> List[Level]:

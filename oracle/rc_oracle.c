@@ -448,6 +448,7 @@ typedef struct {
     int tile_x0, tile_y0, tile_w, tile_h;   /* pixels produced by gather/gbuffer */
     int store_half;                          /* round stored cascade texels / outputs through float16 */
     int clip;                                /* S4b: primary rays limited to the near / far planes of view_proj */
+    int floating;                            /* S6: probes with an empty anchor float to a finer-level anchor (optional) */
 } rco_params;
 
 typedef struct {
@@ -619,7 +620,7 @@ void rco_probes(const rco_scene* s, const rco_params* p, const float cam[20], in
          * levels' probes inside its cell that does (level by level downwards, row-major within a level) */
         rco_hit h; h.prim = 0xffffffffu; h.t = -1.0f; h.u = h.v = 0.0f;
         v3 d = V(0, 0, 0);
-        for (int l = level; l >= 0 && h.prim == 0xffffffffu; l--) {
+        for (int l = level; l >= (p->floating ? 0 : level) && h.prim == 0xffffffffu; l--) {
             const rco_level F = FL[l];
             const int sc = 1 << (level - l);
             for (int qy = py * sc; qy < (py + 1) * sc && qy < F.gh && h.prim == 0xffffffffu; qy++)

@@ -21,6 +21,7 @@ RC_CFG_SEPARATE_MERGE = 0x1
 RC_CFG_NO_TEXTURES = 0x2
 RC_CFG_HALO_EXCHANGE = 0x4
 RC_CFG_RASTER_CLIP = 0x8
+RC_CFG_FLOATING_PROBES = 0x10
 RC_UPD_ENABLE_NORMAL_MAP = 0x1
 
 (RC_TARGET_IRRADIANCE, RC_TARGET_DIRECT, RC_TARGET_DEPTH, RC_TARGET_NORMAL, RC_TARGET_ALBEDO, RC_TARGET_PRIM,

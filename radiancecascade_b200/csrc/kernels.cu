@@ -451,6 +451,11 @@ __device__ __forceinline__ int level_of(const DLevelSet& ls, unsigned i)
 __device__ __forceinline__ bool cell_empty(const DLevel& lv, const DCamera& cam, const TileRect& tile, int px, int py,
                                            const uint32_t* __restrict__ occ, uint32_t frame, int ow, int k, int n)
 {
+    {   // a cell that misses the screen-space rectangle of the scene's bounding box is empty wherever it lies (halo probes of a
+        // multi-GPU strip would otherwise TRACE every candidate anchor of every sky cell: probes stage 0.065 -> 0.13 ms at 8 ranks)
+        const int fx0 = px * lv.P, fy0 = py * lv.P, fx1 = min((px + 1) * lv.P, cam.W) - 1, fy1 = min((py + 1) * lv.P, cam.H) - 1;
+        if (fx1 < cam.sb_x0 || fx0 > cam.sb_x1 || fy1 < cam.sb_y0 || fy0 > cam.sb_y1) return true;
+    }
     const int x0 = px * lv.P - tile.x0, y0 = py * lv.P - tile.y0;
     const int x1 = min((px + 1) * lv.P, cam.W) - 1 - tile.x0, y1 = min((py + 1) * lv.P, cam.H) - 1 - tile.y0;
     if (x0 < 0 || y0 < 0 || x1 >= tile.w || y1 >= tile.h) return false;
@@ -458,6 +463,15 @@ __device__ __forceinline__ bool cell_empty(const DLevel& lv, const DCamera& cam,
     for (int i = k; i < nx * ny; i += n)
         if (occ[(size_t)(oy0 + i / nx) * ow + ox0 + i % nx] == frame) return false;
     return true;
+}
+
+// the traced branch of anchor_hit, out of line: k_probes inlines anchor_hit three times, and three copies of the BVH traversal
+// cost it 64 registers (42 % occupancy) for a branch only halo probes of a multi-GPU tile ever take
+__device__ __noinline__ Hit trace_primary(const DScene& s, const DCamera& cam, float3 d)
+{
+    float tmin, tmax;
+    primary_range(cam, d, tmin, tmax);
+    return trace(s, cam.eye, d, tmin, tmax);
 }
 
 // primary hit through the anchor pixel of probe (qx, qy) of level fl: the G-buffer's when the anchor lies in the tile (same
@@ -476,9 +490,7 @@ __device__ __forceinline__ bool anchor_hit(const DScene& s, const DCamera& cam, 
         return true;
     }
     d = primary_dir(cam, ax, ay);
-    float tmin, tmax;
-    primary_range(cam, d, tmin, tmax);
-    const Hit h = trace(s, cam.eye, d, tmin, tmax);
+    const Hit h = trace_primary(s, cam, d);
     t = h.t;
     id = h.prim;
     return id != 0xffffffffu;
@@ -491,7 +503,7 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
                                                    float offset, const float* __restrict__ depth, const uint32_t* __restrict__ prim,
                                                    float4* __restrict__ origin, float4* __restrict__ normal,
                                                    const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0,
-                                                   const uint32_t* __restrict__ occ, uint32_t frame, int ow)
+                                                   const uint32_t* __restrict__ occ, uint32_t frame, int ow, int floating)
 {
     const unsigned g = blockIdx.x * kBlock + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -528,7 +540,7 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
         // (thread mode: at most 1 + 4 + 16 candidates.)  All candidate anchors that lie inside the tile are looked up FIRST, with
         // independent loads — walking them one by one made every empty cell a chain of up to 21 dependent L2 round trips
         // (k_probes 25 -> 55 us at 4K) — then the candidates are resolved in S6's order; only anchors outside the tile trace.
-        if (!anchor_hit(s, cam, lv, tile, px, py, depth, prim, d, t, id) && level >= 1 && !cell_empty(lv, cam, tile, px, py, occ, frame, ow, 0, 1)) {
+        if (!anchor_hit(s, cam, lv, tile, px, py, depth, prim, d, t, id) && floating && level >= 1 && !cell_empty(lv, cam, tile, px, py, occ, frame, ow, 0, 1)) {
             uint32_t hitm = 0u, unkm = 0u;       // candidate k (S6 order, own anchor excluded): G-buffer says hit / not in the tile
             int k = 0;
             for (int l = level - 1; l >= 0; l--) {
@@ -559,7 +571,7 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
         bool own = false;
         if (lane == 0) own = anchor_hit(s, cam, lv, tile, px, py, depth, prim, d, t, id);
         own = __shfl_sync(0xffffffffu, own ? 1 : 0, 0) != 0;
-        const bool skip = own || level == 0 || __all_sync(0xffffffffu, cell_empty(lv, cam, tile, px, py, occ, frame, ow, (int)lane, 32));
+        const bool skip = own || !floating || level == 0 || __all_sync(0xffffffffu, cell_empty(lv, cam, tile, px, py, occ, frame, ow, (int)lane, 32));
         for (int l = skip ? -1 : level - 1; l >= 0 && id == 0xffffffffu; l--) {     // id is warp-uniform at every loop test
             const DLevel& fl = ls.lv[l];
             const int sc = 1 << (level - l);
@@ -2232,15 +2244,15 @@ void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRe
 
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
-                   uint32_t* need0, const uint32_t* occ, uint32_t frame, int ow, cudaStream_t st)
+                   uint32_t* need0, const uint32_t* occ, uint32_t frame, int ow, bool floating, cudaStream_t st)
 {
-    // levels 0..2: a thread per probe; from level 3 up a warp per probe (k_probes).  The split is rounded down to a multiple of
-    // 32 so that a warp never mixes the two modes (the few probes of level 2 behind it simply get a warp each as well)
-    unsigned thread_probes = ls.n > 3 ? ls.lv[3].probe_offset : total;
-    thread_probes &= ~31u;
+    // floating probes: levels 0..2 a thread per probe, from level 3 up a warp per probe (k_probes).  The split is rounded down to
+    // a multiple of 32 so that a warp never mixes the two modes (the few probes of level 2 behind it simply get a warp each too)
+    unsigned thread_probes = (floating && ls.n > 3) ? ls.lv[3].probe_offset : total;
+    if (thread_probes != total) thread_probes &= ~31u;
     const size_t threads = (size_t)thread_probes + (size_t)(total - thread_probes) * 32;
     k_probes<<<blocks_for(threads), kBlock, 0, st>>>(s, cam, ls, total, thread_probes, tile, offset, depth, prim, origin, normal, pixmask, need0,
-                                                     occ, frame, ow);
+                                                     occ, frame, ow, floating ? 1 : 0);
 }
 
 // lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do

@@ -69,7 +69,7 @@ void launch_direct(const DScene& s, const DCamera& cam, const DLights& L, TileRe
 // culling) every level-0 probe also gets need0[probe] = OR of the masks of the pixels it serves
 void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, unsigned total, TileRect tile, float offset,
                    const float* depth, const uint32_t* prim, float4* origin, float4* normal, const uint16_t* pixmask,
-                   uint32_t* need0, const uint32_t* occ, uint32_t frame, int ow, cudaStream_t st);
+                   uint32_t* need0, const uint32_t* occ, uint32_t frame, int ow, bool floating, cudaStream_t st);
 // One launch, two independent jobs that only read the probe origins:
 //  link:  per lower probe (levels 0..N-2, `link_total` probes) the 4 upper probe slots (sub-grid linear) and
 //         normalised weights (w.x < 0: no valid upper probe)

@@ -823,6 +823,28 @@ rc_status rc_update(rc_ctx* c, const rc_camera* cam, const rc_light* lights, uin
     if (!primary_basis(*cam, c->cam)) { c->error = "rc_update: singular view_proj matrix"; return RC_ERR_INVALID_ARG; }
     c->cam.W = (int)c->W; c->cam.H = (int)c->H;
     c->cam.clip = (c->cfg.flags & RC_CFG_RASTER_CLIP) ? 1 : 0;
+    {   // screen-space rectangle of the scene's bounding box (grown by 1e-3 of the diagonal and by two pixels), in double
+        const rc_scene_info& I = c->host.info;
+        double x0 = 1e30, y0 = 1e30, x1 = -1e30, y1 = -1e30;
+        bool whole = false;
+        const double pad = 1e-3 * (double)c->host.diag;
+        for (int k = 0; k < 8 && !whole; k++) {
+            const double p[3] = {(k & 1 ? I.bbox_max[0] + pad : I.bbox_min[0] - pad), (k & 2 ? I.bbox_max[1] + pad : I.bbox_min[1] - pad),
+                                 (k & 4 ? I.bbox_max[2] + pad : I.bbox_min[2] - pad)};
+            const float* M = cam->view_proj;
+            const double cx = M[0] * p[0] + M[4] * p[1] + M[8] * p[2] + M[12], cy = M[1] * p[0] + M[5] * p[1] + M[9] * p[2] + M[13];
+            const double cw = M[3] * p[0] + M[7] * p[1] + M[11] * p[2] + M[15];
+            if (!(cw > 1e-6 * (std::fabs(cx) + std::fabs(cy) + 1.0))) { whole = true; break; }
+            const double sx = (cx / cw * 0.5 + 0.5) * c->W - 0.5, sy = (1.0 - (cy / cw * 0.5 + 0.5)) * c->H - 0.5;
+            x0 = std::min(x0, sx); x1 = std::max(x1, sx); y0 = std::min(y0, sy); y1 = std::max(y1, sy);
+        }
+        if (whole || !(x0 == x0) || !(y0 == y0) || !(x1 == x1) || !(y1 == y1)) { c->cam.sb_x0 = 0; c->cam.sb_y0 = 0; c->cam.sb_x1 = (int)c->W - 1; c->cam.sb_y1 = (int)c->H - 1; }
+        else {
+            auto cl = [](double v, int hi) { return (int)std::min(std::max(v, -1.0), (double)hi); };
+            c->cam.sb_x0 = cl(std::floor(x0) - 2, (int)c->W); c->cam.sb_y0 = cl(std::floor(y0) - 2, (int)c->H);
+            c->cam.sb_x1 = cl(std::ceil(x1) + 2, (int)c->W); c->cam.sb_y1 = cl(std::ceil(y1) + 2, (int)c->H);
+        }
+    }
     c->lights.n = (int)n_lights;
     for (uint32_t i = 0; i < n_lights; i++) memcpy(c->lights.pos[i], lights[i].position, 16);
     c->lights.flags = flags;
@@ -972,7 +994,8 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     const DLevel& top = c->levels[c->N - 1];
     const unsigned n_probes = top.probe_offset + (unsigned)(top.sw * top.sh);
     launch_probes(c->scene, c->cam, ls, n_probes, c->tile, c->offset, c->d_depth.p, c->d_prim.p, c->d_origin.p, c->d_normal.p,
-                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, c->d_occ.p, c->frame_id, (c->tile.w + 31) / 32, st);
+                  c->frame_culled ? c->d_pixmask.p : nullptr, c->d_need.p, c->d_occ.p, c->frame_id, (c->tile.w + 31) / 32,
+                  (c->cfg.flags & RC_CFG_FLOATING_PROBES) != 0, st);
     c->launches++;
     {
         const int ne = c->march_persist ? 0 : c->entry_levels();

@@ -51,6 +51,9 @@ struct DCamera {                // rc_spec.h S4
     int clip;
     // rows 0, 1, 3 of view_proj (x_clip, y_clip, w_clip of a world point): the triangle binning of the primary-visibility pass
     float4 row_x, row_y, row_w;
+    // conservative screen-space rectangle of the scene's bounding box (pixels, inclusive; the whole frame when a corner of the
+    // box is behind the eye): no primary ray outside it hits anything — k_probes' S6 search skips cells that miss it
+    int sb_x0, sb_y0, sb_x1, sb_y1;
 };
 
 struct DLevel {

@@ -563,6 +563,36 @@ def test_experimental_schedules_are_bit_identical(name, W, H):
     assert float(res[0][0].view(np.float16)[..., :3].astype(np.float32).max()) > 0.0
 
 
+@pytest.mark.culled
+@pytest.mark.parametrize("name,W,H", [("teapot", 480, 270), ("living_room", 320, 180), ("sonic", 200, 260)])
+def test_floating_probes_match_oracle_and_tiles(name, W, H):
+    """RC_CFG_FLOATING_PROBES (rc_spec.h S6): probes with an empty anchor float to a finer-level anchor with geometry.  The
+    default (culled) path against the oracle with the same rule — irradiance within S10, more probes valid than without the
+    flag — and a tile context (whose halo probes trace their candidates) equals the crop of the full frame bit for bit."""
+    st, cam, larr = frame_setup(name, W, H)
+    cc = rc.CascadeConfig(flags=_ffi.RC_CFG_FLOATING_PROBES)
+    r = render_product(name, W, H, st, cc)
+    osc = oracle_scene(name)
+    out = osc.render(osc.params(W, H, store_half=True, floating=True), cam, larr)
+    E, Eo = half_to_f32(r.read_target(_ffi.RC_TARGET_IRRADIANCE)), out["irradiance"]
+    peak = float(Eo[..., :3].max())
+    assert np.array_equal(E[..., 3], Eo[..., 3])
+    assert np.abs(E[..., :3] - Eo[..., :3]).max() <= 1e-2 * peak
+    assert psnr(E[..., :3], Eo[..., :3], peak) >= 50.0
+    plain = osc.render(osc.params(W, H, store_half=True), cam, larr)
+    nv = sum(int((o[:, 3] != 0).sum()) for o in out["origins"])
+    assert nv > sum(int((o[:, 3] != 0).sum()) for o in plain["origins"]) or name == "living_room"
+    # marched rays: more probes are valid, so at least as many rays as without the flag
+    assert sum(m for m in r.rays_marched() if m) >= sum(m for m in render_product(name, W, H, st).rays_marched() if m)
+    full = r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16)
+    for tile in ((0, H // 3, W, H // 4), (W // 4, H // 5, W // 2, H // 2)):
+        x0, y0, w, h = tile
+        rt = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name), rc.CascadeConfig(flags=_ffi.RC_CFG_FLOATING_PROBES, tile=tile))
+        rt.update(st)
+        rt.render()
+        assert np.array_equal(rt.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16), full[y0:y0 + h, x0:x0 + w]), tile
+
+
 def test_resize_matches_fresh_context():
     st, _, _ = frame_setup("cube", 96, 64)
     a = render_product("cube", 96, 64, st)

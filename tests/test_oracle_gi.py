@@ -198,8 +198,8 @@ def test_clipped_ray_cast_equals_the_raster_restatement(name, W, H, near, far):
 
 
 def test_floating_probes_leave_no_lower_probe_without_an_upper_probe():
-    """rc_spec.h S6: a probe whose anchor pixel sees no geometry floats to the first finer-level anchor inside its cell that
-    does.  On the teapot's silhouette (78 % of the frame is background) that makes every valid probe of level i have at least
+    """rc_spec.h S6 with RC_CFG_FLOATING_PROBES: a probe whose anchor pixel sees no geometry floats to the first finer-level
+    anchor inside its cell that does.  On the teapot's silhouette (78 % of the frame is background) that makes every valid probe of level i have at least
     one valid probe among its four upper probes (S1), so S8 never falls back to "far field = sky" next to geometry; probes whose
     whole cell is empty stay invalid, and a probe whose own anchor hits is exactly where it was before the rule existed."""
     name, W, H = "teapot", 480, 270
@@ -207,10 +207,24 @@ def test_floating_probes_leave_no_lower_probe_without_an_upper_probe():
     pos, tgt, zn, zf = rc.scenes.orbit_camera(osc.bbox_min, osc.bbox_max, 5)
     import math
     cam = ri.uniform_camera_look_at(pos, tgt, np.float32(math.radians(45.0)), np.float32(W) / np.float32(H), zn, zf)
-    p = osc.params(W, H)
+    p = osc.params(W, H, floating=True)
     out = osc.render(p, cam, np.array([[0, 0, 0, 1]], np.float32))
     lv, rects = out["levels"], out["rects"]
     depth = out["depth"]
+    # without the flag some valid lower probes have no valid upper probe (the limitation the flag removes)
+    plain = osc.render(osc.params(W, H), cam, np.array([[0, 0, 0, 1]], np.float32))
+    orphans = 0
+    for i in range(p.N - 1):
+        _, _, sw, sh = rects[i]
+        _, _, usw, ush = rects[i + 1]
+        v = (plain["origins"][i][:, 3] != 0).reshape(sh, sw)
+        uv = (plain["origins"][i + 1][:, 3] != 0).reshape(ush, usw)
+        ys, xs = np.nonzero(v)
+        from common import _upper_pair
+        x0, x1 = _upper_pair(xs, usw)
+        y0, y1 = _upper_pair(ys, ush)
+        orphans += int((~(uv[y0, x0] | uv[y0, x1] | uv[y1, x0] | uv[y1, x1])).sum())
+    assert orphans > 0
     floated = 0
     for i in range(p.N):
         _, _, sw, sh = rects[i]
