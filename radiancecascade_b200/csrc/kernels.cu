@@ -86,7 +86,7 @@ __device__ __forceinline__ void gbuffer_store(const DScene& s, const DCamera& ca
                                               int DD0, const float* s_dirs, uint16_t* __restrict__ pixmask, int tx, int ty, float3 d, const Hit& h)
 {
     const size_t o = (size_t)ty * tile.w + tx;
-    {   // a warp covers 8x4 pixels, i.e. lies inside one 32x8 occupancy cell: one stamp per warp that saw geometry
+    if (out.occ) {   // (floating probes only) a warp covers 8x4 pixels, i.e. lies inside one 32x8 occupancy cell: one stamp per warp that saw geometry
         const unsigned act = __activemask();
         const unsigned hits = __ballot_sync(act, h.prim != 0xffffffffu);
         if (hits && (threadIdx.x & 31u) == (unsigned)(__ffs((int)hits) - 1)) out.occ[(size_t)(ty >> 3) * out.ow + (tx >> 5)] = out.frame;
@@ -476,6 +476,7 @@ __device__ __noinline__ Hit trace_primary(const DScene& s, const DCamera& cam, f
 
 // primary hit through the anchor pixel of probe (qx, qy) of level fl: the G-buffer's when the anchor lies in the tile (same
 // ray, same S4/S5 arithmetic -> bit-identical), traced otherwise (halo probes of a multi-GPU tile)
+template <bool OUTLINE>
 __device__ __forceinline__ bool anchor_hit(const DScene& s, const DCamera& cam, const DLevel& fl, const TileRect& tile, int qx, int qy,
                                            const float* __restrict__ depth, const uint32_t* __restrict__ prim, float3& d, float& t, uint32_t& id)
 {
@@ -490,7 +491,14 @@ __device__ __forceinline__ bool anchor_hit(const DScene& s, const DCamera& cam, 
         return true;
     }
     d = primary_dir(cam, ax, ay);
-    const Hit h = trace_primary(s, cam, d);
+    Hit h;
+    if (OUTLINE) {
+        h = trace_primary(s, cam, d);
+    } else {
+        float tmin, tmax;
+        primary_range(cam, d, tmin, tmax);
+        h = trace(s, cam.eye, d, tmin, tmax);
+    }
     t = h.t;
     id = h.prim;
     return id != 0xffffffffu;
@@ -499,15 +507,17 @@ __device__ __forceinline__ bool anchor_hit(const DScene& s, const DCamera& cam, 
 // S6.  Probes of the levels below `warp_level` take one thread each (their cells hold at most 1 + 4 + 16 candidate anchors);
 // from `warp_level` up a probe takes a warp, which checks 32 candidates of a floating probe at a time — an empty cell of the
 // top level has 1365 of them, and one thread walking them would outlast the whole frame.
+template <bool FLOATING>      // compiled twice: without the S6 candidate search k_probes is the lean round-1 kernel (45 registers, no stack)
 __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevelSet ls, unsigned total, unsigned thread_probes, TileRect tile,
                                                    float offset, const float* __restrict__ depth, const uint32_t* __restrict__ prim,
                                                    float4* __restrict__ origin, float4* __restrict__ normal,
                                                    const uint16_t* __restrict__ pixmask, uint32_t* __restrict__ need0,
-                                                   const uint32_t* __restrict__ occ, uint32_t frame, int ow, int floating)
+                                                   const uint32_t* __restrict__ occ, uint32_t frame, int ow)
 {
+    constexpr bool floating = FLOATING;
     const unsigned g = blockIdx.x * kBlock + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    const bool warp_mode = g >= thread_probes;          // thread_probes is a multiple of 32: whole warps are in one mode
+    const bool warp_mode = FLOATING && g >= thread_probes;          // thread_probes is a multiple of 32: whole warps are in one mode
     const unsigned gi = warp_mode ? thread_probes + ((g - thread_probes) >> 5) : g;
     if (gi >= total) return;
     const int level = level_of(ls, gi);
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
         // (thread mode: at most 1 + 4 + 16 candidates.)  All candidate anchors that lie inside the tile are looked up FIRST, with
         // independent loads — walking them one by one made every empty cell a chain of up to 21 dependent L2 round trips
         // (k_probes 25 -> 55 us at 4K) — then the candidates are resolved in S6's order; only anchors outside the tile trace.
-        if (!anchor_hit(s, cam, lv, tile, px, py, depth, prim, d, t, id) && floating && level >= 1 && !cell_empty(lv, cam, tile, px, py, occ, frame, ow, 0, 1)) {
+        if (!anchor_hit<FLOATING>(s, cam, lv, tile, px, py, depth, prim, d, t, id) && floating && level >= 1 && !cell_empty(lv, cam, tile, px, py, occ, frame, ow, 0, 1)) {
             uint32_t hitm = 0u, unkm = 0u;       // candidate k (S6 order, own anchor excluded): G-buffer says hit / not in the tile
             int k = 0;
             for (int l = level - 1; l >= 0; l--) {
@@ -562,14 +572,14 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
                     const int qy1 = min((py + 1) * sc, fl.gh), qx1 = min((px + 1) * sc, fl.gw);
                     for (int qy = py * sc; qy < qy1 && id == 0xffffffffu; qy++)
                         for (int qx = px * sc; qx < qx1; qx++, k++)
-                            if ((((hitm | unkm) >> k) & 1u) && anchor_hit(s, cam, fl, tile, qx, qy, depth, prim, d, t, id)) break;
+                            if ((((hitm | unkm) >> k) & 1u) && anchor_hit<FLOATING>(s, cam, fl, tile, qx, qy, depth, prim, d, t, id)) break;
                 }
             }
         }
     } else {
         // own anchor by lane 0; an empty cell (all 32 lanes look at its occupancy stamps together) ends the search at once
         bool own = false;
-        if (lane == 0) own = anchor_hit(s, cam, lv, tile, px, py, depth, prim, d, t, id);
+        if (lane == 0) own = anchor_hit<FLOATING>(s, cam, lv, tile, px, py, depth, prim, d, t, id);
         own = __shfl_sync(0xffffffffu, own ? 1 : 0, 0) != 0;
         const bool skip = own || !floating || level == 0 || __all_sync(0xffffffffu, cell_empty(lv, cam, tile, px, py, occ, frame, ow, (int)lane, 32));
         for (int l = skip ? -1 : level - 1; l >= 0 && id == 0xffffffffu; l--) {     // id is warp-uniform at every loop test
@@ -583,7 +593,7 @@ __global__ void __launch_bounds__(kBlock) k_probes(DScene s, DCamera cam, DLevel
                 float3 dc = f3(0.f, 0.f, 0.f);
                 float tc = -1.0f;
                 uint32_t ic = 0xffffffffu;
-                const bool hit = c < n && anchor_hit(s, cam, fl, tile, qx0 + c % wdt, qy0 + c / wdt, depth, prim, dc, tc, ic);
+                const bool hit = c < n && anchor_hit<FLOATING>(s, cam, fl, tile, qx0 + c % wdt, qy0 + c / wdt, depth, prim, dc, tc, ic);
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
                 if (m) {                                            // the first candidate in row-major order
                     const int src = __ffs((int)m) - 1;
@@ -2251,8 +2261,12 @@ void launch_probes(const DScene& s, const DCamera& cam, const DLevelSet& ls, uns
     unsigned thread_probes = (floating && ls.n > 3) ? ls.lv[3].probe_offset : total;
     if (thread_probes != total) thread_probes &= ~31u;
     const size_t threads = (size_t)thread_probes + (size_t)(total - thread_probes) * 32;
-    k_probes<<<blocks_for(threads), kBlock, 0, st>>>(s, cam, ls, total, thread_probes, tile, offset, depth, prim, origin, normal, pixmask, need0,
-                                                     occ, frame, ow, floating ? 1 : 0);
+    if (floating)
+        k_probes<true><<<blocks_for(threads), kBlock, 0, st>>>(s, cam, ls, total, thread_probes, tile, offset, depth, prim, origin, normal, pixmask,
+                                                               need0, occ, frame, ow);
+    else
+        k_probes<false><<<blocks_for(threads), kBlock, 0, st>>>(s, cam, ls, total, thread_probes, tile, offset, depth, prim, origin, normal, pixmask,
+                                                                need0, occ, frame, ow);
 }
 
 // lane distance of a texel's +dy neighbour inside the warp, or 0 when the 2x2 children of a lower direction do

@@ -976,7 +976,8 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     c->frame_open = true;
     c->frame_id++;
     if (c->frame_id == 0) c->frame_id = 1;
-    GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p, c->d_occ.p, c->frame_id, (c->tile.w + 31) / 32};
+    GBufferOut gb{c->d_depth.p, c->d_prim.p, c->d_nrm.p, c->d_bary.p, (c->cfg.flags & RC_CFG_FLOATING_PROBES) ? c->d_occ.p : nullptr, c->frame_id,
+                  (c->tile.w + 31) / 32};
     if (c->gbuffer_binned) {
         launch_gbuffer_binned(c->scene, c->cam, c->lights, c->tile, gb, c->levels[0].D * c->levels[0].D, c->d_dirs.p,
                               c->frame_culled ? c->d_pixmask.p : nullptr, c->n_leaf_tris, c->d_bin_count.p, c->d_bin_lists.p,
