@@ -123,7 +123,10 @@ __device__ __forceinline__ void gbuffer_store(const DScene& s, const DCamera& ca
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out,
+#ifndef RC_GBUF_MINB
+#define RC_GBUF_MINB 4   // resident 256-thread blocks per SM the register allocation must allow (A/B: make EXTRA=-DRC_GBUF_MINB=n)
+#endif
+__global__ void __launch_bounds__(kBlock, RC_GBUF_MINB) k_gbuffer(DScene s, DCamera cam, DLights L, TileRect tile, GBufferOut out,
                                                     int DD0, const float* __restrict__ dirs0, uint16_t* __restrict__ pixmask)
 {
     __shared__ float s_dirs[3 * 16];

@@ -313,9 +313,10 @@ class TiledRenderer:
             cc.flags |= _ffi.RC_CFG_HALO_EXCHANGE
         self.exchanger = None
         if self.balancer is not None and world > 1:
-            # the cuts will move: size the (grow-only) device buffers once for a strip of twice the average height, so that
-            # re-tiling never reaches the allocator (a cudaFree + cudaMalloc of the cascade stalls the rank for ~0.1 s)
-            rows = min(H, 2 * -(-H // world) + 64)
+            # the cuts will move: size the (grow-only) device buffers once for a strip of three times the average height (balanced
+            # 8-way cuts of the 4K living room reach 2.5x), so that re-tiling does not normally reach the allocator (a cudaFree +
+            # cudaMalloc of the cascade stalls the rank for ~0.1 s; a taller strip still works, it just pays that once)
+            rows = min(H, 3 * -(-H // world) + 64)
             y0 = min(self.tiles[rank][1], H - rows)
             cc.tile = (0, y0, W, rows)
         self.renderer = DefaultRenderer.new(device, (W, H), state, path, cc)
