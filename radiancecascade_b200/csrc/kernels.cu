@@ -779,6 +779,24 @@ __device__ __forceinline__ uint32_t dup_spread16(uint32_t x)
     return x | (x << 1);
 }
 
+// trace_inv's first iteration (node 0 = the root, far bound = tmax) with the slab reciprocals `inv` of a direction from the level's
+// table: true when both child boxes are missed, i.e. the traversal would pop its empty stack and return "no hit" at once
+__device__ __forceinline__ bool root_miss(float4 q0, float4 q1, float4 q2, float3 o, float3 inv, float tmin, float tmax)
+{
+    const float3 noi = f3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+    float ax = fmaf(q0.x, inv.x, noi.x), bx = fmaf(q0.w, inv.x, noi.x);
+    float ay = fmaf(q0.y, inv.y, noi.y), by = fmaf(q1.x, inv.y, noi.y);
+    float az = fmaf(q0.z, inv.z, noi.z), bz = fmaf(q1.y, inv.z, noi.z);
+    const float n0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    const float f0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    ax = fmaf(q1.z, inv.x, noi.x); bx = fmaf(q2.y, inv.x, noi.x);
+    ay = fmaf(q1.w, inv.y, noi.y); by = fmaf(q2.z, inv.y, noi.y);
+    az = fmaf(q2.x, inv.z, noi.z); bz = fmaf(q2.w, inv.z, noi.z);
+    const float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    const float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    return !(n0 <= f0 || n1 <= f1);
+}
+
 template <int BLK>
 __device__ __forceinline__ void need_body(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* __restrict__ origin,
                                           const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
@@ -1009,6 +1027,88 @@ __global__ void __launch_bounds__(kChainBlock) k_need_chain(NeedChain c, const f
     }
 }
 
+// ------------------------------------------------------------------ split ray lists
+// In the open scenes half of a level's requests or more are rays that leave the scene's bounds at once; in k_march they idle
+// next to lanes that traverse for hundreds of instructions (ncu r2e: 14 of 32 lanes active in level 3's node loop).  k_split
+// runs once per frame between the request chain and the march, one thread per list entry of every level chosen by the host:
+// an entry whose rays ALL fail the first step of the traversal — root_miss, the very expressions of trace_inv's first iteration
+// — is a certain miss.  The level's list is copied into a second one, entries that enter the tree at the front (in their old
+// order: the 4x2-tile order of k_need survives), certain misses at the back; k_march gives the latter threads that skip
+// the traversal.  Same rays, same outcome for each: every texel is unchanged.
+constexpr int kSplitBlock = 256, kSplitChunk = 2048;
+
+// true when every ray of list entry e (levels >= 1: the 2x2 children of a quad; level 0: one texel) misses both root boxes
+__device__ __forceinline__ bool entry_misses(const SplitJob& jb, float4 q0, float4 q1, float4 q2, bool quad, int ld, uint32_t DD, uint32_t e)
+{
+    const DLevel& lv = jb.lv;
+    if (quad) {
+        // consecutive entries of a list are mostly consecutive quads of one probe: one broadcast origin and three coalesced
+        // 16-byte loads per lane (through the per-direction table the four children cost eight loads on 64-byte strides,
+        // and the kernel was bound by L1 wavefronts, not by its arithmetic)
+        const uint32_t qd = e & ((DD >> 2) - 1u), probe = e >> (2 * ld - 2);
+        const float3 o = xyz(__ldg(jb.origin + probe));
+        const float4 a = __ldg(jb.qinv + 3 * (size_t)qd), b = __ldg(jb.qinv + 3 * (size_t)qd + 1), c = __ldg(jb.qinv + 3 * (size_t)qd + 2);
+        const bool m0 = root_miss(q0, q1, q2, o, f3(a.x, a.y, a.z), lv.t0, lv.t1), m1 = root_miss(q0, q1, q2, o, f3(a.w, b.x, b.y), lv.t0, lv.t1);
+        const bool m2 = root_miss(q0, q1, q2, o, f3(b.z, b.w, c.x), lv.t0, lv.t1), m3 = root_miss(q0, q1, q2, o, f3(c.y, c.z, c.w), lv.t0, lv.t1);
+        return m0 & m1 & m2 & m3;
+    }
+    const uint32_t probe = e >> (2 * ld), d = e & (DD - 1u);
+    const float3 o = xyz(__ldg(jb.origin + probe));
+    const float4 a0 = __ldg(jb.dirq + 2 * (size_t)d), a1 = __ldg(jb.dirq + 2 * (size_t)d + 1);
+    return root_miss(q0, q1, q2, o, f3(a0.w, a1.x, a1.y), lv.t0, lv.t1);
+}
+
+// Block `blk` of `nblk` working on one level's list, kSplitBlock consecutive entries per step (one per thread), in chunks of
+// kSplitChunk consecutive entries per block.
+__device__ __forceinline__ void split_body(const SplitJob& jb, unsigned blk, unsigned nblk, unsigned* s_w, unsigned* s_base)
+{
+    const unsigned n = jb.counts[jb.level];
+    unsigned int* n_triv = jb.counts + RC_MAX_LEVELS + jb.level;      // bit 31: "this level was classified in this frame" (rc_api: adaptive choice)
+    unsigned int* n_real = jb.counts + 2 * RC_MAX_LEVELS + jb.level;
+    const bool quad = jb.level >= 1;
+    const int ld = 31 - __clz(jb.lv.D);
+    const uint32_t DD = (uint32_t)jb.lv.D * (uint32_t)jb.lv.D;
+    if (blk == 0 && threadIdx.x == 0) atomicOr(n_triv, 0x80000000u);
+    const float4 q0 = __ldg(jb.root), q1 = __ldg(jb.root + 1), q2 = __ldg(jb.root + 2);
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    for (size_t chunk = (size_t)blk * kSplitChunk; chunk < n; chunk += (size_t)nblk * kSplitChunk) {
+        for (size_t base = chunk; base < chunk + kSplitChunk && base < n; base += kSplitBlock) {      // (uniform over the block)
+            const size_t j = base + threadIdx.x;
+            const bool have = j < n;
+            uint32_t e = 0u;
+            bool miss = false;
+            if (have) {
+                e = __ldg(jb.list_a + j);
+                miss = entry_misses(jb, q0, q1, q2, quad, ld, DD, e);
+            }
+            // stable partition, block-aggregated: one atomicAdd per class; counts packed 16 : 16
+            const unsigned br = __ballot_sync(0xffffffffu, have && !miss), bt = __ballot_sync(0xffffffffu, have && miss);
+            if (lane == 0) s_w[wid] = (unsigned)__popc(br) | ((unsigned)__popc(bt) << 16);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned tot = 0;
+                for (int i = 0; i < kSplitBlock / 32; i++) { const unsigned t = s_w[i]; s_w[i] = tot; tot += t; }
+                s_base[0] = (tot & 0xffffu) ? atomicAdd(n_real, tot & 0xffffu) : 0u;
+                s_base[1] = (tot >> 16) ? (atomicAdd(n_triv, tot >> 16) & 0x7fffffffu) : 0u;
+            }
+            __syncthreads();
+            if (have) {
+                if (!miss) jb.list_b[s_base[0] + (s_w[wid] & 0xffffu) + (unsigned)__popc(br & lt)] = e;
+                else jb.list_b[jb.cap - 1u - (s_base[1] + (s_w[wid] >> 16) + (unsigned)__popc(bt & lt))] = e;
+            }
+            __syncthreads();      // s_w / s_base are reused by the next step
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSplitBlock) k_split(SplitPlan plan)
+{
+    __shared__ unsigned s_w[kSplitBlock / 32], s_base[2];
+    int k = 0;
+    while (k + 1 < plan.n && blockIdx.x >= plan.block_off[k + 1]) k++;
+    split_body(plan.job[k], blockIdx.x - plan.block_off[k], plan.block_off[k + 1] - plan.block_off[k], s_w, s_base);
+}
+
 // far-field radiance of lower texel (dx, dy) from the merged upper level (S8).
 // `up_avg` holds, per upper probe and LOWER direction, a_k = 0.25*(((c0 + c1) + c2) + c3) of the four child texels
 // (float16 values summed in float32, exactly the S8 expression) — written once by the kernel that finalised
@@ -1154,26 +1254,35 @@ __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel
                                                   uint2* __restrict__ texels, const float4* __restrict__ up_avg,
                                                   const uint4* __restrict__ link_idx, const float4* __restrict__ link_w,
                                                   const int4* __restrict__ entry, float4* __restrict__ avg_out, int ystep,
-                                                  const uint32_t* __restrict__ list, const unsigned int* __restrict__ count, int quad)
+                                                  const uint32_t* __restrict__ list, const unsigned int* __restrict__ count, int quad,
+                                                  const unsigned int* __restrict__ count_triv, unsigned list_cap)
 {
     cudaTriggerProgrammaticLaunchCompletion();   // the next level's kernel may begin once every block got here
     const size_t DD = (size_t)lv.D * lv.D;
     // culled mode (list != null): thread j marches the j-th requested texel of the level's ray list (k_need) —
-    // for levels >= 1 the list holds 2x2 quads, four consecutive lanes each, so the child average is two shuffles
-    if (list) total = (size_t)__ldg(count) * (quad ? 4u : 1u);
+    // for levels >= 1 the list holds 2x2 quads, four consecutive lanes each, so the child average is two shuffles.
+    // Entries [0, n_real) are read from the front of the list; the n_triv entries after them from its back: certain
+    // misses (k_split), which get the merge and the store but no traversal.
+    unsigned n_real = 0u;
+    if (list) {
+        n_real = __ldg(count);
+        total = ((size_t)n_real + (count_triv ? (__ldg(count_triv) & 0x7fffffffu) : 0u)) * (quad ? 4u : 1u);
+    }
     // grid-stride over whole warps (the child-average epilogue shuffles with a full mask): with a full-size grid
     // this is one iteration; with a resident grid (rc_set_tuning "march_waves") each warp walks packets g, g + G, ...
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const unsigned lane = threadIdx.x & 31u;
     for (size_t g0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); g0 < total; g0 += stride) {
         uint32_t probe = 0, d = 0;
-        bool in_range;
+        bool in_range, certain_miss = false;
         if (list) {
             const size_t j = g0 + lane;
             in_range = j < total;
             if (in_range) {
                 const int ld = 31 - __clz(lv.D);   // culled mode requires power-of-two D (rc_api)
-                const uint32_t e = __ldg(list + (quad ? j >> 2 : j));
+                const size_t q = quad ? j >> 2 : j;
+                certain_miss = q >= n_real;
+                const uint32_t e = __ldg(list + (certain_miss ? (size_t)list_cap - 1u - (q - n_real) : q));
                 if (quad) {
                     const uint32_t q = e & (uint32_t)((DD >> 2) - 1);
                     const uint32_t x = q & (uint32_t)((lv.D >> 1) - 1), y = q >> (ld - 1);
@@ -1195,7 +1304,8 @@ __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel
                 const float4 qa = __ldg(dirq + 2 * (size_t)d), qb = __ldg(dirq + 2 * (size_t)d + 1);
                 const float3 w = xyz(qa);
                 const float3 o = xyz(og);
-                const Hit h = trace_inv(s, o, w, f3(qa.w, qb.x, qb.y), lv.t0, lv.t1, entry ? entry + 2 * (size_t)probe : nullptr);
+                Hit h; h.t = -1.0f; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+                if (!certain_miss) h = trace_inv(s, o, w, f3(qa.w, qb.x, qb.y), lv.t0, lv.t1, entry ? entry + 2 * (size_t)probe : nullptr);
                 t = finalize_texel<FUSED>(s, L, lv, UD, top, sky, probe, d, o, w, h, up_avg, link_idx, link_w);
             }
             texels[(size_t)probe * DD + d] = t;
@@ -1647,8 +1757,8 @@ __global__ void __launch_bounds__(kBlock) k_gather(DCamera cam, DLevel l0, TileR
     extern __shared__ uint4 s_mem[];
     // last kernel of the frame: publish the ray-list lengths to (mapped, pinned) host memory — posted writes,
     // nothing waits for them; the host sizes the next frames' march grids from whatever has arrived
-    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) {
-        counts_out[threadIdx.x] = counts_in[threadIdx.x];
+    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 3 * RC_MAX_LEVELS) {
+        if (threadIdx.x < 2 * RC_MAX_LEVELS) counts_out[threadIdx.x] = counts_in[threadIdx.x];   // (lengths, certain misses; k_split)
         counts_in[threadIdx.x] = 0u;   // the next frame's lists start empty
     }
     const int DD = DDT ? DDT : l0.D * l0.D, H2 = DD >> 1, stride = H2 + 1;
@@ -1735,8 +1845,8 @@ __global__ void __launch_bounds__(kBlock) k_gather_pipe(DCamera cam, DLevel l0, 
 {
     constexpr int DD = 16, H2 = DD >> 1, stride = H2 + 1;
     extern __shared__ uint4 s_mem[];
-    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) {   // see k_gather
-        counts_out[threadIdx.x] = counts_in[threadIdx.x];
+    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 3 * RC_MAX_LEVELS) {   // see k_gather
+        if (threadIdx.x < 2 * RC_MAX_LEVELS) counts_out[threadIdx.x] = counts_in[threadIdx.x];
         counts_in[threadIdx.x] = 0u;
     }
     const size_t buf_u4 = (size_t)max_probes * (stride + 1);            // texels + one float4 origin per probe
@@ -1873,8 +1983,8 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
 {
     extern __shared__ __align__(128) unsigned char gm_raw[];
     GatherMmaSmem& sm = *reinterpret_cast<GatherMmaSmem*>(gm_raw);
-    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < RC_MAX_LEVELS) {   // see k_gather
-        counts_out[threadIdx.x] = counts_in[threadIdx.x];
+    if (counts_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 3 * RC_MAX_LEVELS) {   // see k_gather
+        if (threadIdx.x < 2 * RC_MAX_LEVELS) counts_out[threadIdx.x] = counts_in[threadIdx.x];
         counts_in[threadIdx.x] = 0u;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2302,7 +2412,8 @@ void launch_link_entry(const DScene& s, const DLevelSet& ls, unsigned link_total
 void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLevel* up, bool top, float3 sky,
                   const float4* origin, const float* dirs, const float4* dirq, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ, bool pdl,
-                  bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const, cudaStream_t st)
+                  bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const,
+                  const unsigned int* count_triv, unsigned list_cap, cudaStream_t st)
 {
     const int block = 128;
     if (map == MAP_DIR_TILE && (lv.D & 7)) map = MAP_LINEAR;   // the 8x4 direction tile needs D % 8 == 0
@@ -2326,7 +2437,7 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
     cfg.numAttrs = (pdl && fused && !top) ? 1 : 0;   // only a kernel that waits on its predecessor may start early
 #define RC_LAUNCH_MARCH(F, M, T)                                                                                              \
     (compact ? cudaLaunchKernelEx(&cfg, k_march_compact<F, M>, s, L, lv, UD, T, sky, map, origin, dirs, texels, up_avg, link_idx, link_w) \
-             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirq, texels, up_avg, link_idx, link_w, entry, avg_out, ystep, list, count, quad))
+             : cudaLaunchKernelEx(&cfg, k_march<F, M>, s, L, lv, UD, T, sky, map, n, origin, dirq, texels, up_avg, link_idx, link_w, entry, avg_out, ystep, list, count, quad, count_triv, list_cap))
     const bool f = fused && !top;
     const int t = f ? 0 : topi;
     if (occ >= 16) { if (f) RC_LAUNCH_MARCH(true, 16, t); else RC_LAUNCH_MARCH(false, 16, t); }
@@ -2396,6 +2507,14 @@ void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const fl
     cudaLaunchKernelEx(&cfg, k_need, lv, Dr, has_upper, up_words, origin, link_idx, link_w, need, need_up, list, count, clear ? 1 : 0,
                        trigger ? 1 : 0, dir_major ? 1 : 0, (tile_order && has_upper != 1 && (Dr == 32 || (tile_order > 1 && (Dr == 8 || Dr == 16)))) ? 1 : 0,
                        append ? 1 : 0, own);
+}
+
+int split_chunk() { return kSplitChunk; }
+
+void launch_split(const SplitPlan& plan, cudaStream_t st)
+{
+    if (plan.n <= 0 || !plan.block_off[plan.n]) return;
+    k_split<<<plan.block_off[plan.n], kSplitBlock, 0, st>>>(plan);
 }
 
 void launch_march_all(const DScene& s, const DLights& L, const DLevelSet& ls, const int* levels, int n, const int* map,

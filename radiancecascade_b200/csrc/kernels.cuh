@@ -90,7 +90,7 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
                   const float4* origin, const float* dirs, const float4* dirq, uint2* texels, const float4* up_avg,
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ,
                   bool pdl, bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const,
-                  cudaStream_t st);
+                  const unsigned int* count_triv, unsigned list_cap, cudaStream_t st);
 // culled levels >= 1, one 2x2 quad of texels per thread (k_march_quad): list = the level's quad list, count = its length;
 // occ = resident 64-thread blocks per SM the register allocation must allow (8 -> 128 regs, 12 -> 80, 16 -> 64)
 void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,
@@ -98,6 +98,29 @@ void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, floa
                        const uint32_t* list, const unsigned int* count, bool up_const, cudaStream_t st);
 // levels first..last of the request chain in one launch (a thread-block cluster with a cluster barrier between the levels);
 // per level the same parameters as launch_need, offsets in words / entries from need_all / list_all; probe arrays are whole-frame
+// split ray lists (k_split): a level's list (list_a, length counts[level]) is copied into list_b — entries whose rays all miss the
+// BVH root's two child boxes from the back of the level's `cap` entries (counted in counts[RC_MAX_LEVELS + level], bit 31 set as
+// "classified"), the others from the front (counts[2 * RC_MAX_LEVELS + level]).
+struct SplitJob {
+    DLevel lv;
+    int level;
+    unsigned cap;
+    const float4* root;       // node 0 of the BVH
+    const float4* origin;     // the level's probe origins
+    const float4* dirq;       // the level's direction + slab-reciprocal table (2 x float4 per direction): level 0
+    const float4* qinv;       // levels >= 1: 3 x float4 per quad = the reciprocals of its children (0,0) (1,0) (0,1) (1,1)
+    const uint32_t* list_a;
+    uint32_t* list_b;
+    unsigned int* counts;
+};
+// blocks [block_off[k], block_off[k+1]) of one launch work on job[k]
+struct SplitPlan {
+    int n;
+    unsigned block_off[RC_MAX_LEVELS + 1];
+    SplitJob job[RC_MAX_LEVELS];
+};
+int split_chunk();
+void launch_split(const SplitPlan& plan, cudaStream_t st);
 struct NeedChain {
     DLevel lv[RC_MAX_LEVELS];
     int Dr[RC_MAX_LEVELS], has_upper[RC_MAX_LEVELS], up_words[RC_MAX_LEVELS], clear[RC_MAX_LEVELS], dir_major[RC_MAX_LEVELS], tile_order[RC_MAX_LEVELS];

@@ -126,7 +126,34 @@ struct rc_ctx {
     // host memory (posted writes, no copy, no sync); the next frames size their march grids from the latest values that have arrived
     // (x1.25 + slack).  The kernels loop over the list with a grid stride, so any grid size is correct — a
     // stale or missing estimate only costs empty blocks (too large) or a second loop trip (too small).
-    unsigned int* h_ray_count = nullptr;            // pinned, RC_MAX_LEVELS entries; 0xffffffff = nothing arrived yet
+    unsigned int* h_ray_count = nullptr;            // pinned, 2 x RC_MAX_LEVELS entries: [i] = entries of level i's list (0xffffffff = nothing arrived yet),
+                                                    // [RC_MAX_LEVELS + i] = its certain misses, bit 31 set if k_split classified the level in that frame
+    // Split lists: k_split sorts certain misses (root-box test) to the back of a copy of the level's list, k_march skips their traversal.
+    // 0 = off, 2 = every level, 1 = adaptive: the test costs ~40 instructions per requested ray and pays only where many rays leave
+    // the scene at once, so a level is classified while the last measured share of certain misses is high (on at >= 25 %, off
+    // below 15 %); every level >= 1 is measured in the first frame and in every 64th.  Any choice gives the same texels.
+    int list_split = 1;
+    bool split_on[RC_MAX_LEVELS] = {};
+    uint32_t split_mask = 0;                         // levels whose split list (d_list2) the frame being enqueued marches
+    DevBuf<uint32_t> d_list2;
+    unsigned int list_len(uint32_t i) const          // entries of level i's last list that arrived (0xffffffff: none yet)
+    {
+        const unsigned int a = *(volatile unsigned int*)(h_ray_count + i);
+        return a;
+    }
+    bool split_level(uint32_t i)                     // classify level i in the frame being enqueued?
+    {
+        if (!list_split || march_quad) return false;
+        if (list_split >= 2) return true;
+        if (i == 0) return false;                    // level 0: short rays from the entry frontier, a certain miss costs the march next to nothing
+        const unsigned int a = *(volatile unsigned int*)(h_ray_count + i), t = *(volatile unsigned int*)(h_ray_count + RC_MAX_LEVELS + i);
+        if (a == 0xffffffffu) return true;           // nothing has arrived yet: measure
+        if (t & 0x80000000u) {
+            const double share = a ? (double)(t & 0x7fffffffu) / (double)a : 0.0;
+            if (share >= 0.25) split_on[i] = true; else if (share < 0.15) split_on[i] = false;
+        }
+        return split_on[i] || (frame_id & 63u) == 1u;
+    }
     std::vector<size_t> need_offset, list_offset;   // words / entries before level i
     std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
     int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
@@ -206,6 +233,8 @@ struct rc_ctx {
     // per direction (w.xyz, 1/w.x), (1/w.y, 1/w.z, 0, 0): the slab-test reciprocals of S5 depend on the direction only,
     // so they are divided once here (IEEE, the same safe_inv expression) instead of three times per ray in k_march
     DevBuf<float4> d_dirq;
+    DevBuf<float4> d_qinv;                         // per level >= 1 and quad: slab reciprocals of its four children (k_split)
+    size_t qinv_offset[RC_MAX_LEVELS] = {};
     DevBuf<float> d_depth;
     DevBuf<uint32_t> d_prim, d_nrm;
     DevBuf<uint2> d_albedo, d_direct, d_irr, d_irr2;   // irradiance is double-buffered for rc_read_target_async
@@ -467,9 +496,10 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H, bool retile = false)
     }
     CU_OK(c, c->d_need.alloc_zero(c->need_offset[N], !retile));
     CU_OK(c, c->d_list.alloc(c->list_offset[N]));
-    CU_OK(c, c->d_ray_count.alloc_zero(RC_MAX_LEVELS, !retile));
-    if (!c->h_ray_count) CU_OK(c, cudaHostAlloc((void**)&c->h_ray_count, RC_MAX_LEVELS * sizeof(unsigned int), cudaHostAllocMapped));
-    if (!retile) for (uint32_t i = 0; i < RC_MAX_LEVELS; i++) c->h_ray_count[i] = 0xffffffffu;   // (a re-tiled context keeps its grid-size estimates)
+    CU_OK(c, c->d_list2.alloc(c->list_offset[N]));
+    CU_OK(c, c->d_ray_count.alloc_zero(3 * RC_MAX_LEVELS, !retile));
+    if (!c->h_ray_count) CU_OK(c, cudaHostAlloc((void**)&c->h_ray_count, 2 * RC_MAX_LEVELS * sizeof(unsigned int), cudaHostAllocMapped));
+    if (!retile) for (uint32_t i = 0; i < 2 * RC_MAX_LEVELS; i++) c->h_ray_count[i] = i < RC_MAX_LEVELS ? 0xffffffffu : 0u;   // (a re-tiled context keeps its grid-size estimates)
     if (!retile) CU_OK(c, c->d_dirs.upload(all_dirs));
     if (!retile) {   // S4's per-column / per-row terms, evaluated once with the very expressions primary_dir uses
         std::vector<float> axis((size_t)W + H);
@@ -487,6 +517,26 @@ rc_status setup_frame(rc_ctx* c, uint32_t W, uint32_t H, bool retile = false)
             q[2 * k + 1] = make_float4(safe_inv(y), safe_inv(z), 0.f, 0.f);
         }
         CU_OK(c, c->d_dirq.upload(q));
+        // k_split's table: the same reciprocals, the four children of a quad (levels >= 1: direction (2x + i, 2y + j) of quad (x, y),
+        // in the order (0,0) (1,0) (0,1) (1,1)) side by side — 3 x float4 per quad, consecutive quads consecutive
+        std::vector<float4> qi;
+        for (uint32_t i = 0; i < N; i++) {
+            c->qinv_offset[i] = qi.size();
+            const int D = c->levels[i].D;
+            if (i == 0 || (D & 1)) continue;
+            const float4* lq = q.data() + 2 * (c->dir_offset[i] / 3);
+            for (int y = 0; y < D / 2; y++)
+                for (int x = 0; x < D / 2; x++) {
+                    float v[12];
+                    for (int ch = 0; ch < 4; ch++) {
+                        const size_t d = (size_t)(2 * y + (ch >> 1)) * D + 2 * x + (ch & 1);
+                        v[3 * ch] = lq[2 * d].w; v[3 * ch + 1] = lq[2 * d + 1].x; v[3 * ch + 2] = lq[2 * d + 1].y;
+                    }
+                    for (int k = 0; k < 3; k++) qi.push_back(make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+                }
+        }
+        if (qi.empty()) qi.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+        CU_OK(c, c->d_qinv.upload(qi));
     }
     CU_OK(c, c->d_occ.alloc_zero((size_t)((t.w + 31) / 32) * ((t.h + 7) / 8), !retile));    // stale stamps carry older frame ids
     CU_OK(c, c->d_bin_count.alloc_zero(bin_tiles(t)));          // always zeroed: a re-tiled context starts from empty candidate lists
@@ -705,11 +755,11 @@ void destroy_ctx(rc_ctx* c)
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_nodes.release(); c->d_tri_geom.release(); c->d_tri_eg.release(); c->d_tris.release(); c->d_tri_model.release();
     c->d_verts.release(); c->d_srgb.release(); c->d_mats.release(); c->d_tex.release(); c->d_tex_data.release();
-    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release(); c->d_need.release(); c->d_list.release(); c->d_pixmask.release();
+    c->d_cascade.release(); c->d_origin.release(); c->d_normal.release(); c->d_link_idx.release(); c->d_link_w.release(); c->d_entry.release(); c->d_avg.release(); c->d_need.release(); c->d_list.release(); c->d_list2.release(); c->d_pixmask.release();
     if (c->h_ray_count) cudaFreeHost(c->h_ray_count);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     peer_release(c); c->d_ray_count.release();
-    c->d_dirs.release(); c->d_dirq.release(); c->d_axis.release(); c->d_occ.release(); c->d_bin_count.release(); c->d_bin_lists.release(); c->d_bin_huge_count.release(); c->d_bin_huge.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
+    c->d_dirs.release(); c->d_dirq.release(); c->d_qinv.release(); c->d_axis.release(); c->d_occ.release(); c->d_bin_count.release(); c->d_bin_lists.release(); c->d_bin_huge_count.release(); c->d_bin_huge.release(); c->d_depth.release(); c->d_prim.release(); c->d_nrm.release(); c->d_albedo.release();
     c->d_bary.release(); c->d_direct.release(); c->d_irr.release(); c->d_irr2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_frame_done) cudaEventDestroy(c->ev_frame_done);
@@ -794,6 +844,7 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
         if (const char* e = getenv("RC_COPY_BLOCKS")) c->copy_blocks = atoi(e) < 0 ? 0 : (atoi(e) > 1024 ? 1024 : atoi(e));
         if (const char* e = getenv("RC_NEED_FUSED")) c->need_fused = atoi(e) != 0;
+        if (const char* e = getenv("RC_LIST_SPLIT")) c->list_split = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
         if (const char* e = getenv("RC_LIST_TILED")) c->list_tiled = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
         if (const char* e = getenv("RC_LIST_DIRMAJOR")) c->list_dir_major = (int)strtol(e, nullptr, 0);
         if (const char* e = getenv("RC_GATHER_MMA")) c->gather_mma = atoi(e) != 0;
@@ -925,6 +976,36 @@ static rc_status enqueue_need_chain(rc_ctx* c, cudaStream_t st, int pass)
         launch_need_chain(ch, c->d_origin.p, c->d_link_idx.p, c->d_link_w.p, c->d_need.p, c->d_list.p, c->d_ray_count.p, st);
         c->launches++;
     }
+    if (append) {
+        // split lists (k_split): one launch over every level chosen for this frame, sized like the march grids from the last
+        // list lengths that arrived (grid-stride inside a level's blocks; the whole capacity while nothing has arrived)
+        SplitPlan plan{};
+        c->split_mask = 0;
+        for (uint32_t i = 0; i < n_lists; i++) {
+            if (!c->split_level(i)) continue;
+            const size_t cap = c->list_offset[i + 1] - c->list_offset[i];
+            const unsigned int prev = c->list_len(i);
+            const double entries = prev == 0xffffffffu ? (double)cap : std::min((double)prev * 1.25 + 4096.0, (double)cap);
+            const int k = plan.n++;
+            SplitJob& jb = plan.job[k];
+            jb.lv = c->levels[i];
+            jb.level = (int)i;
+            jb.cap = (unsigned)cap;
+            jb.root = c->scene.nodes;
+            jb.origin = c->d_origin.p + c->levels[i].probe_offset;
+            jb.dirq = c->d_dirq.p + 2 * (c->dir_offset[i] / 3);
+            jb.qinv = c->d_qinv.p + c->qinv_offset[i];
+            jb.list_a = c->d_list.p + c->list_offset[i];
+            jb.list_b = c->d_list2.p + c->list_offset[i];
+            jb.counts = c->d_ray_count.p;
+            plan.block_off[k + 1] = plan.block_off[k] + (unsigned)std::min(entries / (double)split_chunk() + 1.0, 1.0e6);
+            c->split_mask |= 1u << i;
+        }
+        if (plan.n) {
+            launch_split(plan, st);
+            c->launches++;
+        }
+    }
     return RC_OK;
 }
 
@@ -972,7 +1053,7 @@ rc_status rc_render_begin(rc_ctx* c, void* stream)
     CU_OK(c, record_event(c, c->ev[EV_START], st));
     c->frame_culled = c->cull_possible();
     if (c->frame_open && c->frame_culled)           // the last frame never reached its gather: its list lengths are still set
-        CU_OK(c, cudaMemsetAsync(c->d_ray_count.p, 0, RC_MAX_LEVELS * sizeof(unsigned int), st));
+        CU_OK(c, cudaMemsetAsync(c->d_ray_count.p, 0, 3 * RC_MAX_LEVELS * sizeof(unsigned int), st));
     c->frame_open = true;
     c->frame_id++;
     if (c->frame_id == 0) c->frame_id = 1;
@@ -1086,7 +1167,7 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     const bool culled = c->frame_culled && !c->march_persist && !compact && fused;
     int list_blocks = 0;   // 0 = the upper bound (every texel)
     if (culled && c->h_ray_count) {
-        const unsigned int prev = *(volatile unsigned int*)(c->h_ray_count + level);   // entries of the last list that arrived
+        const unsigned int prev = c->list_len(level);   // entries of the last list that arrived
         if (prev != 0xffffffffu) {
             const double threads = (double)prev * (level >= 1 ? 4.0 : 1.0) * 1.25;
             list_blocks = (int)std::min(threads / 128.0 + 64.0, 2.0e9);
@@ -1094,10 +1175,11 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     }
     const bool avg_in_kernel = my_avg && (fused || top) && !c->march_persist && !compact && (culled || march_avg_ystep(L.D, eff_map) != 0);
     const bool quad_kernel = culled && level >= 1 && !top && c->march_quad;
+    const bool split = culled && ((c->split_mask >> level) & 1u) != 0;      // this frame's k_split partitioned the level's list
     if (quad_kernel) {
         int qblocks = 0;
         if (c->h_ray_count) {
-            const unsigned int prev = *(volatile unsigned int*)(c->h_ray_count + level);
+            const unsigned int prev = c->list_len(level);
             if (prev != 0xffffffffu) qblocks = (int)std::min((double)prev * 1.25 / 64.0 + 64.0, 2.0e9);
         }
         launch_march_quad(c->scene, c->lights, L, sky, c->d_origin.p + L.probe_offset, c->d_dirq.p + 2 * (c->dir_offset[level] / 3), tex, up,
@@ -1114,7 +1196,9 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
                      (int)level < c->entry_levels() ? c->d_entry.p + 2 * (size_t)L.probe_offset : nullptr,
                      avg_in_kernel ? my_avg : nullptr, fused, c->march_map[level], c->march_occ, c->march_pdl != 0, compact,
                      culled ? list_blocks : (c->march_waves > 0 ? c->sm_count * c->march_occ * c->march_waves : 0),
-                     culled ? c->d_list.p + c->list_offset[level] : nullptr, c->d_ray_count.p + level, level >= 1 ? 1 : 0, up_const, st);
+                     culled ? (split ? c->d_list2.p : c->d_list.p) + c->list_offset[level] : nullptr,
+                     c->d_ray_count.p + (split ? 2 * RC_MAX_LEVELS : 0) + level, level >= 1 ? 1 : 0, up_const,
+                     split ? c->d_ray_count.p + RC_MAX_LEVELS + level : nullptr, (unsigned)(c->list_offset[level + 1] - c->list_offset[level]), st);
     c->launches++;
     if (!fused && !top) {
         launch_merge(L, *U, sky, c->d_origin.p + L.probe_offset, tex, up, c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset, st);
@@ -1156,6 +1240,7 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "copy_blocks" && value >= 0 && value <= 1024) c->copy_blocks = value;
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
     else if (k == "list_tiled" && value >= 0 && value <= 2) c->list_tiled = value;
+    else if (k == "list_split" && value >= 0 && value <= 2) c->list_split = value;
     else if (k == "need_fused" && value >= 0 && value <= 1) c->need_fused = value;
     else if (k == "graph" && value >= 0 && value <= 1) c->use_graph = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;
@@ -1564,7 +1649,7 @@ rc_status rc_rays_marched(rc_ctx* c, uint32_t* rays, uint32_t n)
         uint32_t v = 0xffffffffu;
         if (i < c->N && c->frame_culled) {
             if (i + 1 == c->N && c->top_fillable()) v = 0;
-            else v = c->h_ray_count[i] * (i >= 1 ? 4u : 1u);   // lists above level 0 hold 2x2 quads
+            else v = c->list_len(i) * (i >= 1 ? 4u : 1u);   // lists above level 0 hold 2x2 quads
         }
         rays[i] = v;
     }
