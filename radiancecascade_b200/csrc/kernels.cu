@@ -1058,9 +1058,12 @@ __device__ __forceinline__ bool entry_misses(const SplitJob& jb, float4 q0, floa
     return root_miss(q0, q1, q2, o, f3(a0.w, a1.x, a1.y), lv.t0, lv.t1);
 }
 
-// Block `blk` of `nblk` working on one level's list, kSplitBlock consecutive entries per step (one per thread), in chunks of
-// kSplitChunk consecutive entries per block.
-__device__ __forceinline__ void split_body(const SplitJob& jb, unsigned blk, unsigned nblk, unsigned* s_w, unsigned* s_base)
+// Block `blk` of `nblk` working on one level's list: chunks of kSplitChunk consecutive entries, kSplitBlock consecutive entries per
+// step (one per thread, coalesced), all steps classified before the chunk is appended with ONE atomicAdd per class — a block's
+// critical path holds one atomic round trip, not one per step, and the chunk lands in the new list as a whole and in order.
+constexpr int kSplitSteps = kSplitChunk / kSplitBlock;
+
+__device__ __forceinline__ void split_body(const SplitJob& jb, unsigned blk, unsigned nblk, unsigned* s_cnt, unsigned* s_base)
 {
     const unsigned n = jb.counts[jb.level];
     unsigned int* n_triv = jb.counts + RC_MAX_LEVELS + jb.level;      // bit 31: "this level was classified in this frame" (rc_api: adaptive choice)
@@ -1071,42 +1074,58 @@ __device__ __forceinline__ void split_body(const SplitJob& jb, unsigned blk, uns
     if (blk == 0 && threadIdx.x == 0) atomicOr(n_triv, 0x80000000u);
     const float4 q0 = __ldg(jb.root), q1 = __ldg(jb.root + 1), q2 = __ldg(jb.root + 2);
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    constexpr int kWarps = kSplitBlock / 32;
+    static_assert(kSplitSteps * kWarps == 64, "the chunk's (step, warp) cells are scanned by one warp, two per lane");
     for (size_t chunk = (size_t)blk * kSplitChunk; chunk < n; chunk += (size_t)nblk * kSplitChunk) {
-        for (size_t base = chunk; base < chunk + kSplitChunk && base < n; base += kSplitBlock) {      // (uniform over the block)
-            const size_t j = base + threadIdx.x;
-            const bool have = j < n;
-            uint32_t e = 0u;
-            bool miss = false;
-            if (have) {
-                e = __ldg(jb.list_a + j);
-                miss = entry_misses(jb, q0, q1, q2, quad, ld, DD, e);
-            }
-            // stable partition, block-aggregated: one atomicAdd per class; counts packed 16 : 16
-            const unsigned br = __ballot_sync(0xffffffffu, have && !miss), bt = __ballot_sync(0xffffffffu, have && miss);
-            if (lane == 0) s_w[wid] = (unsigned)__popc(br) | ((unsigned)__popc(bt) << 16);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned tot = 0;
-                for (int i = 0; i < kSplitBlock / 32; i++) { const unsigned t = s_w[i]; s_w[i] = tot; tot += t; }
-                s_base[0] = (tot & 0xffffu) ? atomicAdd(n_real, tot & 0xffffu) : 0u;
-                s_base[1] = (tot >> 16) ? (atomicAdd(n_triv, tot >> 16) & 0x7fffffffu) : 0u;
-            }
-            __syncthreads();
-            if (have) {
-                if (!miss) jb.list_b[s_base[0] + (s_w[wid] & 0xffffu) + (unsigned)__popc(br & lt)] = e;
-                else jb.list_b[jb.cap - 1u - (s_base[1] + (s_w[wid] >> 16) + (unsigned)__popc(bt & lt))] = e;
-            }
-            __syncthreads();      // s_w / s_base are reused by the next step
+        uint32_t e[kSplitSteps];
+        unsigned have = 0u, miss = 0u;
+#pragma unroll
+        for (int k = 0; k < kSplitSteps; k++) {
+            const size_t j = chunk + (size_t)k * kSplitBlock + threadIdx.x;
+            e[k] = 0u;
+            if (j < n) { e[k] = __ldg(jb.list_a + j); have |= 1u << k; }
         }
+#pragma unroll
+        for (int k = 0; k < kSplitSteps; k++)
+            if (((have >> k) & 1u) && entry_misses(jb, q0, q1, q2, quad, ld, DD, e[k])) miss |= 1u << k;
+        // stable partition of the chunk: (entering, certain miss) counts per (step, warp) cell packed 16 : 16, cells in list order
+#pragma unroll
+        for (int k = 0; k < kSplitSteps; k++) {
+            const unsigned br = __ballot_sync(0xffffffffu, ((have & ~miss) >> k) & 1u), bt = __ballot_sync(0xffffffffu, (miss >> k) & 1u);
+            if (lane == 0) s_cnt[k * kWarps + wid] = (unsigned)__popc(br) | ((unsigned)__popc(bt) << 16);
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+            unsigned incl = a + b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            s_cnt[2 * lane] = incl - (a + b);
+            s_cnt[2 * lane + 1] = incl - b;
+            if (lane == 31) {
+                s_base[0] = (incl & 0xffffu) ? atomicAdd(n_real, incl & 0xffffu) : 0u;
+                s_base[1] = (incl >> 16) ? (atomicAdd(n_triv, incl >> 16) & 0x7fffffffu) : 0u;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSplitSteps; k++) {
+            const bool r = ((have & ~miss) >> k) & 1u, t = (miss >> k) & 1u;
+            const unsigned br = __ballot_sync(0xffffffffu, r), bt = __ballot_sync(0xffffffffu, t);
+            const unsigned cell = s_cnt[k * kWarps + wid];
+            if (r) jb.list_b[s_base[0] + (cell & 0xffffu) + (unsigned)__popc(br & lt)] = e[k];
+            else if (t) jb.list_b[jb.cap - 1u - (s_base[1] + (cell >> 16) + (unsigned)__popc(bt & lt))] = e[k];
+        }
+        __syncthreads();      // s_cnt / s_base are reused by the next chunk
     }
 }
 
 __global__ void __launch_bounds__(kSplitBlock) k_split(SplitPlan plan)
 {
-    __shared__ unsigned s_w[kSplitBlock / 32], s_base[2];
+    __shared__ unsigned s_cnt[kSplitSteps * (kSplitBlock / 32)], s_base[2];
     int k = 0;
     while (k + 1 < plan.n && blockIdx.x >= plan.block_off[k + 1]) k++;
-    split_body(plan.job[k], blockIdx.x - plan.block_off[k], plan.block_off[k + 1] - plan.block_off[k], s_w, s_base);
+    split_body(plan.job[k], blockIdx.x - plan.block_off[k], plan.block_off[k + 1] - plan.block_off[k], s_cnt, s_base);
 }
 
 // far-field radiance of lower texel (dx, dy) from the merged upper level (S8).
