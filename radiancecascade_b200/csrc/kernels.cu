@@ -1339,6 +1339,166 @@ __global__ void __launch_bounds__(128, MINB) k_march(DScene s, DLights L, DLevel
     }
 }
 
+// ------------------------------------------------------------------ march with a block-local ray pool (culled levels >= 1)
+// ncu (r2s, level 3 of the 4K frame, split lists): two thirds of k_march's warp-instructions are traversal, executed with 12 of
+// 32 lanes — a warp marches 32 fixed rays and idles behind its longest one.  Here a block owns a pool of kPoolRays consecutive
+// rays (256 list quads) and works in two phases.  (A) Traversal: a lane that has finished its ray takes the next one of the
+// pool (one shared-memory atomicAdd per warp and refill; the warp refills when fewer than `thresh` lanes are busy, Aila &
+// Laine's "replace terminated rays") and leaves the closest hit — 16 bytes — in shared memory.  (B) After a barrier the block
+// walks the pool in list order exactly like k_march: four consecutive lanes per quad shade, merge, store and form the child
+// average.  Which lane traverses a ray cannot change its closest hit (min (t, triangle id) over the same candidate set,
+// rc_spec.h S5), so every texel is unchanged.
+constexpr int kPoolRays = 1024;
+
+template <bool FUSED, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_march_pool(DScene s, DLights L, DLevel lv, int UD, float3 sky, const float4* __restrict__ origin,
+                                                          const float4* __restrict__ dirq, uint2* __restrict__ texels,
+                                                          const float4* __restrict__ up_avg, const uint4* __restrict__ link_idx,
+                                                          const float4* __restrict__ link_w, const int4* __restrict__ entry,
+                                                          float4* __restrict__ avg_out, const uint32_t* __restrict__ list,
+                                                          const unsigned int* __restrict__ count, const unsigned int* __restrict__ count_triv,
+                                                          unsigned list_cap, int thresh)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    __shared__ float4 s_hit[kPoolRays];
+    __shared__ unsigned s_next;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int kDone = kDoneLinkC;
+    const unsigned n_real = __ldg(count), n_triv = count_triv ? (__ldg(count_triv) & 0x7fffffffu) : 0u;
+    const size_t real_rays = 4 * (size_t)n_real, total = 4 * ((size_t)n_real + n_triv);
+    const size_t DD = (size_t)lv.D * lv.D;
+    const int ld = 31 - __clz(lv.D);
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    for (size_t b0 = (size_t)blockIdx.x * kPoolRays; b0 < total; b0 += (size_t)gridDim.x * kPoolRays) {
+        const unsigned pool = real_rays > b0 ? (unsigned)(real_rays - b0 < (size_t)kPoolRays ? real_rays - b0 : (size_t)kPoolRays) : 0u;
+        if (threadIdx.x == 0) s_next = 0u;
+        __syncthreads();
+        if (pool) {
+            // ---- (A) traversal with refill
+            int ray = -1, cur = kDone, sp = 0;
+            int stack[48];
+            float3 o = f3(0.f, 0.f, 0.f), w = o, inv = o, noi = o;
+            Hit h; h.t = 0.f; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+            bool exhausted = false;
+            for (;;) {
+                const unsigned freem = __ballot_sync(FULL, ray < 0);
+                if (freem && !exhausted) {
+                    const int leader = __ffs((int)freem) - 1;
+                    const unsigned want = (unsigned)__popc(freem);
+                    unsigned base = 0u;
+                    if ((int)lane == leader) base = atomicAdd(&s_next, want);
+                    base = __shfl_sync(FULL, base, leader);
+                    if (ray < 0) {
+                        const unsigned r = base + (unsigned)__popc(freem & lt);
+                        if (r < pool) {
+                            const size_t g = b0 + r;
+                            const uint32_t e = __ldg(list + (g >> 2));
+                            const uint32_t q = e & (uint32_t)((DD >> 2) - 1), probe = e >> (2 * ld - 2);
+                            const uint32_t x = q & (uint32_t)((lv.D >> 1) - 1), y = q >> (ld - 1);
+                            const uint32_t d = ((2u * y + (((uint32_t)g >> 1) & 1u)) << ld) + 2u * x + ((uint32_t)g & 1u);
+                            const float4 og = __ldg(origin + probe);
+                            const float4 qa = __ldg(dirq + 2 * (size_t)d), qb = __ldg(dirq + 2 * (size_t)d + 1);
+                            o = xyz(og); w = xyz(qa); inv = f3(qa.w, qb.x, qb.y);
+                            noi = f3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+                            h.t = lv.t1; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+                            sp = 0; cur = 0; ray = (int)r;
+                            if (entry) {      // as trace_inv: start at the probe's entry frontier
+                                const int4 ea = __ldg(entry + 2 * (size_t)probe), eb = __ldg(entry + 2 * (size_t)probe + 1);
+                                if (eb.w != kDone) stack[sp++] = eb.w;
+                                if (eb.z != kDone) stack[sp++] = eb.z;
+                                if (eb.y != kDone) stack[sp++] = eb.y;
+                                if (eb.x != kDone) stack[sp++] = eb.x;
+                                if (ea.w != kDone) stack[sp++] = ea.w;
+                                if (ea.z != kDone) stack[sp++] = ea.z;
+                                if (ea.y != kDone) stack[sp++] = ea.y;
+                                cur = ea.x;
+                            }
+                            if (og.w == 0.0f) cur = kDone;      // (lists hold valid probes only; phase B writes the S7 texel of an invalid one)
+                        }
+                    }
+                    if (base + want >= pool) exhausted = true;
+                }
+                unsigned act = __ballot_sync(FULL, ray >= 0);
+                if (!act) break;
+                const int lim = exhausted ? 1 : thresh;
+                do {
+                    while (cur >= 0) {      // trace_inv's node step
+                        const float4* n = s.nodes + 4 * (size_t)cur;
+                        const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+                        float ax = fmaf(q0.x, inv.x, noi.x), bx = fmaf(q0.w, inv.x, noi.x);
+                        float ay = fmaf(q0.y, inv.y, noi.y), by = fmaf(q1.x, inv.y, noi.y);
+                        float az = fmaf(q0.z, inv.z, noi.z), bz = fmaf(q1.y, inv.z, noi.z);
+                        const float n0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), lv.t0));
+                        const float f0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+                        ax = fmaf(q1.z, inv.x, noi.x); bx = fmaf(q2.y, inv.x, noi.x);
+                        ay = fmaf(q1.w, inv.y, noi.y); by = fmaf(q2.z, inv.y, noi.y);
+                        az = fmaf(q2.x, inv.z, noi.z); bz = fmaf(q2.w, inv.z, noi.z);
+                        const float n1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), lv.t0));
+                        const float f1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));
+                        const bool hit0 = n0 <= f0, hit1 = n1 <= f1;
+                        const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+                        const bool first1 = hit1 && (!hit0 || n1 < n0);
+                        const int nearc = first1 ? c1 : c0, farc = first1 ? c0 : c1;
+                        if (hit0 && hit1) stack[sp++] = farc;
+                        if (hit0 || hit1) cur = nearc;
+                        else cur = sp ? stack[--sp] : kDone;
+                    }
+                    while (cur < 0 && cur != kDone) {
+                        const uint32_t leaf = (uint32_t)~cur;
+                        const uint32_t first = leaf >> 3, cnt = leaf & 7u;
+                        for (uint32_t i = 0; i < cnt; i++) tri_test(s.tri_geom + 3 * (size_t)(first + i), o, w, lv.t0, lv.t1, h);
+                        cur = sp ? stack[--sp] : kDone;
+                    }
+                    if (ray >= 0 && cur == kDone) {
+                        s_hit[ray] = make_float4(h.prim == 0xffffffffu ? -1.0f : h.t, h.u, h.v, __uint_as_float(h.prim));
+                        ray = -1;
+                    }
+                    act = __ballot_sync(FULL, ray >= 0);
+                } while (__popc(act) >= lim);
+            }
+        }
+        __syncthreads();
+        // ---- (B) shade / merge / store / child average, in list order (k_march's epilogue)
+#pragma unroll 1
+        for (int k = 0; k < kPoolRays / 128; k++) {
+            const unsigned r = (unsigned)k * 128u + threadIdx.x;
+            const size_t j = b0 + r;
+            if (b0 + (size_t)k * 128u >= total) break;      // (uniform over the block)
+            const bool in_range = j < total;
+            uint32_t probe = 0, d = 0;
+            bool certain_miss = false;
+            if (in_range) {
+                const size_t qi = j >> 2;
+                certain_miss = qi >= n_real;
+                const uint32_t e = __ldg(list + (certain_miss ? (size_t)list_cap - 1u - (qi - n_real) : qi));
+                const uint32_t q = e & (uint32_t)((DD >> 2) - 1);
+                const uint32_t x = q & (uint32_t)((lv.D >> 1) - 1), y = q >> (ld - 1);
+                probe = e >> (2 * ld - 2);
+                d = ((2u * y + (((uint32_t)j >> 1) & 1u)) << ld) + 2u * x + ((uint32_t)j & 1u);
+            }
+            uint2 t = pack_half4(0.f, 0.f, 0.f, 1.f);   // invalid probe (S7)
+            if (in_range) {
+                const float4 og = __ldg(origin + probe);
+                if (og.w != 0.0f) {
+                    const float4 qa = __ldg(dirq + 2 * (size_t)d);
+                    const float3 w = xyz(qa), o = xyz(og);
+                    Hit h; h.t = -1.0f; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu;
+                    if (!certain_miss) { const float4 hr = s_hit[r]; h.t = hr.x; h.u = hr.y; h.v = hr.z; h.prim = __float_as_uint(hr.w); }
+                    t = finalize_texel<FUSED>(s, L, lv, UD, 0, sky, probe, d, o, w, h, up_avg, link_idx, link_w);
+                }
+                texels[(size_t)probe * DD + d] = t;
+            }
+            if (avg_out) {
+                const int dx = (int)(d & (uint32_t)(lv.D - 1)), dy = (int)(d >> ld);
+                float4 avg;
+                if (child_avg_shfl(t, 2, dx, dy, avg) && in_range)
+                    avg_out[(size_t)probe * (DD >> 2) + (size_t)(dy >> 1) * (lv.D >> 1) + (dx >> 1)] = avg;
+            }
+        }
+        __syncthreads();      // s_hit / s_next are reused by the next pool
+    }
+}
+
 // ------------------------------------------------------------------ march, one 2x2 quad of texels per thread (culled levels >= 1)
 // The ray lists of levels >= 1 hold quads (the four children of one direction of the level below).  k_march gives each
 // ray its own thread, so every ray pays the list decode, the probe / link fetches, the merge set-up and three shuffles for
@@ -2505,6 +2665,33 @@ void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, floa
     } else {
         cudaLaunchKernelEx(&cfg, k_march_quad<false, 12>, s, L, lv, UD, sky, origin, dirq, texels, up_avg, link_idx, link_w, avg_out, list, count);
     }
+}
+
+void launch_march_pool(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,
+                       const float4* up_avg, const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int occ,
+                       bool pdl, int max_blocks, const uint32_t* list, const unsigned int* count, const unsigned int* count_triv, unsigned list_cap,
+                       int thresh, bool up_const, cudaStream_t st)
+{
+    const int UD = up_const ? -1 : 0;
+    cudaLaunchConfig_t cfg{};
+    const size_t n = (size_t)lv.sw * lv.sh * lv.D * lv.D;
+    size_t blocks = (n + kPoolRays - 1) / kPoolRays;
+    if (max_blocks > 0 && blocks > (size_t)max_blocks) blocks = (size_t)max_blocks;
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(128);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && fused) ? 1 : 0;
+#define RC_LAUNCH_POOL(F, M) cudaLaunchKernelEx(&cfg, k_march_pool<F, M>, s, L, lv, UD, sky, origin, dirq, texels, up_avg, link_idx, link_w, entry, \
+                                                avg_out, list, count, count_triv, list_cap, thresh)
+    if (!fused) RC_LAUNCH_POOL(false, 10);
+    else if (occ >= 12) RC_LAUNCH_POOL(true, 12);
+    else if (occ >= 10) RC_LAUNCH_POOL(true, 10);
+    else RC_LAUNCH_POOL(true, 8);
+#undef RC_LAUNCH_POOL
 }
 
 void launch_need(const DLevel& lv, int Dr, int has_upper, int up_words, const float4* origin, const uint4* link_idx,

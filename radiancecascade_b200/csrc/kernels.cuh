@@ -91,6 +91,11 @@ void launch_march(const DScene& s, const DLights& L, const DLevel& lv, const DLe
                   const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int map, int occ,
                   bool pdl, bool compact, int max_blocks, const uint32_t* list, const unsigned int* count, int quad, bool up_const,
                   const unsigned int* count_triv, unsigned list_cap, cudaStream_t st);
+// culled levels >= 1, block-local ray pool with refill of finished lanes (k_march_pool); max_blocks: pools of 1024 rays
+void launch_march_pool(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,
+                       const float4* up_avg, const uint4* link_idx, const float4* link_w, const int4* entry, float4* avg_out, bool fused, int occ,
+                       bool pdl, int max_blocks, const uint32_t* list, const unsigned int* count, const unsigned int* count_triv, unsigned list_cap,
+                       int thresh, bool up_const, cudaStream_t st);
 // culled levels >= 1, one 2x2 quad of texels per thread (k_march_quad): list = the level's quad list, count = its length;
 // occ = resident 64-thread blocks per SM the register allocation must allow (8 -> 128 regs, 12 -> 80, 16 -> 64)
 void launch_march_quad(const DScene& s, const DLights& L, const DLevel& lv, float3 sky, const float4* origin, const float4* dirq, uint2* texels,

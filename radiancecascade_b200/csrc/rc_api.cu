@@ -134,6 +134,7 @@ struct rc_ctx {
     // below 15 %); every level >= 1 is measured in the first frame and in every 64th.  Any choice gives the same texels.
     int list_split = 1;
     bool split_on[RC_MAX_LEVELS] = {};
+    int march_pool = 0, march_pool_thresh = 20;      // k_march_pool (block-local ray pool with refill) for the culled levels >= 1
     uint32_t split_mask = 0;                         // levels whose split list (d_list2) the frame being enqueued marches
     DevBuf<uint32_t> d_list2;
     unsigned int list_len(uint32_t i) const          // entries of level i's last list that arrived (0xffffffff: none yet)
@@ -844,6 +845,8 @@ rc_status rc_create(const rc_config* cfg, rc_ctx** out)
         if (const char* e = getenv("RC_NEED_PDL")) c->need_pdl = atoi(e) != 0;
         if (const char* e = getenv("RC_COPY_BLOCKS")) c->copy_blocks = atoi(e) < 0 ? 0 : (atoi(e) > 1024 ? 1024 : atoi(e));
         if (const char* e = getenv("RC_NEED_FUSED")) c->need_fused = atoi(e) != 0;
+        if (const char* e = getenv("RC_MARCH_POOL")) c->march_pool = atoi(e) != 0;
+        if (const char* e = getenv("RC_MARCH_POOL_THRESH")) c->march_pool_thresh = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
         if (const char* e = getenv("RC_LIST_SPLIT")) c->list_split = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
         if (const char* e = getenv("RC_LIST_TILED")) c->list_tiled = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
         if (const char* e = getenv("RC_LIST_DIRMAJOR")) c->list_dir_major = (int)strtol(e, nullptr, 0);
@@ -1176,7 +1179,20 @@ rc_status rc_render_level(rc_ctx* c, uint32_t level, void* stream)
     const bool avg_in_kernel = my_avg && (fused || top) && !c->march_persist && !compact && (culled || march_avg_ystep(L.D, eff_map) != 0);
     const bool quad_kernel = culled && level >= 1 && !top && c->march_quad;
     const bool split = culled && ((c->split_mask >> level) & 1u) != 0;      // this frame's k_split partitioned the level's list
-    if (quad_kernel) {
+    const bool pool_kernel = culled && level >= 1 && !top && c->march_pool && !quad_kernel;
+    if (pool_kernel) {
+        int pblocks = 0;
+        if (c->h_ray_count) {
+            const unsigned int prev = c->list_len(level);
+            if (prev != 0xffffffffu) pblocks = (int)std::min((double)prev * 4.0 * 1.25 / 1024.0 + 16.0, 2.0e9);
+        }
+        launch_march_pool(c->scene, c->lights, L, sky, c->d_origin.p + L.probe_offset, c->d_dirq.p + 2 * (c->dir_offset[level] / 3), tex, up,
+                          c->d_link_idx.p + L.probe_offset, c->d_link_w.p + L.probe_offset,
+                          (int)level < c->entry_levels() ? c->d_entry.p + 2 * (size_t)L.probe_offset : nullptr, avg_in_kernel ? my_avg : nullptr,
+                          fused, c->march_occ, c->march_pdl != 0, pblocks, (split ? c->d_list2.p : c->d_list.p) + c->list_offset[level],
+                          c->d_ray_count.p + (split ? 2 * RC_MAX_LEVELS : 0) + level, split ? c->d_ray_count.p + RC_MAX_LEVELS + level : nullptr,
+                          (unsigned)(c->list_offset[level + 1] - c->list_offset[level]), c->march_pool_thresh, up_const, st);
+    } else if (quad_kernel) {
         int qblocks = 0;
         if (c->h_ray_count) {
             const unsigned int prev = c->list_len(level);
@@ -1241,6 +1257,8 @@ rc_status rc_set_tuning(rc_ctx* c, const char* key, int value)
     else if (k == "list_dir_major" && value >= 0) c->list_dir_major = value;
     else if (k == "list_tiled" && value >= 0 && value <= 2) c->list_tiled = value;
     else if (k == "list_split" && value >= 0 && value <= 2) c->list_split = value;
+    else if (k == "march_pool" && value >= 0 && value <= 1) c->march_pool = value;
+    else if (k == "march_pool_thresh" && value >= 1 && value <= 32) c->march_pool_thresh = value;
     else if (k == "need_fused" && value >= 0 && value <= 1) c->need_fused = value;
     else if (k == "graph" && value >= 0 && value <= 1) c->use_graph = value;
     else if (k == "march_block" && (value == 64 || value == 128 || value == 256 || value == 512)) c->march_block = value;

@@ -546,7 +546,8 @@ def test_experimental_schedules_are_bit_identical(name, W, H):
     st, _, _ = frame_setup(name, W, H)
     res = []
     for knobs in ({}, {"march_quad": 1}, {"march_quad": 1, "march_quad_occ": 8}, {"need_fused": 1}, {"need_fused": 1, "list_tiled": 2},
-                  {"need_fused": 1, "march_quad": 1, "gbuffer_binned": 1}):
+                  {"need_fused": 1, "march_quad": 1, "gbuffer_binned": 1}, {"march_pool": 1}, {"march_pool": 1, "march_pool_thresh": 28, "list_split": 0},
+                  {"march_pool": 1, "march_pool_thresh": 8, "list_split": 2}):
         r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name))
         for k, v in knobs.items():
             r.set_tuning(k, v)
