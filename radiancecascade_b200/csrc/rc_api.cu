@@ -662,7 +662,8 @@ rc_status load_scene(rc_ctx* c)
     const uint32_t nt = h.info.num_triangles;
     const float diag = h.diag;
     Bvh bvh;
-    int max_leaf = 4;
+    int max_leaf = 3;      // A/B on the B200 (tools/ab_bvh.sh, frame ms for leaf 4 / 3 / 2): living_room 4K 1.206 / 1.182 / 1.185, cube 512 0.176 / 0.172 / 0.172,
+                           // sonic 8K 4.70 / 4.69 / 4.75, teapot 1080p 0.529 / 0.538 / 0.526; SAH leaf termination (RC_BVH_NODE_COST) no better
     float node_cost = 0.f;
     if (const char* e = getenv("RC_BVH_LEAF")) max_leaf = atoi(e);
     if (const char* e = getenv("RC_BVH_NODE_COST")) node_cost = (float)atof(e);
