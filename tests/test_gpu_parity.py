@@ -602,6 +602,30 @@ def test_split_ray_lists_change_no_texel(name, W, H):
 
 
 @pytest.mark.culled
+@pytest.mark.parametrize("cfg", [dict(probe_spacing0=2, dir_res0=2, num_levels=5), dict(probe_spacing0=4, dir_res0=8, num_levels=4),
+                                 dict(probe_spacing0=8, dir_res0=4, num_levels=3, sky=(0.2, 0.3, 0.5)),
+                                 dict(tile=(64, 40, 200, 120))])
+def test_split_ray_lists_other_cascade_shapes(cfg):
+    """k_split on cascade shapes other than the default (direction resolutions 2..64 per level, a top level that is marched, a tile
+    context): irradiance, ray counts and lists with every level classified equal the unsplit frame's."""
+    name, W, H = "living_room", 400, 232
+    st, _, _ = frame_setup(name, W, H)
+    res = []
+    for split in (2, 0):
+        r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name), rc.CascadeConfig(**cfg))
+        r.set_tuning("list_split", split)
+        r.update(st)
+        for _ in range(2):
+            r.render()
+        n = len(r.levels())
+        res.append((r.read_target(_ffi.RC_TARGET_IRRADIANCE).view(np.uint16).copy(), r.rays_marched(), [np.sort(r.ray_list(i)) for i in range(n)]))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1] and sum(x for x in res[0][1] if x) > 0
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.culled
 @pytest.mark.parametrize("name,W,H", [("teapot", 480, 270), ("living_room", 320, 180), ("sonic", 200, 260)])
 def test_floating_probes_match_oracle_and_tiles(name, W, H):
     """RC_CFG_FLOATING_PROBES (rc_spec.h S6): probes with an empty anchor float to a finer-level anchor with geometry.  The
