@@ -602,11 +602,11 @@ def test_split_ray_lists_change_no_texel(name, W, H):
 
 
 @pytest.mark.culled
-@pytest.mark.parametrize("cfg", [dict(probe_spacing0=2, dir_res0=2, num_levels=5), dict(probe_spacing0=4, dir_res0=8, num_levels=4),
+@pytest.mark.parametrize("cfg", [dict(probe_spacing0=2, dir_res0=2, num_levels=5), dict(probe_spacing0=4, dir_res0=4, num_levels=4),
                                  dict(probe_spacing0=8, dir_res0=4, num_levels=3, sky=(0.2, 0.3, 0.5)),
                                  dict(tile=(64, 40, 200, 120))])
 def test_split_ray_lists_other_cascade_shapes(cfg):
-    """k_split on cascade shapes other than the default (direction resolutions 2..64 per level, a top level that is marched, a tile
+    """k_split on cascade shapes other than the default (direction resolutions 2..32 per level, a top level that is marched, a tile
     context): irradiance, ray counts and lists with every level classified equal the unsplit frame's."""
     name, W, H = "living_room", 400, 232
     st, _, _ = frame_setup(name, W, H)
