@@ -195,7 +195,11 @@ rc_status rc_level_times(rc_ctx* ctx, float* ms, uint32_t n);
  * "cull" 0/1 (direction culling), "graph" 0/1 (submit the frame as one CUDA graph), "gather_tiles" 0 auto / 1 the
  * one-tile-per-block gather / n tiles per block with prefetch, "list_dir_major" bit i: level i's ray list is ordered
  * direction-major, "need_pdl" 0/1 (programmatic dependent launch along the k_need chain), "copy_blocks" 0 = the copy
- * engine / n = rc_read_target_async stores the frame into page-locked memory from n resident blocks. */
+ * engine / n = rc_read_target_async stores the frame into page-locked memory from n resident blocks,
+ * "list_split" 0 off / 1 adaptive (default) / 2 every level: k_split sorts the list entries whose rays all miss the BVH
+ * root's two child boxes to the back of the level's list and k_march skips their traversal (bit-identical texels),
+ * "march_pool" 0/1 + "march_pool_thresh" 1..32 (block-local ray pool with refill of finished lanes; measured slower),
+ * "gather_mma", "list_tiled", "need_fused", "march_quad", "gbuffer_binned", "peer_stores", "peer_broadcast": DESIGN.md §4-5. */
 rc_status rc_set_tuning(rc_ctx* ctx, const char* key, int value);
 /* Number of kernels rc_render launches per frame. */
 rc_status rc_launch_count(rc_ctx* ctx, uint32_t* launches);
