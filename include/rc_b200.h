@@ -213,6 +213,12 @@ rc_status rc_rays_marched(rc_ctx* ctx, uint32_t* rays, uint32_t n);
  * linear probe index; level 0: R = D_0, r = texel (dy * D_0 + dx); level i >= 1: R = D_{i-1}, r = the 2x2 quad of
  * level-i texels below direction r of level i-1.  *count = entries of the list; at most bytes / 4 are copied. */
 rc_status rc_get_ray_list(rc_ctx* ctx, uint32_t level, uint32_t* entries, size_t bytes, uint32_t* count);
+/* Debug / parity entry for the split ray lists (rc_set_tuning "list_split"): the list of `level` as k_split partitioned it
+ * in the last frame — first the *n_enter entries whose rays are traversed, then the *n_miss entries classified as certain
+ * misses (every ray of the entry fails the slab test of the BVH root's two child boxes over the level's interval, so
+ * none of them can hit a triangle).  Same entry format as rc_get_ray_list; together the two parts are that list.
+ * RC_ERR_STATE when the last frame did not classify the level.  At most bytes / 4 entries are copied. */
+rc_status rc_get_split_list(rc_ctx* ctx, uint32_t level, uint32_t* entries, size_t bytes, uint32_t* n_enter, uint32_t* n_miss);
 
 /* ---- Tiled multi-GPU: final-image exchange through NVLink peer memory (one context per GPU, one process each,
  * all on one node).  Replaces the all-gather of the finished tiles: k_gather stores every pixel of this rank's tile

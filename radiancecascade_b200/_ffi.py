@@ -96,6 +96,7 @@ SYMBOLS = {
     "rc_launch_count": (C.c_int32, [_P, C.POINTER(C.c_uint32)]),
     "rc_rays_marched": (C.c_int32, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "rc_get_ray_list": (C.c_int32, [_P, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "rc_get_split_list": (C.c_int32, [_P, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rc_peer_export": (C.c_int32, [_P, C.c_void_p, C.c_size_t]),
     "rc_peer_attach": (C.c_int32, [_P, C.c_void_p, C.c_uint32, C.c_uint32]),
     "rc_peer_wait": (C.c_int32, [_P, C.c_void_p]),

@@ -1691,6 +1691,27 @@ rc_status rc_get_ray_list(rc_ctx* c, uint32_t level, uint32_t* entries, size_t b
     return RC_OK;
 }
 
+rc_status rc_get_split_list(rc_ctx* c, uint32_t level, uint32_t* entries, size_t bytes, uint32_t* n_enter, uint32_t* n_miss)
+{
+    if (!c || !n_enter || !n_miss || level >= c->N) return RC_ERR_INVALID_ARG;
+    if (!c->ev_recorded || !c->frame_culled) { c->error = "rc_get_split_list needs a rendered frame with direction culling on"; return RC_ERR_STATE; }
+    cudaSetDevice(c->device);
+    CU_OK(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
+    const unsigned int len = c->h_ray_count[level], triv = c->h_ray_count[RC_MAX_LEVELS + level];
+    if (!((c->split_mask >> level) & 1u) || len == 0xffffffffu || !(triv & 0x80000000u)) {
+        c->error = "rc_get_split_list: the last frame did not classify this level (rc_set_tuning list_split)";
+        return RC_ERR_STATE;
+    }
+    const uint32_t nm = triv & 0x7fffffffu, ne = len - nm;
+    *n_enter = ne; *n_miss = nm;
+    const size_t cap = c->list_offset[level + 1] - c->list_offset[level], room = bytes / 4;
+    const size_t copy_a = std::min<size_t>(ne, room), copy_b = std::min<size_t>(nm, room - copy_a);
+    const uint32_t* lb = c->d_list2.p + c->list_offset[level];
+    if (entries && copy_a) CU_OK(c, cudaMemcpy(entries, lb, copy_a * 4, cudaMemcpyDeviceToHost));
+    if (entries && copy_b) CU_OK(c, cudaMemcpy(entries + copy_a, lb + (cap - copy_b), copy_b * 4, cudaMemcpyDeviceToHost));   // (appended from the back)
+    return RC_OK;
+}
+
 rc_status rc_get_levels(rc_ctx* c, rc_level_info* out, uint32_t max_levels, uint32_t* num_levels)
 {
     if (!c) return RC_ERR_INVALID_ARG;

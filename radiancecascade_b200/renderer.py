@@ -358,6 +358,16 @@ class DefaultRenderer:
             self._check(self._lib.rc_get_ray_list(self._h, level, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(n)))
         return out
 
+    def split_list(self, level: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(entries that are traversed, entries classified as certain misses) of the level's list in the last frame
+        (include/rc_b200.h rc_get_split_list; RcError RC_ERR_STATE when the frame did not classify the level)."""
+        ne, nm = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.rc_get_split_list(self._h, level, None, 0, C.byref(ne), C.byref(nm)))
+        out = np.zeros(ne.value + nm.value, dtype=np.uint32)
+        if out.size:
+            self._check(self._lib.rc_get_split_list(self._h, level, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(ne), C.byref(nm)))
+        return out[:ne.value], out[ne.value:]
+
     def launch_count(self) -> int:
         n = C.c_uint32()
         self._check(self._lib.rc_launch_count(self._h, C.byref(n)))

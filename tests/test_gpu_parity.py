@@ -602,6 +602,55 @@ def test_split_ray_lists_change_no_texel(name, W, H):
 
 
 @pytest.mark.culled
+@pytest.mark.parametrize("name,W,H", [("living_room", 480, 270), ("test_room", 333, 205), ("teapot", 384, 216)])
+def test_split_lists_certain_misses_are_misses_in_the_oracle(name, W, H):
+    """k_split against the oracle: the two parts of a split list are a partition of the level's ray list, and every ray of an entry
+    classified as a certain miss has no hit in the oracle's brute-force closest-hit search (rc_spec.h S5) over the level's
+    interval — origins, directions and intervals taken from the oracle's own frame."""
+    st, cam, larr = frame_setup(name, W, H, lights="room" if name == "test_room" else "bench")
+    r = rc.DefaultRenderer.new(0, (W, H), st, rc.scenes.scene_path(name))
+    r.set_tuning("list_split", 2)
+    r.update(st)
+    r.render()
+    osc = oracle_scene(name)
+    out = osc.render(osc.params(W, H, store_half=True), cam, larr)
+    lv = out["levels"]
+    rng = np.random.default_rng(7)
+    n_miss_total = 0
+    for i in range(5):
+        enter, miss = r.split_list(i)
+        full = np.sort(r.ray_list(i))
+        assert np.array_equal(np.sort(np.concatenate([enter, miss])), full)
+        n_miss_total += len(miss)
+        if not len(miss):
+            continue
+        e = miss.astype(np.int64)
+        if len(e) > 6000:
+            e = e[rng.choice(len(e), 6000, replace=False)]
+        D = lv[i].D
+        dirs = out["dirs"][i].astype(np.float32)
+        if i == 0:
+            probe, d = np.divmod(e, D * D)
+        else:
+            Dr = D // 2
+            probe, q = np.divmod(e, Dr * Dr)
+            qy, qx = np.divmod(q, Dr)
+            d = np.stack([(2 * qy + j) * D + 2 * qx + k for j in (0, 1) for k in (0, 1)], 1).reshape(-1)
+            probe = np.repeat(probe, 4)
+        og = out["origins"][i][probe].astype(np.float32)
+        assert np.all(og[:, 3] != 0)
+        rays = np.concatenate([og[:, :3], np.full((len(d), 1), lv[i].t0, np.float32), dirs[d], np.full((len(d), 1), lv[i].t1, np.float32)], 1)
+        hits = osc.trace(rays, brute=True)
+        assert np.all(hits[:, 3].view(np.uint32) == 0xFFFFFFFF), f"level {i}: a classified miss hits a triangle"
+    if name != "teapot":
+        assert n_miss_total > 0      # the open views: something is classified
+    with pytest.raises(rc.RcError):
+        r.set_tuning("list_split", 0)
+        r.render()
+        r.split_list(1)
+
+
+@pytest.mark.culled
 @pytest.mark.parametrize("cfg", [dict(probe_spacing0=2, dir_res0=2, num_levels=5), dict(probe_spacing0=4, dir_res0=4, num_levels=4),
                                  dict(probe_spacing0=8, dir_res0=4, num_levels=3, sky=(0.2, 0.3, 0.5)),
                                  dict(tile=(64, 40, 200, 120))])
