@@ -1048,9 +1048,10 @@ __device__ __forceinline__ bool entry_misses(const SplitJob& jb, float4 q0, floa
         const uint32_t qd = e & ((DD >> 2) - 1u), probe = e >> (2 * ld - 2);
         const float3 o = xyz(__ldg(jb.origin + probe));
         const float4 a = __ldg(jb.qinv + 3 * (size_t)qd), b = __ldg(jb.qinv + 3 * (size_t)qd + 1), c = __ldg(jb.qinv + 3 * (size_t)qd + 2);
-        const bool m0 = root_miss(q0, q1, q2, o, f3(a.x, a.y, a.z), lv.t0, lv.t1), m1 = root_miss(q0, q1, q2, o, f3(a.w, b.x, b.y), lv.t0, lv.t1);
-        const bool m2 = root_miss(q0, q1, q2, o, f3(b.z, b.w, c.x), lv.t0, lv.t1), m3 = root_miss(q0, q1, q2, o, f3(c.y, c.z, c.w), lv.t0, lv.t1);
-        return m0 & m1 & m2 & m3;
+        // one child that enters the tree settles the quad: neighbouring entries mostly agree, so whole warps leave after the first test
+        if (!root_miss(q0, q1, q2, o, f3(a.x, a.y, a.z), lv.t0, lv.t1)) return false;
+        if (!root_miss(q0, q1, q2, o, f3(c.y, c.z, c.w), lv.t0, lv.t1)) return false;      // (the diagonally opposite child next)
+        return root_miss(q0, q1, q2, o, f3(a.w, b.x, b.y), lv.t0, lv.t1) & root_miss(q0, q1, q2, o, f3(b.z, b.w, c.x), lv.t0, lv.t1);
     }
     const uint32_t probe = e >> (2 * ld), d = e & (DD - 1u);
     const float3 o = xyz(__ldg(jb.origin + probe));
