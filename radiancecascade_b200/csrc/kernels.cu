@@ -2240,7 +2240,15 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
         const int ly0 = clampy(by) - pr_lo, ly1 = clampy(by + 1) - pr_lo;
         const float dep = dep_n; const uint32_t nrm = nrm_n; const int y = y_n;
         if (s + 1 < nsteps) gload(s + 1, dep_n, nrm_n, y_n);
-        mbar_wait(&sm.bar[b], (unsigned)((s >> 1) & 1));
+        // A warp whose 32 pixels all lack geometry (31-41 % of the pixels of living_room's orbit, ~78 % of the teapot's and of sonic's,
+        // nearly all of them in such warps) has nothing to compute: S9 gives (0,0,0,0), which is also what the contraction would
+        // produce from a_k = 0.  It leaves its 8 x 4 pixels of the output tile empty and waits for the others.
+        const bool warp_has_geometry = __any_sync(0xffffffffu, dep >= 0.0f);
+        // (warp 0 always waits: its thread 0 re-arms this barrier two steps later and must have seen this phase complete)
+        if (warp == 0 || warp_has_geometry) mbar_wait(&sm.bar[b], (unsigned)((s >> 1) & 1));
+        if (!warp_has_geometry) {
+            sm.outt[(4 * wrow + (lane >> 3)) * 32 + 8 * (warp & 3) + (lane & 7)] = make_uint2(0u, 0u);
+        } else {
         const uint4* s_tex = sm.tex[b];
         const float4* s_org = sm.org[b];
 
@@ -2340,6 +2348,7 @@ __global__ void __launch_bounds__(256) k_gather_mma(DCamera cam, DLevel l0, Tile
                 }
             }
         }
+        }      // warp_has_geometry
         __syncthreads();
         // ---- phase 4: the finished 32 x 8 tile leaves the block as 16-byte vectors (two pixels), row segments contiguous:
         // full sectors for the local store and for the NVLink stores of the fused final-image exchange (4-byte stores from
