@@ -152,9 +152,16 @@ struct rc_ctx {
         if (t & 0x80000000u) {
             const double share = a ? (double)(t & 0x7fffffffu) / (double)a : 0.0;
             if (share >= 0.25) split_on[i] = true; else if (share < 0.15) split_on[i] = false;
+            split_triv[i] = t & 0x7fffffffu;
         }
-        return split_on[i] || (frame_id & 63u) == 1u;
+        return split_on[i] || split_measure_frame();
     }
+    bool split_measure_frame() const { return (frame_id & 63u) == 1u; }
+    // k_split is one more launch in the latency-bound chain before the march (~8 us however short the lists are) and a certain miss
+    // saves the march ~70 ns per thousand entries... i.e. ~7 us per 100 k: below that the classification costs more than it saves
+    // (teapot 1080p: only level 4 qualifies, 82 k certain misses, frame +0.8 % with the split)
+    static constexpr unsigned kSplitMinMisses = 120000u;
+    unsigned int split_triv[RC_MAX_LEVELS] = {};
     std::vector<size_t> need_offset, list_offset;   // words / entries before level i
     std::vector<int> need_res;                      // Dr_i: D_0 for levels 0 and 1, D_{i-1} above
     int cull = 1;                                   // rc_set_tuning("cull", 0) marches every texel
@@ -985,8 +992,17 @@ static rc_status enqueue_need_chain(rc_ctx* c, cudaStream_t st, int pass)
         // list lengths that arrived (grid-stride inside a level's blocks; the whole capacity while nothing has arrived)
         SplitPlan plan{};
         c->split_mask = 0;
+        bool chosen[RC_MAX_LEVELS] = {};
+        bool measuring = c->list_split >= 2 || c->split_measure_frame();
+        unsigned long long expected_misses = 0;
         for (uint32_t i = 0; i < n_lists; i++) {
-            if (!c->split_level(i)) continue;
+            chosen[i] = c->split_level(i);
+            if (chosen[i] && c->h_ray_count[i] == 0xffffffffu) measuring = true;      // nothing measured yet
+            if (chosen[i]) expected_misses += c->split_triv[i];
+        }
+        const bool worth_it = measuring || expected_misses >= rc_ctx::kSplitMinMisses;
+        for (uint32_t i = 0; i < n_lists; i++) {
+            if (!chosen[i] || !worth_it) continue;
             const size_t cap = c->list_offset[i + 1] - c->list_offset[i];
             const unsigned int prev = c->list_len(i);
             const double entries = prev == 0xffffffffu ? (double)cap : std::min((double)prev * 1.25 + 4096.0, (double)cap);
