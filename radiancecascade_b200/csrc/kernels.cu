@@ -5,17 +5,22 @@
 //   k_probes     probe placement for all cascade levels (+ level-0 request masks)              (S6)
 //   k_link_entry per-probe upper-probe slots and bilateral weights (S1, S8) + optional per-probe BVH entry frontiers
 //   k_need       direction culling: request masks pushed up the cascade, one ray list per level
+//   k_split      split ray lists: entries whose rays all miss the BVH root's two child boxes go to the back of a copy
+//                of the level's list; k_march skips their traversal
 //   k_march      per-level interval ray march fused with the merge from level i+1 and with the child
 //                averages the level below will read (S7, S8); list-driven in culled frames
-//   k_merge / k_child_avg / k_fill_top / k_march_all / k_march_persist / k_march_compact   A/B variants and the
-//                every-texel path (rc_set_tuning)
-//   k_gather     final irradiance gather (+ peer-memory stores of the tile in tiled multi-GPU mode)   (S9)
+//   k_merge / k_child_avg / k_fill_top / k_march_all / k_march_persist / k_march_compact / k_march_quad / k_march_pool /
+//   k_need_chain / k_bin + k_gbuffer_binned   A/B variants, measured-and-rejected schedules and the every-texel path
+//                (rc_set_tuning; all bit-identical to the default)
+//   k_gather_mma final irradiance gather on mma.sync with TMA-staged probes (+ peer-memory stores of the tile in tiled
+//                multi-GPU mode) (S9);  k_gather / k_gather_pipe: the scalar forms in S9's exact summation order
 //   k_peer_*     flag handshake of the peer-memory frame exchange
 //
 // Data layout (all in HBM, sized at rc_create): cascade levels are probe-major RGBA16F texels (8 B): one warp
 // marches directions of ONE probe (shared origin -> coherent BVH traversal); the merge reads, per lower texel,
-// 4 upper probes x one 16-byte child average.  None of these stages is a dense contraction, so tensor cores /
-// TMEM are not used; the BVH + triangles (< 4 MB) live in L2 (126 MB) and are read through the read-only path.
+// 4 upper probes x one 16-byte child average.  The one dense contraction of the path is the gather's 16x16x8 product
+// per 4x4-pixel cell (mma.sync; far too small for tcgen05 / TMEM); the BVH + triangles (< 4 MB) live in L2 (126 MB)
+// and are read through the read-only path.
 #include "kernels.cuh"
 
 namespace rc {
