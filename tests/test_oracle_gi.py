@@ -246,3 +246,44 @@ def test_floating_probes_leave_no_lower_probe_without_an_upper_probe():
             has = uvalid[y0, x0] | uvalid[y0, x1] | uvalid[y1, x0] | uvalid[y1, x1]
             assert np.all(has), (i, int((~has).sum()))
     assert floated > 20
+
+
+@pytest.mark.parametrize("name", ["living_room", "test_room"])
+def test_rays_that_miss_the_padded_scene_box_hit_nothing(name):
+    """The principle behind the product's split ray lists (k_split), checked on CPU with the oracle alone: a cascade
+    ray whose float32 slab test against the scene's bounding box — padded by 1e-4 of its diagonal like the product's BVH boxes,
+    clipped to the level's interval [t0, t1) — fails has no hit in the brute-force closest-hit search (rc_spec.h S5).  In the
+    orbit's open views that is a large share of the rays of every level (the reason the split pays)."""
+    W, H = 320, 180
+    osc = go.OracleScene(rc.scenes.scene_path(name))
+    pos, tgt, zn, zf = rc.scenes.orbit_camera(osc.bbox_min, osc.bbox_max, 5)
+    import math
+    cam = ri.uniform_camera_look_at(pos, tgt, np.float32(math.radians(45.0)), np.float32(W) / np.float32(H), zn, zf)
+    out = osc.render(osc.params(W, H), cam, np.array([[0, 0, 0, 1]], np.float32))
+    f32 = np.float32
+    lo, hi = osc.bbox_min.astype(f32), osc.bbox_max.astype(f32)
+    pad = f32(1e-4) * f32(np.linalg.norm((hi - lo).astype(np.float64)))
+    lo, hi = lo - pad, hi + pad
+    rng = np.random.default_rng(3)
+    shares = []
+    for i, lv in enumerate(out["levels"][:5]):
+        og = out["origins"][i]
+        probes = np.nonzero(og[:, 3] != 0)[0]
+        dirs = out["dirs"][i].astype(f32)
+        n = 4000
+        pi = probes[rng.integers(0, len(probes), n)]
+        di = rng.integers(0, len(dirs), n)
+        o, d = og[pi, :3].astype(f32), dirs[di]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = (f32(1.0) / np.where(np.abs(d) > f32(1e-20), d, np.copysign(f32(1e-20), d))).astype(f32)
+            ta, tb = ((lo - o) * inv).astype(f32), ((hi - o) * inv).astype(f32)
+        tn = np.maximum(np.minimum(ta, tb).max(1), f32(lv.t0))
+        tf = np.minimum(np.maximum(ta, tb).min(1), f32(lv.t1))
+        miss = ~(tn <= tf)
+        shares.append(float(miss.mean()))
+        if not miss.any():
+            continue
+        rays = np.concatenate([o[miss], np.full((int(miss.sum()), 1), lv.t0, f32), d[miss], np.full((int(miss.sum()), 1), lv.t1, f32)], 1)
+        hits = osc.trace(rays, brute=True)
+        assert np.all(hits[:, 3].view(np.uint32) == 0xFFFFFFFF), f"level {i}: a ray that misses the padded box hits a triangle"
+    assert max(shares) > 0.2      # random directions of valid probes: a good part leaves the scene at once
